@@ -1,0 +1,162 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python oracle/make_golden.py            # writes tests/golden/
+
+Every fixture stores inputs, outputs and the (name, shape) list the synthetic weights were
+generated from (oracle/synth.py) -- never the weights themselves.  The reference has no tests
+or golden vectors of its own, so these outputs of the reference code are what
+pins the oracle.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import ref_shims, synth  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _load_synth(module, seed):
+    shapes = synth.module_shapes(module)
+    module.load_state_dict(synth.synth_state_dict(shapes, seed), strict=True)
+    return json.dumps([[n, list(s)] for n, s in shapes])
+
+
+def gen_schedule():
+    ref_shims.install()
+    from lvdm.models import utils_diffusion as U
+    from lvdm.models.ddpm3d import DDPM
+    from lvdm.models.samplers.ddim import DDIMSampler
+    out = {}
+    for m, S in (("uniform_trailing", 50), ("uniform_trailing", 10), ("uniform_trailing", 3),
+                 ("uniform_trailing", 1), ("uniform", 50), ("quad", 20)):
+        out[f"ts_{m}_{S}"] = U.make_ddim_timesteps(m, S, 1000, verbose=False)
+    out["temb_999_320"] = U.timestep_embedding(torch.tensor([999, 499, 19, 0]), 320).numpy()
+    out["temb_10_64"] = U.timestep_embedding(torch.tensor([10]), 64).numpy()
+    for base in (0.3, 0.7):
+        model = _stub_model(base)
+        out[f"alphas_cumprod"] = model.alphas_cumprod.numpy()
+        out[f"scale_arr_{base}"] = model.scale_arr.numpy()
+        for S, eta in ((50, 1.0), (10, 1.0), (50, 0.0)):
+            smp = _cpu_sampler(model)
+            smp.make_schedule(S, "uniform_trailing", eta, verbose=False)
+            rows = []
+            for index in range(S):
+                vals = [torch.full((1,), smp.ddim_alphas[index]), torch.full((1,), smp.ddim_alphas_prev[index]),
+                        torch.full((1,), smp.ddim_sigmas[index]), torch.full((1,), smp.ddim_sqrt_one_minus_alphas[index]),
+                        torch.full((1,), smp.ddim_scale_arr[index]), torch.full((1,), smp.ddim_scale_arr_prev[index])]
+                rows.append([v.to(torch.float32).item() for v in vals])
+            out[f"step_scalars_b{base}_S{S}_eta{eta}"] = np.asarray(rows, dtype=np.float32)
+    np.savez_compressed(os.path.join(OUT, "schedule_kat.npz"), **out)
+
+
+def _stub_model(base_scale):
+    """A bare nn.Module given the reference's own schedule via DDPM.register_schedule (ddpm3d.py:123-186)
+    and the scale_arr formula of LatentDiffusion.__init__ (ddpm3d.py:522-527)."""
+    ref_shims.install()
+    from lvdm.models.ddpm3d import DDPM
+
+    class Stub(torch.nn.Module):
+        pass
+
+    m = Stub()
+    m.rescale_betas_zero_snr = True
+    m.parameterization = "v"
+    m.v_posterior = 0.0
+    DDPM.register_schedule(m, beta_schedule="linear", timesteps=1000, linear_start=0.00085, linear_end=0.012)
+    m.use_dynamic_rescale = True
+    m.register_buffer("scale_arr", torch.tensor(np.concatenate((np.linspace(1.0, base_scale, 400), np.full(1000, base_scale))), dtype=torch.float32))
+    m.predict_start_from_z_and_v = lambda x, t, v: DDPM.predict_start_from_z_and_v(m, x, t, v)
+    m.predict_eps_from_z_and_v = lambda x, t, v: DDPM.predict_eps_from_z_and_v(m, x, t, v)
+    m.device = torch.device("cpu")
+    return m
+
+
+def _cpu_sampler(model):
+    from lvdm.models.samplers.ddim import DDIMSampler
+    smp = DDIMSampler(model)
+    smp.register_buffer = lambda name, attr: setattr(smp, name, attr)     # ddim.py:18-22 hard-codes "cuda"
+    return smp
+
+
+def toy_denoiser(x, t, c):
+    """Cheap deterministic stand-in for apply_model used by the sampler goldens (both sides call it)."""
+    return torch.tanh(0.7 * x * c["k"] + 0.05 * torch.sin(t.float())[:, None, None, None, None]) + 0.1 * c["b"]
+
+
+def gen_ddim():
+    ref_shims.install()
+    import lvdm.models.samplers.ddim as ddim_mod
+    out = {}
+    for tag, S, base in (("S5", 5, 0.3), ("S50", 50, 0.7)):
+        model = _stub_model(base)
+        model.apply_model = lambda x, t, c, **kw: toy_denoiser(x, t, c)
+        g = torch.Generator().manual_seed(11)
+        shape = (1, 4, 3, 4, 6)
+        x_T = torch.randn(shape, generator=g)
+        noises = [torch.randn(shape, generator=g) for _ in range(S)]
+        cond = {"b": torch.randn(shape, generator=g), "k": torch.tensor([1.3])}
+        uncond = {"b": torch.randn(shape, generator=g), "k": torch.tensor([0.4])}
+        it = iter(noises)
+        ddim_mod.noise_like = lambda shape_, device, repeat=False: next(it)
+        smp = _cpu_sampler(model)
+        samples, inter = smp.sample(S=S, batch_size=1, shape=shape[1:], conditioning=cond, eta=1.0, verbose=False,
+                                    x_T=x_T, unconditional_guidance_scale=7.5, unconditional_conditioning=uncond,
+                                    timestep_spacing="uniform_trailing", guidance_rescale=0.7)
+        out[f"{tag}_x_T"] = x_T.numpy(); out[f"{tag}_noises"] = torch.stack(noises).numpy()
+        out[f"{tag}_cond_b"] = cond["b"].numpy(); out[f"{tag}_uncond_b"] = uncond["b"].numpy()
+        out[f"{tag}_samples"] = samples.numpy()
+        out[f"{tag}_n_inter"] = np.asarray(len(inter["x_inter"]))
+        out[f"{tag}_pred_x0_last"] = inter["pred_x0"][-1].numpy()
+    np.savez_compressed(os.path.join(OUT, "ddim_small.npz"), **out)
+
+
+def gen_unet():
+    cases = {
+        # name: (unet kwargs overrides, T, H, W)
+        "mc64_T4": (dict(model_channels=64), 4, 8, 16),
+        "mc64_T16": (dict(model_channels=64), 16, 8, 8),        # 77+16*T == 333 -> per-frame image-token branch
+        "mc128_T3": (dict(model_channels=128), 3, 8, 8),
+    }
+    for name, (over, T, H, W) in cases.items():
+        m = ref_shims.build_unet(**over)
+        shapes = _load_synth(m, seed=3)
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(1, 8, T, H, W, generator=g)
+        ctx = torch.randn(1, 333, 1024, generator=g)
+        t = torch.tensor([499])
+        fs = torch.tensor([10])
+        with torch.no_grad():
+            y = m(x, t, context=ctx, fs=fs)
+        np.savez_compressed(os.path.join(OUT, f"unet_{name}.npz"), shapes=shapes, kwargs=json.dumps(over),
+                            x=x.numpy(), ctx=ctx.numpy(), t=t.numpy(), fs=fs.numpy(), y=y.numpy())
+        print(name, "out std", float(y.std()), "absmax", float(y.abs().max()))
+
+
+def gen_vae():
+    dec, pq = ref_shims.build_decoder(ch=32)
+    shapes_d = _load_synth(dec, seed=4)
+    pq.load_state_dict(synth.synth_state_dict(synth.module_shapes(pq), 4))
+    g = torch.Generator().manual_seed(6)
+    z = torch.randn(2, 4, 8, 12, generator=g)
+    with torch.no_grad():
+        y = dec(pq(z))
+    np.savez_compressed(os.path.join(OUT, "vae_ch32.npz"), shapes=shapes_d, z=z.numpy(), y=y.numpy())
+    print("vae out std", float(y.std()))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["schedule", "ddim", "unet", "vae"]
+    with torch.no_grad():
+        for w in which:
+            globals()["gen_" + w]()
+    print("golden fixtures written to", OUT)
