@@ -1,0 +1,125 @@
+/* vc_b200.h -- C ABI of libvc_b200.so: the sm_100a kernels behind ViewCrafter's DDIM-denoise hot path.
+ *
+ * Boundary contract: the reference has no FFI of its own on this path -- its "plugin API" is the
+ * Python class surface (DDIMSampler.sample / UNetModel.forward / AutoencoderKL.decode).  The Python mirror of
+ * those classes lives in viewcrafter_b200/{ddim,unet,autoencoder}.py and binds THIS library with ctypes
+ * (viewcrafter_b200/_lib.py); a maintainer of the reference would add the same ctypes stub.
+ *
+ * Conventions: every entry point returns 0 on success, non-zero on failure (vc_last_error() holds the text);
+ * all pointers are DEVICE pointers borrowed from the caller (torch storage) unless stated otherwise; `stream`
+ * is a cudaStream_t passed as void*; activations are channels-last fp16 ("rows x channels", row = pixel/token);
+ * parameters that the reference keeps in fp32 (norm scales, biases) stay fp32.  No call synchronises the device.
+ *
+ * Each declaration cites the reference code it replaces (paths relative to the upstream repo root).
+ */
+#ifndef VC_B200_H
+#define VC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VC_B200_ABI_VERSION 1
+
+int vc_abi_version(void);
+const char* vc_last_error(void);
+/* number of kernel launches issued by this library since the last vc_reset_launch_count() (bench "gpu_launches") */
+long long vc_launch_count(void);
+void vc_reset_launch_count(void);
+
+/* ---- tensor-core tap-GEMM: every nn.Linear / nn.Conv2d(3x3,1x1) / nn.Conv3d(3,1,1) on the path -------------
+ * replaces: torch conv2d/conv3d/linear calls in lvdm/modules/networks/openaimodel3d.py:154,179,191,255-266,
+ *           lvdm/modules/attention.py:52-55,71-72,418-422,435-439, lvdm/modules/networks/ae_modules.py:157-188
+ * out[row, n] = sum_tap sum_k A[row shifted by tap, k] * w[tap*N + n, k]  (+bias) (GEGLU) (+res)
+ */
+typedef struct vc_gemm_desc {
+  const void* a;   int32_t lda;      /* fp16 A, logical (K, X, Y, Z), row pitch lda elements            */
+  const void* a2;  int32_t lda2;     /* optional second K-slab (channel concat), NULL if unused          */
+  int32_t X, Y, Z;                   /* spatial extents; plain GEMM: X = M rows, Y = Z = 1               */
+  int32_t bx, by;                    /* 128-row tile = bx * by pixels (by > 1 requires bx == X)          */
+  int32_t K, K1;                     /* reduction per tap; K1 = channels served by `a` (== K if no a2)   */
+  const void* w;                     /* fp16 weights [num_taps*N, K], K contiguous                       */
+  int32_t N;
+  int32_t num_taps;                  /* 1 (linear), 3 (temporal conv), 9 (3x3 conv)                      */
+  int32_t tap_dx[9], tap_dy[9];      /* per-tap shift of the tile origin along X / Y                     */
+  void* out;       void* out_f32;    /* fp16 output (or fp32 if out_f32 != NULL), row pitch ldo          */
+  int32_t ldo;
+  const float* bias; int32_t bias_z_div;   /* bias row = z / bias_z_div (0: single row)                  */
+  const void* res; int32_t ldr;      /* optional fp16 residual added in the epilogue                     */
+  int32_t geglu;                     /* 1: x*gelu(gate) epilogue, weights pre-interleaved per N tile     */
+} vc_gemm_desc;
+int vc_gemm_tap(const vc_gemm_desc* d, void* stream);
+/* N-tile width the kernel will use for (N, geglu): needed to interleave GEGLU weights on the host */
+int vc_gemm_tile_n(int32_t N, int32_t geglu);
+
+/* ---- fused attention, head_dim 64 ---------------------------------------------------------------------------
+ * replaces: CrossAttention.forward / efficient_forward, lvdm/modules/attention.py:81-144 / 146-209
+ *           (einsum-softmax-einsum or xformers.ops.memory_efficient_attention)
+ */
+typedef struct vc_attn_desc {
+  const void* q; int32_t ldq;        /* [B, Nq, heads, 64] fp16, row pitch ldq                           */
+  const void* k; int32_t ldk;        /* [Bk, Nk, heads, 64]                                              */
+  const void* v; int32_t ldv;
+  void* out;     int32_t ldo;        /* [B, Nq, heads*64]                                                */
+  int32_t B, heads, Nq, Nk;
+  int64_t kv_batch_stride;           /* elements between K/V batches; 0 = one K/V shared by all B        */
+  float scale;                       /* dim_head^-0.5                                                     */
+  int32_t accumulate;                /* out += result (image branch, attention.py:128-142)               */
+} vc_attn_desc;
+int vc_flash_attn_d64(const vc_attn_desc* d, void* stream);
+
+/* temporal self-attention over T <= 32 frames per spatial site (TemporalTransformer, attention.py:365-412;
+ * always the naive path in the reference, attention.py:66).  q/k/v rows at (t*sites + site), pitch ld. */
+int vc_temporal_attn(const void* q, const void* k, const void* v, int32_t ld, void* out, int32_t ldo, int32_t T,
+                     int64_t sites, int32_t heads, float scale, void* stream);
+
+/* ---- normalisation --------------------------------------------------------------------------------------------
+ * GroupNorm(32)+optional SiLU on channels-last fp16; x = concat(x1[C1], x2[C2]) along channels (x2 may be NULL).
+ * replaces: GroupNormSpecific lvdm/basics.py:76-87, nn.GroupNorm in attention.py:265,331, openaimodel3d.py:256-265
+ *           (5-D statistics: pass samples = B, rows_per_sample = T*H*W), ae_modules.py:15-16; SiLU openaimodel3d.py:152
+ */
+size_t vc_groupnorm_ws_bytes(int32_t samples);
+int vc_groupnorm_nhwc(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t samples, int64_t rows_per_sample,
+                      const float* gamma, const float* beta, float eps, int32_t silu, void* out, void* ws, size_t ws_bytes,
+                      void* stream);
+/* nn.LayerNorm over the last dim (attention.py:233-235), fp16 in/out, fp32 statistics */
+int vc_layernorm(const void* x, int64_t rows, int32_t C, const float* gamma, const float* beta, float eps, void* out,
+                 void* stream);
+
+/* ---- data movement ----------------------------------------------------------------------------------------------- */
+int vc_upsample2x_nhwc(const void* x, void* out, int32_t N, int32_t H, int32_t W, int32_t C, void* stream); /* F.interpolate nearest x2 */
+int vc_im2col3x3_s2(const void* x, void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t pad_lo, int32_t Ho, int32_t Wo,
+                    void* stream);                                                                            /* Downsample conv, openaimodel3d.py:51-77 */
+int vc_ncthw_f32_to_rows_f16(const float* x, void* out, int32_t B, int32_t C, int32_t T, int64_t HW, int32_t c_off, int32_t ldo,
+                             void* stream);                                                                   /* 'b c t h w -> (b t) h w c' + hybrid concat ddpm3d.py:1437-1443 */
+int vc_rows_f32_to_ncthw(const float* x, int32_t ldx, float* out, int32_t B, int32_t C, int32_t T, int64_t HW, void* stream);
+int vc_rows_f16_to_nchw_f32(const void* x, int32_t ldx, float* out, int32_t N, int32_t C, int64_t HW, void* stream);
+int vc_cast_f32_to_f16(const float* x, void* out, int64_t n, void* stream);
+int vc_add_f16(const void* a, const void* b, void* out, int64_t n, void* stream);
+
+/* ---- timestep / fps embedding (fp32, tiny) -------------------------------------------------------------------------
+ * replaces: timestep_embedding utils_diffusion.py:8-28; time_embed / fps_embedding / emb_layers openaimodel3d.py:370-382,164-170 */
+int vc_timestep_embedding(const int64_t* t, int32_t n, int32_t dim, float* out, void* stream);
+int vc_small_linear_f32(const float* x, int32_t rows, int32_t K, const float* W, const float* bias, int32_t N, int32_t silu_in,
+                        float* out, const float* add, void* stream);
+
+/* ---- fused DDIM update --------------------------------------------------------------------------------------------
+ * replaces: DDIMSampler.p_sample_ddim after the two apply_model calls, lvdm/models/samplers/ddim.py:228-281,
+ *           rescale_noise_cfg utils_diffusion.py:147-158, predict_{eps,start}_from_z_and_v ddpm3d.py:239-251 */
+typedef struct vc_ddim_scalars {
+  float cfg_scale, guidance_rescale;
+  float sqrt_ac_t, sqrt_1mac_t;
+  float a_prev, sigma_t;
+  float scale_t, prev_scale_t;
+  int32_t use_cfg;
+} vc_ddim_scalars;
+int vc_ddim_update(const float* x, const float* v_cond, const float* v_uncond, const float* noise, float* x_prev, float* pred_x0,
+                   int64_t n, const vc_ddim_scalars* s, void* ws32bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VC_B200_H */

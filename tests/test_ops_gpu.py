@@ -1,0 +1,280 @@
+"""Op-level parity of the sm_100a kernels (called through the C ABI) against plain PyTorch fp32 references.
+
+Tolerances: inputs/outputs are fp16 with fp32 accumulation, so the bound is a few fp16 ulps of the output
+magnitude: |err| <= atol + rtol*|ref| with rtol 4e-3 (fp16 eps = 9.8e-4) unless stated.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from viewcrafter_b200 import ops as _ops
+    return _ops
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+def close(out, ref, atol, rtol=4e-3, what=""):
+    out, ref = out.float(), ref.float()
+    err = (out - ref).abs()
+    bound = atol + rtol * ref.abs()
+    bad = (err > bound)
+    assert not bool(bad.any()), f"{what}: max err {float(err.max()):.4g} (ref absmax {float(ref.abs().max()):.4g}), {int(bad.sum())} / {bad.numel()} outside tolerance"
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,K,N", [(300, 320, 320), (128, 64, 512), (1000, 1280, 1280), (257, 1024, 640), (77, 1024, 320),
+                                   (4096, 512, 4096), (130, 320, 64), (513, 2560, 1280)])
+def test_linear(ops, M, K, N):
+    x, w = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    b = rnd(N, seed=3, dtype=torch.float32)
+    r = rnd(M, N, seed=4)
+    ref = x.float() @ w.float().t()
+    close(ops.linear(x, w), ref, 2e-3, what="plain")
+    close(ops.linear(x, w, bias=b, res=r), ref + b + r.float(), 4e-3, what="bias+res")
+    o32 = ops.linear(x, w, bias=b, out_f32=True)
+    assert o32.dtype == torch.float32
+    close(o32, ref + b, 1e-3, rtol=1e-3, what="f32 out")
+
+
+def test_linear_inplace_residual_and_views(ops):
+    M, C = 640, 320
+    x = rnd(M, 3 * C, seed=5)
+    w = rnd(C, C, seed=6, scale=C ** -0.5)
+    h = rnd(M, C, seed=7)
+    ref = x[:, C:2 * C].float() @ w.float().t() + h.float()
+    ops.linear(x[:, C:2 * C], w, res=h, out=h)          # strided A view, in-place residual
+    close(h, ref, 4e-3, what="inplace")
+
+
+def test_linear_two_sources(ops):
+    M, K1, K2, N = 384, 640, 320, 320
+    a, b = rnd(M, K1, seed=8), rnd(M, K2, seed=9)
+    w = rnd(N, K1 + K2, seed=10, scale=(K1 + K2) ** -0.5)
+    ref = torch.cat([a, b], 1).float() @ w.float().t()
+    close(ops.linear(a, w, x2=b), ref, 2e-3, what="concat-K")
+
+
+@pytest.mark.parametrize("C", [320, 512, 1280])
+def test_geglu(ops, C):
+    M = 300
+    x = rnd(M, C, seed=11)
+    w = rnd(8 * C, C, seed=12, scale=C ** -0.5)
+    b = rnd(8 * C, seed=13, dtype=torch.float32, scale=0.1)
+    h = x.float() @ w.float().t() + b
+    val, gate = h.chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    wp, bp = ops.pack_geglu(w, b)
+    close(ops.linear(x, wp, bias=bp, geglu=True), ref, 4e-3, what="geglu")
+
+
+def test_linear_ragged_n(ops):
+    M, K, N = 200, 320, 4
+    x, w = rnd(M, K, seed=14), rnd(N, K, seed=15, scale=K ** -0.5)
+    b = rnd(N, seed=16, dtype=torch.float32)
+    out = ops.linear(x, w, bias=b, out_f32=True)
+    close(out, x.float() @ w.float().t() + b, 1e-3, what="N=4")
+
+
+# ---------------------------------------------------------------------------------------------- convs
+def _nhwc_rows(x_nchw):
+    n, c, h, w = x_nchw.shape
+    return x_nchw.permute(0, 2, 3, 1).reshape(n * h * w, c).contiguous()
+
+
+@pytest.mark.parametrize("frames,H,W,Ci,Co", [(2, 9, 16, 64, 128), (3, 18, 32, 320, 320), (1, 8, 128, 128, 64), (2, 5, 8, 64, 64),
+                                             (1, 6, 256, 64, 32), (2, 36, 64, 320, 640), (1, 8, 16, 8, 320), (2, 8, 16, 320, 4)])
+def test_conv3x3(ops, frames, H, W, Ci, Co):
+    x = rnd(frames, Ci, H, W, seed=20)
+    w = rnd(Co, Ci, 3, 3, seed=21, scale=(9 * Ci) ** -0.5)
+    b = rnd(Co, seed=22, dtype=torch.float32)
+    ref = _nhwc_rows(F.conv2d(x.float(), w.float(), b, padding=1))
+    out = ops.conv3x3(_nhwc_rows(x), frames, H, W, ops.pack_conv3x3(w), bias=b, out_f32=(Co < 8))
+    close(out, ref, 3e-3, what="conv3x3")
+
+
+def test_conv3x3_concat_bias_per_batch_residual(ops):
+    frames, H, W, C1, C2, Co = 4, 9, 16, 128, 64, 128
+    a, s = rnd(frames, C1, H, W, seed=23), rnd(frames, C2, H, W, seed=24)
+    w = rnd(Co, C1 + C2, 3, 3, seed=25, scale=(9 * (C1 + C2)) ** -0.5)
+    b = rnd(2, Co, seed=26, dtype=torch.float32)           # one bias row per batch of 2 frames
+    r = rnd(frames * H * W, Co, seed=27)
+    ref = F.conv2d(torch.cat([a, s], 1).float(), w.float(), None, padding=1) + b.repeat_interleave(2, 0)[:, :, None, None]
+    ref = _nhwc_rows(ref) + r.float()
+    out = ops.conv3x3(_nhwc_rows(a), frames, H, W, ops.pack_conv3x3(w), bias=b, bias_z_div=2, res=r, x2=_nhwc_rows(s))
+    close(out, ref, 4e-3, what="conv concat")
+
+
+@pytest.mark.parametrize("B,T,HW,C", [(1, 5, 144, 320), (2, 4, 64, 128), (1, 25, 40, 64), (1, 1, 256, 64)])
+def test_conv_temporal(ops, B, T, HW, C):
+    x5 = rnd(B, C, T, HW, 1, seed=30)
+    w = rnd(C, C, 3, 1, 1, seed=31, scale=(3 * C) ** -0.5)
+    b = rnd(C, seed=32, dtype=torch.float32)
+    ref5 = F.conv3d(x5.float(), w.float(), b, padding=(1, 0, 0))
+    rows = lambda t5: t5.permute(0, 2, 3, 4, 1).reshape(B * T * HW, C).contiguous()
+    r = rnd(B * T * HW, C, seed=33)
+    out = ops.conv_temporal(rows(x5), B, T, HW, ops.pack_conv_temporal(w), bias=b, res=r)
+    close(out, rows(ref5) + r.float(), 4e-3, what="conv_temporal")
+
+
+def test_downsample_conv_via_im2col(ops):
+    N, H, W, C = 3, 18, 32, 64
+    x = rnd(N, C, H, W, seed=34)
+    w = rnd(C, C, 3, 3, seed=35, scale=(9 * C) ** -0.5)
+    b = rnd(C, seed=36, dtype=torch.float32)
+    ref = _nhwc_rows(F.conv2d(x.float(), w.float(), b, stride=2, padding=1))
+    cols, Ho, Wo = ops.im2col_s2(_nhwc_rows(x), N, H, W)
+    wk = w.permute(0, 2, 3, 1).reshape(C, 9 * C).to(torch.float16).contiguous()
+    out = ops.linear(cols, wk, bias=b)
+    assert (Ho, Wo) == (9, 16)
+    close(out, ref, 3e-3, what="stride-2 conv")
+
+
+def test_upsample2x(ops):
+    N, H, W, C = 2, 5, 7, 64
+    x = rnd(N, C, H, W, seed=37)
+    ref = _nhwc_rows(F.interpolate(x.float(), scale_factor=2, mode="nearest"))
+    assert torch.equal(ops.upsample2x(_nhwc_rows(x), N, H, W).float(), ref)
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, heads, scale):
+    B, Nq, _ = q.shape
+    f = lambda t: t.float().reshape(t.shape[0], t.shape[1], heads, 64).permute(0, 2, 1, 3)
+    s = torch.einsum("bhid,bhjd->bhij", f(q), f(k)) * scale
+    o = torch.einsum("bhij,bhjd->bhid", s.softmax(-1), f(v))
+    return o.permute(0, 2, 1, 3).reshape(B, Nq, heads * 64)
+
+
+@pytest.mark.parametrize("B,heads,N", [(2, 5, 576), (1, 2, 128), (3, 1, 144), (1, 5, 2304), (2, 10, 1000)])
+def test_flash_self_attention(ops, B, heads, N):
+    C = heads * 64
+    qkv = rnd(B * N, 3 * C, seed=40)
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    ref = _attn_ref(q.reshape(B, N, C), k.reshape(B, N, C), v.reshape(B, N, C), heads, 0.125)
+    out = ops.flash_attn(q, k, v, B, N, N, heads)
+    close(out.reshape(B, N, C), ref, 2e-3, rtol=1e-2, what="self-attn")
+
+
+@pytest.mark.parametrize("Nk", [77, 256, 16, 333])
+def test_flash_cross_attention_shared_kv_and_accumulate(ops, Nk):
+    B, heads, Nq = 3, 5, 200
+    C = heads * 64
+    q = rnd(B * Nq, C, seed=41)
+    kv = rnd(Nk, 2 * C, seed=42)
+    k, v = kv[:, :C], kv[:, C:]
+    ref = _attn_ref(q.reshape(B, Nq, C), k.reshape(1, Nk, C).expand(B, Nk, C), v.reshape(1, Nk, C).expand(B, Nk, C), heads, 0.125)
+    out = ops.flash_attn(q, k, v, B, Nq, Nk, heads, kv_shared=True)
+    close(out.reshape(B, Nq, C), ref, 2e-3, rtol=1e-2, what="cross-attn")
+    out2 = ops.flash_attn(q, k, v, B, Nq, Nk, heads, kv_shared=True, out=out.clone(), accumulate=True)
+    close(out2.reshape(B, Nq, C), 2 * ref, 4e-3, rtol=1e-2, what="cross-attn accumulate")
+
+
+def test_flash_cross_attention_per_batch_kv(ops):
+    B, heads, Nq, Nk = 4, 2, 130, 93
+    C = heads * 64
+    q, k, v = rnd(B * Nq, C, seed=43), rnd(B * Nk, C, seed=44), rnd(B * Nk, C, seed=45)
+    ref = _attn_ref(q.reshape(B, Nq, C), k.reshape(B, Nk, C), v.reshape(B, Nk, C), heads, 0.125)
+    close(ops.flash_attn(q, k, v, B, Nq, Nk, heads).reshape(B, Nq, C), ref, 2e-3, rtol=1e-2, what="per-batch kv")
+
+
+@pytest.mark.parametrize("T,sites,heads", [(25, 144, 5), (16, 100, 8), (1, 7, 1), (32, 33, 2)])
+def test_temporal_attention(ops, T, sites, heads):
+    C = heads * 64
+    qkv = rnd(T * sites, 3 * C, seed=46)
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    tok = lambda t: t.reshape(T, sites, C).permute(1, 0, 2)       # (site, t, c)
+    ref = _attn_ref(tok(q), tok(k), tok(v), heads, 0.125).permute(1, 0, 2).reshape(T * sites, C)
+    close(ops.temporal_attn(q, k, v, T, sites, heads), ref, 2e-3, rtol=5e-3, what="temporal attn")
+
+
+# ---------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("samples,rows,C,eps,silu", [(5, 144, 320, 1e-5, True), (1, 5 * 144, 640, 1e-5, True), (2, 1000, 128, 1e-6, False),
+                                                    (3, 64, 2560, 1e-5, True), (25, 64, 64, 1e-6, False)])
+def test_groupnorm(ops, samples, rows, C, eps, silu):
+    x = rnd(samples * rows, C, seed=50, scale=2.0) + 0.5
+    g, b = rnd(C, seed=51, dtype=torch.float32), rnd(C, seed=52, dtype=torch.float32)
+    xr = x.float().reshape(samples, rows, C).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, g, b, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(samples * rows, C)
+    close(ops.groupnorm(x, samples, g, b, eps, silu), ref, 3e-3, what="groupnorm")
+
+
+def test_groupnorm_concat(ops):
+    samples, rows, C1, C2 = 3, 200, 640, 320
+    a, s = rnd(samples * rows, C1, seed=53), rnd(samples * rows, C2, seed=54, scale=3.0)
+    C = C1 + C2
+    g, b = rnd(C, seed=55, dtype=torch.float32), rnd(C, seed=56, dtype=torch.float32)
+    xr = torch.cat([a, s], 1).float().reshape(samples, rows, C).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(xr, 32, g, b, 1e-5)).permute(0, 2, 1).reshape(samples * rows, C)
+    close(ops.groupnorm(a, samples, g, b, 1e-5, True, x2=s), ref, 3e-3, what="groupnorm concat")
+
+
+@pytest.mark.parametrize("rows,C", [(1000, 320), (77, 512), (300, 1280), (9, 640), (5, 64)])
+def test_layernorm(ops, rows, C):
+    x = rnd(rows, C, seed=57, scale=2.0) + 1.0
+    g, b = rnd(C, seed=58, dtype=torch.float32), rnd(C, seed=59, dtype=torch.float32)
+    close(ops.layernorm(x, g, b), F.layer_norm(x.float(), (C,), g, b, 1e-5), 3e-3, what="layernorm")
+
+
+# ---------------------------------------------------------------------------------------------- boundary / embedding / ddim
+def test_layout_roundtrip(ops):
+    B, C, T, H, W = 2, 4, 3, 5, 8
+    x = rnd(B, C, T, H, W, seed=60, dtype=torch.float32)
+    rows = torch.zeros(B * T * H * W, 8, device="cuda", dtype=torch.float16)
+    ops.ncthw_to_rows(x, rows, 0)
+    ops.ncthw_to_rows(x * 2, rows, 4)
+    ref = x.permute(0, 2, 3, 4, 1).reshape(-1, C)
+    assert torch.equal(rows[:, :4].float(), ref.half().float()) and torch.equal(rows[:, 4:].float(), (2 * ref).half().float())
+    back = ops.rows_to_ncthw(ref.contiguous(), B, C, T, H, W)
+    assert torch.equal(back, x)
+    img = ops.rows_f16_to_nchw(rows, B * T, 8, H, W)
+    assert torch.equal(img, rows.float().reshape(B * T, H, W, 8).permute(0, 3, 1, 2))
+
+
+def test_embedding_mlp(ops):
+    t = torch.tensor([999, 19], device="cuda", dtype=torch.int64)
+    e = ops.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+    args = t.cpu()[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert float((e.cpu() - ref).abs().max()) < 2e-4          # fp32 exp/sincos at |arg| <= 999
+    w, b = rnd(1280, 320, seed=61, dtype=torch.float32, scale=0.05), rnd(1280, seed=62, dtype=torch.float32)
+    add = rnd(2, 1280, seed=63, dtype=torch.float32)
+    out = ops.small_linear(e, w, b, silu_in=True, add=add)
+    close(out, F.linear(F.silu(e), w, b) + add, 1e-4, rtol=1e-4, what="small_linear")
+
+
+@pytest.mark.parametrize("cfg,gr", [(7.5, 0.7), (7.5, 0.0), (1.0, 0.0)])
+def test_ddim_update_matches_oracle(ops, cfg, gr):
+    from oracle import lvdm_oracle as O
+    sched = O.model_schedule(base_scale=0.3)
+    tab = O.ddim_tables(sched, 50, "uniform_trailing", 1.0)
+    shape = (1, 4, 5, 8, 16)
+    g = torch.Generator().manual_seed(64)
+    x, vc_, vu, nz = (torch.randn(shape, generator=g) for _ in range(4))
+    for index in (49, 20, 0):
+        step = int(tab["timesteps"][index])
+        sc = O.step_scalars(tab, index)
+        sa, s1 = sched["sqrt_alphas_cumprod"][step].item(), sched["sqrt_one_minus_alphas_cumprod"][step].item()
+        ref_prev, ref_x0 = O.ddim_update(x, vc_, vu if cfg != 1.0 else None, sc, sa, s1, nz, cfg, gr)
+        d = dict(cfg_scale=cfg, guidance_rescale=gr, sqrt_ac_t=sa, sqrt_1mac_t=s1, a_prev=float(sc[1]), sigma_t=float(sc[2]),
+                 scale_t=float(sc[4]), prev_scale_t=float(sc[5]))
+        xp, x0 = ops.ddim_update(x.cuda(), vc_.cuda(), vu.cuda(), nz.cuda(), d)
+        close(xp.cpu(), ref_prev, 2e-5, rtol=2e-5, what=f"x_prev index {index}")
+        close(x0.cpu(), ref_x0, 2e-5, rtol=2e-5, what=f"pred_x0 index {index}")

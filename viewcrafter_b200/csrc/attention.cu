@@ -1,0 +1,254 @@
+// FlashAttention-style fused softmax(Q K^T * scale) V for head_dim 64 on tcgen05 (sm_100a).
+//
+// Used for the spatial self-attention (Nq = Nk = H*W up to 9216) and the text / image cross-attention
+// (Nk = 77 / 256) of lvdm/modules/attention.py:81-144.  One CTA owns 128 query rows of one (batch, head)
+// and streams 128-key tiles:   S = Q K^T  (SS MMA, fp32 in TMEM)  ->  online softmax by 128 threads, one row
+// each (exp2 domain)  ->  P (fp16) written back to TMEM  ->  O += P V  (TS MMA, A from TMEM, V MN-major in
+// smem).  K/V tiles arrive by TMA through a 2-stage mbarrier ring.  Two CTAs are co-resident per SM so one
+// CTA's MUFU-bound softmax overlaps the other's MMAs.
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2..5 = softmax /
+// correction / epilogue (TMEM lane quadrant = warp % 4).
+// TMEM columns: [0,128) S fp32 | [128,192) P fp16x2 | [192,256) O fp32.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vc {
+
+struct AttnParams {
+  CUtensorMap tmap_q, tmap_k, tmap_v;
+  __half* out;
+  int ldo;
+  int Nq, Nk;
+  int kv_shared;       // 1: K/V batch coordinate is always 0
+  float scale_log2;    // scale * log2(e)
+  int accumulate;
+};
+
+static constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64;
+static constexpr int ATT_TILE_BYTES = 128 * 64 * 2;                    // 16 KB
+static constexpr int ATT_SMEM = ATT_TILE_BYTES * 5 + 1024 + 256;       // Q + 2x(K,V) + slack + barriers
+
+__global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + ATT_TILE_BYTES;                                 // stage s: K at s*32K, V at s*32K+16K
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_final = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BM, head = blockIdx.y, b = blockIdx.z;
+  const int bk = p.kv_shared ? 0 : b;
+  const int ntiles = (p.Nk + ATT_BN - 1) / ATT_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_q);
+    tma_prefetch_desc(&p.tmap_k);
+    tma_prefetch_desc(&p.tmap_v);
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_final, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_4d(sQ, &p.tmap_q, q_full, 0, head, q0, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j & 1;
+        if (j >= 2) mbar_wait(&kv_empty[s], ((j >> 1) - 1) & 1);
+        uint8_t* sk = sKV + s * 2 * ATT_TILE_BYTES;
+        mbar_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
+        tma_load_4d(sk, &p.tmap_k, &kv_full[s], 0, head, j * ATT_BN, bk);
+        tma_load_4d(sk + ATT_TILE_BYTES, &p.tmap_v, &kv_full[s], 0, head, j * ATT_BN, bk);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);      // B = V is MN-major
+      mbar_wait(q_full, 0);
+      const uint32_t aQ = smem_u32(sQ);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sKV + s * 2 * ATT_TILE_BYTES);
+        const uint32_t aV = aK + ATT_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_ss(tS, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc_qk, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k)
+          umma_ts(tO, tP + k * 8, umma_desc_sw128(aV + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[s]);
+      }
+      umma_commit(o_final);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      const int valid = min(ATT_BN, p.Nk - j * ATT_BN);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + c * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c * 32 + e < valid) mx = fmaxf(mx, __uint_as_float(v[e]));
+      }
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      const float alpha = exp2f(m - m_new);
+      l *= alpha;
+      // pass 2: probabilities -> P (fp16 pairs) in TMEM
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 2 + cc;
+          uint32_t v[32];
+          tmem_ld32(tS + lane_off + c * 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = (c * 32 + e < valid) ? exp2f(__uint_as_float(v[e]) * p.scale_log2 - m_new) : 0.f;
+            const float p1 = (c * 32 + e + 1 < valid) ? exp2f(__uint_as_float(v[e + 1]) * p.scale_log2 - m_new) : 0.f;
+            l += p0 + p1;
+            pk[cc * 16 + e / 2] = pack_half2(p0, p1);
+          }
+        }
+        tmem_st32(tP + lane_off + half * 32, pk);
+      }
+      // correction: O *= alpha (PV of the previous tile has retired: it was issued before this tile's QK)
+      if (j > 0) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tO + lane_off + c * 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+          tmem_st32(tO + lane_off + c * 32, v);
+        }
+      }
+      m = m_new;
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // epilogue
+    mbar_wait(o_final, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int row = q0 + r;
+    __half* op = p.out + ((long long)b * p.Nq + row) * p.ldo + head * ATT_D;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(tO + lane_off + c * 32, v);
+      tc_wait_ld();
+      if (row < p.Nq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]) * inv;
+          uint4* dst = reinterpret_cast<uint4*>(op + c * 32 + g * 8);
+          if (p.accumulate) {
+            const uint4 u = *dst;
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = __half22float2(h[e]);
+              f[2 * e] += t.x; f[2 * e + 1] += t.y;
+            }
+          }
+          uint4 o;
+          o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
+          o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
+          *dst = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int flash_attn_d64(const AttnDesc& d, cudaStream_t stream) {
+  VC_REQUIRE(d.q && d.k && d.v && d.out, "flash_attn: null pointer");
+  VC_REQUIRE(d.Nq > 0 && d.Nk > 0 && d.B > 0 && d.heads > 0, "flash_attn: empty problem");
+  VC_REQUIRE(d.ldq % 8 == 0 && d.ldk % 8 == 0 && d.ldv % 8 == 0 && d.ldo % 8 == 0, "flash_attn: pitches must be multiples of 8");
+  VC_REQUIRE(d.kv_batch_stride % 8 == 0, "flash_attn: kv batch stride must be a multiple of 8");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  uint32_t box[4] = {64, 1, 128, 1};
+  {
+    uint64_t dims[4] = {64, (uint64_t)d.heads, (uint64_t)d.Nq, (uint64_t)d.B};
+    uint64_t str[3] = {128, (uint64_t)d.ldq * 2, (uint64_t)d.ldq * 2 * d.Nq};
+    int rc = encode_tmap_f16(&p.tmap_q, d.q, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  const int shared = d.kv_batch_stride == 0;
+  {
+    uint64_t dims[4] = {64, (uint64_t)d.heads, (uint64_t)d.Nk, (uint64_t)(shared ? 1 : d.B)};
+    uint64_t strk[3] = {128, (uint64_t)d.ldk * 2, (uint64_t)(shared ? (long long)d.ldk * d.Nk : d.kv_batch_stride) * 2};
+    uint64_t strv[3] = {128, (uint64_t)d.ldv * 2, (uint64_t)(shared ? (long long)d.ldv * d.Nk : d.kv_batch_stride) * 2};
+    int rc = encode_tmap_f16(&p.tmap_k, d.k, 4, dims, strk, box);
+    if (rc) return rc;
+    rc = encode_tmap_f16(&p.tmap_v, d.v, 4, dims, strv, box);
+    if (rc) return rc;
+  }
+  p.out = d.out; p.ldo = d.ldo; p.Nq = d.Nq; p.Nk = d.Nk; p.kv_shared = shared;
+  p.scale_log2 = d.scale * 1.4426950408889634f;
+  p.accumulate = d.accumulate;
+  static bool configured = false;
+  if (!configured) {
+    VC_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    configured = true;
+  }
+  dim3 grid((d.Nq + ATT_BM - 1) / ATT_BM, d.heads, d.B);
+  flash_attn_d64_kernel<<<grid, 192, ATT_SMEM, stream>>>(p);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+}  // namespace vc

@@ -1,0 +1,353 @@
+// Tap-GEMM on tcgen05: D[M,N] = sum_taps A_tap[M,K] * W_tap[N,K]^T  (fp16 in, fp32 accumulate in TMEM).
+//
+// One kernel family covers every tensor-core op on the U-Net / VAE path:
+//   * nn.Linear / 1x1 conv            : 1 tap, A = [M,K] row-major
+//   * 3x3 conv, stride 1, pad 1 (NHWC): 9 taps, A tile = TMA box (64ch, bw, bh, 1 frame) shifted by (dx-1, dy-1);
+//                                       the zero padding is TMA out-of-bounds fill
+//   * Conv3d (3,1,1), pad (1,0,0)     : 3 taps, A rows shifted by +-H*W rows of the [T*H*W, C] matrix (OOB rows = 0)
+// A may come from two tensors split along K (channel concat of skip connections without materialising it).
+// Epilogue (TMEM -> regs): + bias[z/bias_z_div][n], GEGLU (value*gelu(gate)), + residual, fp16 / fp32 store.
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2..5 = epilogue.
+// Two CTAs are co-resident per SM (<=113 KB smem, <=256 TMEM columns each) so one CTA's epilogue overlaps the
+// other's main loop.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vc {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int MAX_TAPS = 9;
+
+struct GemmParams {
+  CUtensorMap tmap_a;
+  CUtensorMap tmap_a2;
+  CUtensorMap tmap_b;
+  int tiles_x, tiles_y, Z;
+  int bx, by;
+  int X, Y;
+  int N, K, K1;          // K1 = channels served by tmap_a (K1 == K when single source)
+  int num_taps;
+  int tap_dx[MAX_TAPS];
+  int tap_dy[MAX_TAPS];
+  int n_tiles;
+  __half* out;
+  float* out_f32;
+  int ldo;
+  const float* bias;
+  int bias_z_div;
+  const __half* res;
+  int ldr;
+  int geglu;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (112 * 1024) / STAGE_BYTES >= 4 ? 4 : (112 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 2) gemm_tap_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tile = blockIdx.x;
+  const int n_tile = tile % p.n_tiles;
+  int m_tile = tile / p.n_tiles;
+  const int tx = m_tile % p.tiles_x;
+  m_tile /= p.tiles_x;
+  const int ty = m_tile % p.tiles_y;
+  const int z = m_tile / p.tiles_y;
+  const int x0 = tx * p.bx, y0 = ty * p.by, n0 = n_tile * BN;
+  const int kblocks = (p.K + BK - 1) / BK;
+  const int iters = p.num_taps * kblocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_a);
+    tma_prefetch_desc(&p.tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tap = 0; tap < p.num_taps; ++tap) {
+        const int cx = x0 + p.tap_dx[tap], cy = y0 + p.tap_dy[tap];
+        const int brow = tap * p.N + n0;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          const int k = kb * BK;
+          if (k < p.K1)
+            tma_load_4d(sa, &p.tmap_a, &full_bar[s], k, cx, cy, z);
+          else
+            tma_load_4d(sa, &p.tmap_a2, &full_bar[s], k - p.K1, cx, cy, z);
+          tma_load_2d(sb, &p.tmap_b, &full_bar[s], k, brow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = umma_desc_sw128(sa + k * 32);
+          const uint64_t db = umma_desc_sw128(sb + k * 32);
+          umma_ss(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);     // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: one accumulator row per thread ----------------
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;
+    const int x = x0 + (r % p.bx), y = y0 + (r / p.bx);
+    const bool row_ok = (x < p.X) && (y < p.Y);
+    const long long orow = ((long long)z * p.Y + y) * p.X + x;
+    const float* bias = p.bias ? p.bias + (long long)(p.bias_z_div > 0 ? z / p.bias_z_div : 0) * p.N : nullptr;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    if (!p.geglu) {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(trow + c * 32, v);
+        tc_wait_ld();
+        const int nb = n0 + c * 32;
+        if (!row_ok || nb >= p.N) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (nb + 32 <= p.N) {
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if (p.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + orow * p.ldr + nb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = rp[j];   // plain load: res may alias out (in-place residual)
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __half22float2(h[e]);
+                f[j * 8 + e * 2] += t.x;
+                f[j * 8 + e * 2 + 1] += t.y;
+              }
+            }
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(p.out + orow * p.ldo + nb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_half2(f[j * 8 + 0], f[j * 8 + 1]);
+              u.y = pack_half2(f[j * 8 + 2], f[j * 8 + 3]);
+              u.z = pack_half2(f[j * 8 + 4], f[j * 8 + 5]);
+              u.w = pack_half2(f[j * 8 + 6], f[j * 8 + 7]);
+              op[j] = u;
+            }
+          }
+        } else {
+          // ragged N tail (e.g. the 320->4 output conv): predicated scalar path, fully unrolled so f[] stays in registers
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nb + j < p.N) {
+              float t = f[j];
+              if (bias) t += bias[nb + j];
+              if (p.res) t += __half2float(p.res[orow * p.ldr + nb + j]);
+              if (p.out_f32) p.out_f32[orow * p.ldo + nb + j] = t;
+              else p.out[orow * p.ldo + nb + j] = __float2half_rn(t);
+            }
+          }
+        }
+      }
+    } else {
+      // GEGLU: tile columns [0,BN/2) are values, [BN/2,BN) the matching gates (weights were interleaved per tile).
+      constexpr int HALF = BN / 2;
+      const int ob = n_tile * HALF;
+#pragma unroll 1
+      for (int c = 0; c < HALF / 32; ++c) {
+        uint32_t a[32], g[32];
+        __syncwarp();
+        tmem_ld32(trow + c * 32, a);
+        tmem_ld32(trow + HALF + c * 32, g);
+        tc_wait_ld();
+        if (!row_ok) continue;
+        const int nv = n0 + c * 32;          // bias index of the value columns inside the permuted weight
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float va = __uint_as_float(a[j]), vg = __uint_as_float(g[j]);
+          if (bias) {
+            va += __ldg(bias + nv + j);
+            vg += __ldg(bias + nv + HALF + j);
+          }
+          f[j] = va * gelu_erf_f(vg);
+        }
+        uint4* op = reinterpret_cast<uint4*>(p.out + orow * p.ldo + ob + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_half2(f[j * 8 + 0], f[j * 8 + 1]);
+          u.y = pack_half2(f[j * 8 + 2], f[j * 8 + 3]);
+          u.z = pack_half2(f[j * 8 + 4], f[j * 8 + 5]);
+          u.w = pack_half2(f[j * 8 + 6], f[j * 8 + 7]);
+          op[j] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    VC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  gemm_tap_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+static int pick_bn(int N, int geglu) {
+  if (geglu) return (N % 256 == 0) ? 256 : 128;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N % 256 == 0) return 256;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0) return 128;
+  if (N % 96 == 0 && N <= 192) return 96;
+  if (N % 64 == 0 && N < 256) return 64;
+  return 128;
+}
+
+int pick_bn_public(int N, int geglu) { return pick_bn(N, geglu); }
+
+int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
+  VC_REQUIRE(d.a && d.w && (d.out || d.out_f32), "gemm_tap: null pointer");
+  VC_REQUIRE(d.num_taps >= 1 && d.num_taps <= MAX_TAPS, "gemm_tap: num_taps=%d out of range", d.num_taps);
+  VC_REQUIRE(d.bx * d.by == BM && d.bx >= 1, "gemm_tap: box %dx%d must cover 128 rows", d.bx, d.by);
+  VC_REQUIRE(d.by == 1 || d.bx == d.X, "gemm_tap: multi-row boxes need bx == X (X=%d bx=%d)", d.X, d.bx);
+  VC_REQUIRE(d.K % 8 == 0 && d.lda % 8 == 0, "gemm_tap: K and lda must be multiples of 8 (TMA 16-byte strides)");
+  VC_REQUIRE(d.out_f32 || d.N < 32 || d.ldo % 8 == 0, "gemm_tap: ldo must be a multiple of 8");
+  VC_REQUIRE(d.K1 == d.K || (d.a2 && d.K1 % BK == 0 && d.K1 < d.K), "gemm_tap: bad K split K1=%d K=%d", d.K1, d.K);
+  VC_REQUIRE(!d.geglu || (d.N % 128 == 0 && !d.res && !d.out_f32), "gemm_tap: GEGLU needs N %% 128 == 0");
+  if ((reinterpret_cast<uintptr_t>(d.a) & 15) || (reinterpret_cast<uintptr_t>(d.w) & 15)) {
+    set_error("gemm_tap: operands must be 16-byte aligned");
+    return VC_ERR_ARG;
+  }
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  // A: (K, X, Y, Z) with row pitch lda
+  {
+    uint64_t dims[4] = {(uint64_t)d.K1, (uint64_t)d.X, (uint64_t)d.Y, (uint64_t)d.Z};
+    uint64_t str[3] = {(uint64_t)d.lda * 2, (uint64_t)d.lda * 2 * d.X, (uint64_t)d.lda * 2 * d.X * d.Y};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)d.bx, (uint32_t)d.by, 1};
+    int rc = encode_tmap_f16(&p.tmap_a, d.a, 4, dims, str, box);
+    if (rc) return rc;
+    if (d.K1 != d.K) {
+      uint64_t dims2[4] = {(uint64_t)(d.K - d.K1), (uint64_t)d.X, (uint64_t)d.Y, (uint64_t)d.Z};
+      uint64_t str2[3] = {(uint64_t)d.lda2 * 2, (uint64_t)d.lda2 * 2 * d.X, (uint64_t)d.lda2 * 2 * d.X * d.Y};
+      rc = encode_tmap_f16(&p.tmap_a2, d.a2, 4, dims2, str2, box);
+      if (rc) return rc;
+    } else {
+      p.tmap_a2 = p.tmap_a;
+    }
+  }
+  const int BN = pick_bn(d.N, d.geglu);
+  {
+    uint64_t dims[2] = {(uint64_t)d.K, (uint64_t)d.num_taps * d.N};
+    uint64_t str[1] = {(uint64_t)d.K * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    int rc = encode_tmap_f16(&p.tmap_b, d.w, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  p.bx = d.bx; p.by = d.by; p.X = d.X; p.Y = d.Y; p.Z = d.Z;
+  p.tiles_x = (d.X + d.bx - 1) / d.bx;
+  p.tiles_y = (d.Y + d.by - 1) / d.by;
+  p.N = d.N; p.K = d.K; p.K1 = d.K1;
+  p.num_taps = d.num_taps;
+  for (int t = 0; t < d.num_taps; ++t) { p.tap_dx[t] = d.tap_dx[t]; p.tap_dy[t] = d.tap_dy[t]; }
+  p.n_tiles = (d.N + BN - 1) / BN;
+  p.out = d.out; p.out_f32 = d.out_f32; p.ldo = d.ldo;
+  p.bias = d.bias; p.bias_z_div = d.bias_z_div;
+  p.res = d.res; p.ldr = d.ldr;
+  p.geglu = d.geglu;
+  const long long grid = (long long)p.tiles_x * p.tiles_y * p.Z * p.n_tiles;
+  VC_REQUIRE(grid > 0 && grid < (1ll << 31), "gemm_tap: grid %lld out of range", grid);
+  switch (BN) {
+    case 32: return launch_gemm<32>(p, (int)grid, stream);
+    case 64: return launch_gemm<64>(p, (int)grid, stream);
+    case 96: return launch_gemm<96>(p, (int)grid, stream);
+    case 128: return launch_gemm<128>(p, (int)grid, stream);
+    case 160: return launch_gemm<160>(p, (int)grid, stream);
+    case 256: return launch_gemm<256>(p, (int)grid, stream);
+  }
+  set_error("gemm_tap: no kernel for BN=%d", BN);
+  return VC_ERR_UNSUPPORTED;
+}
+
+}  // namespace vc

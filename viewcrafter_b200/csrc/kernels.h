@@ -1,0 +1,77 @@
+// Internal C++ launch interface of the sm_100a kernels (the public boundary is include/vc_b200.h).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vc {
+
+struct GemmDesc {
+  // A operand: fp16, logical (K channels, X, Y, Z) with row pitch lda elements; optional second K-slab a2.
+  const __half* a = nullptr; int lda = 0;
+  const __half* a2 = nullptr; int lda2 = 0;
+  int X = 0, Y = 1, Z = 1;        // spatial extents (linear: X = M rows)
+  int bx = 128, by = 1;           // TMA box: bx*by == 128 rows per tile
+  int K = 0, K1 = 0;              // reduction length per tap; K1 = part served by `a`
+  const __half* w = nullptr;      // weights [num_taps*N, K] fp16, K contiguous
+  int N = 0;
+  int num_taps = 1;
+  int tap_dx[9] = {0}; int tap_dy[9] = {0};
+  __half* out = nullptr; float* out_f32 = nullptr; int ldo = 0;
+  const float* bias = nullptr; int bias_z_div = 0;
+  const __half* res = nullptr; int ldr = 0;
+  int geglu = 0;
+};
+int gemm_tap(const GemmDesc& d, cudaStream_t stream);
+
+struct AttnDesc {
+  // q [B, Nq, heads, 64] (row pitch ldq), k/v [Bk, Nk, heads, 64] (pitch ldk/ldv), out [B, Nq, heads*64] (pitch ldo).
+  const __half* q = nullptr; int ldq = 0;
+  const __half* k = nullptr; int ldk = 0;
+  const __half* v = nullptr; int ldv = 0;
+  __half* out = nullptr; int ldo = 0;
+  int B = 1, heads = 1, Nq = 0, Nk = 0;
+  long long kv_batch_stride = 0;   // elements between K/V batches (0 = shared by all B)
+  float scale = 0.125f;
+  int accumulate = 0;              // out += result (second softmax branch of the image cross-attention)
+};
+int flash_attn_d64(const AttnDesc& d, cudaStream_t stream);
+
+// GroupNorm(32) on NHWC fp16; x is the channel concat of (x1: C1 channels) and (x2: C2 channels, may be null).
+// Statistics over `rows_per_sample` rows (pixels, or frames*pixels for the 5-D variant) x C/32 channels.
+int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample,
+                   const float* gamma, const float* beta, float eps, int silu, __half* out, float* partial_ws,
+                   size_t ws_bytes, cudaStream_t stream);
+size_t groupnorm_ws_bytes(int samples);
+
+int layernorm_rows(const __half* x, long long rows, int C, const float* gamma, const float* beta, float eps, __half* out,
+                   cudaStream_t stream);
+
+// Temporal self-attention over T<=32 frames per spatial site; qkv rows are [T*sites, ld] with q|k|v at column offsets.
+int temporal_attn(const __half* q, const __half* k, const __half* v, int ld, __half* out, int ldo, int T, long long sites,
+                  int heads, float scale, cudaStream_t stream);
+
+int upsample2x_nhwc(const __half* x, __half* out, int N, int H, int W, int C, cudaStream_t stream);
+int im2col3x3_s2_nhwc(const __half* x, __half* out, int N, int H, int W, int C, int pad_lo, int Ho, int Wo, cudaStream_t stream);
+int nchw_to_nhwc_f16(const float* x, __half* out, int B, int C, int T, long long HW, int c_off, int ldo, cudaStream_t stream);
+int nhwc_to_ncthw_f32(const float* x, int ldx, float* out, int B, int C, int T, long long HW, cudaStream_t stream);
+int nhwc_to_nchw_f32_from_f16(const __half* x, int ldx, float* out, int N, int C, long long HW, cudaStream_t stream);
+int cast_f32_to_f16(const float* x, __half* out, long long n, cudaStream_t stream);
+int add_rows_f16(const __half* a, const __half* b, __half* out, long long n, cudaStream_t stream);
+
+// emb path: out[r, n] = bias[n] + sum_k act(x[r,k]) * W[n,k]   (fp32, tiny M); act: 0 none, 1 SiLU
+int small_linear_f32(const float* x, int rows, int K, const float* W, const float* bias, int N, int act_in, float* out,
+                     const float* add, cudaStream_t stream);
+int timestep_embedding_f32(const long long* t, int n, int dim, float* out, cudaStream_t stream);
+
+struct DdimStepScalars {
+  float cfg_scale, guidance_rescale;
+  float sqrt_ac_t, sqrt_1mac_t;     // model buffers gathered by timestep t (ddpm3d.py:239-251)
+  float a_prev, sigma_t;            // ddim tables gathered by index
+  float scale_t, prev_scale_t;      // dynamic rescale
+  int use_cfg;
+};
+int ddim_update(const float* x, const float* v_cond, const float* v_uncond, const float* noise, float* x_prev, float* pred_x0,
+                long long n, const DdimStepScalars& s, double* ws, cudaStream_t stream);
+
+}  // namespace vc

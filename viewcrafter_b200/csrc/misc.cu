@@ -1,0 +1,378 @@
+// Small / HBM-bound kernels of the denoise step: temporal self-attention over T<=32 frames,
+// nearest-2x upsample, stride-2 im2col, layout conversions, the timestep/fps embedding MLP pieces
+// and the fused DDIM update.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vc {
+
+// ------------------------------------------------------------------------------------------------
+// Temporal self-attention (attention.py:81-126 with N = T frames, batch = spatial sites):
+// one warp per (site, head); lane t owns query frame t.  q/k/v rows live at row (t*sites + site).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) temporal_attn_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
+                                                            const __half* __restrict__ v, int ld, __half* __restrict__ out, int ldo,
+                                                            int T, long long sites, int heads, float scale) {
+  __shared__ __align__(16) __half ks[4][32][64];
+  __shared__ __align__(16) __half vs[4][32][64];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pairs = sites * heads;
+  for (long long pair = (long long)blockIdx.x * 4 + w; pair < pairs; pair += (long long)gridDim.x * 4) {
+    const long long site = pair / heads;
+    const int head = (int)(pair % heads);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = (lane >> 3) + 4 * i;
+      if (j < T) {
+        const long long off = ((long long)j * sites + site) * ld + head * 64 + (lane & 7) * 8;
+        *reinterpret_cast<uint4*>(&ks[w][j][(lane & 7) * 8]) = *reinterpret_cast<const uint4*>(k + off);
+        *reinterpret_cast<uint4*>(&vs[w][j][(lane & 7) * 8]) = *reinterpret_cast<const uint4*>(v + off);
+      }
+    }
+    __syncwarp();
+    if (lane < T) {
+      float qf[64];
+      const __half* qp = q + ((long long)lane * sites + site) * ld + head * 64;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 u = *reinterpret_cast<const uint4*>(qp + i * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 t = __half22float2(h[e]);
+          qf[i * 8 + 2 * e] = t.x * scale;
+          qf[i * 8 + 2 * e + 1] = t.y * scale;
+        }
+      }
+      float sc[32];
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float s = -INFINITY;
+        if (j < T) {
+          s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 u = *reinterpret_cast<const uint4*>(&ks[w][j][i * 8]);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = __half22float2(h[e]);
+              s += qf[i * 8 + 2 * e] * t.x + qf[i * 8 + 2 * e + 1] * t.y;
+            }
+          }
+        }
+        sc[j] = s;
+        m = fmaxf(m, s);
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float p = (j < T) ? __expf(sc[j] - m) : 0.f;
+        sc[j] = p;
+        l += p;
+      }
+      const float inv = 1.f / l;
+      float o[64];
+#pragma unroll
+      for (int d = 0; d < 64; ++d) o[d] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < T) {
+          const float p = sc[j] * inv;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 u = *reinterpret_cast<const uint4*>(&vs[w][j][i * 8]);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = __half22float2(h[e]);
+              o[i * 8 + 2 * e] += p * t.x;
+              o[i * 8 + 2 * e + 1] += p * t.y;
+            }
+          }
+        }
+      }
+      __half* op = out + ((long long)lane * sites + site) * ldo + head * 64;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 u;
+        u.x = pack_half2(o[i * 8 + 0], o[i * 8 + 1]); u.y = pack_half2(o[i * 8 + 2], o[i * 8 + 3]);
+        u.z = pack_half2(o[i * 8 + 4], o[i * 8 + 5]); u.w = pack_half2(o[i * 8 + 6], o[i * 8 + 7]);
+        *reinterpret_cast<uint4*>(op + i * 8) = u;
+      }
+    }
+  }
+}
+
+int temporal_attn(const __half* q, const __half* k, const __half* v, int ld, __half* out, int ldo, int T, long long sites,
+                  int heads, float scale, cudaStream_t stream) {
+  VC_REQUIRE(q && k && v && out, "temporal_attn: null pointer");
+  VC_REQUIRE(T >= 1 && T <= 32, "temporal_attn: T=%d unsupported (1..32)", T);
+  VC_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "temporal_attn: pitches must be multiples of 8");
+  const long long pairs = sites * heads;
+  long long blocks = (pairs + 3) / 4;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  temporal_attn_kernel<<<(unsigned)blocks, 128, 0, stream>>>(q, k, v, ld, out, ldo, T, sites, heads, scale);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest 2x upsample (F.interpolate scale 2, openaimodel3d.py:101-104 / ae_modules.py:123), NHWC, 16-byte vectors
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long total, int H, int W, int vecs) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    long long p = i / vecs;
+    const int xo = (int)(p % (2 * W)); p /= (2 * W);
+    const int yo = (int)(p % (2 * H));
+    const long long n = p / (2 * H);
+    out[i] = x[((n * H + (yo >> 1)) * W + (xo >> 1)) * vecs + v];
+  }
+}
+int upsample2x_nhwc(const __half* x, __half* out, int N, int H, int W, int C, cudaStream_t stream) {
+  VC_REQUIRE(x && out && C % 8 == 0, "upsample2x: bad args");
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  const int blocks = (int)min((long long)sm_count() * 16, (total + 255) / 256);
+  upsample2x_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), total, H, W, C / 8);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// im2col for the stride-2 3x3 downsample conv (openaimodel3d.py:51-77): out [N*Ho*Wo, 9*C], tap-major then channel.
+__global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long total, int H, int W, int vecs,
+                                 int pad_lo, int Ho, int Wo) {
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    long long p = i / vecs;
+    const int tap = (int)(p % 9); p /= 9;
+    const int xo = (int)(p % Wo); p /= Wo;
+    const int yo = (int)(p % Ho);
+    const long long n = p / Ho;
+    const int yi = 2 * yo - pad_lo + tap / 3, xi = 2 * xo - pad_lo + tap % 3;
+    out[i] = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? x[((n * H + yi) * W + xi) * vecs + v] : zero;
+  }
+}
+int im2col3x3_s2_nhwc(const __half* x, __half* out, int N, int H, int W, int C, int pad_lo, int Ho, int Wo, cudaStream_t stream) {
+  VC_REQUIRE(x && out && C % 8 == 0, "im2col: bad args");
+  const long long total = (long long)N * Ho * Wo * 9 * (C / 8);
+  const int blocks = (int)min((long long)sm_count() * 16, (total + 255) / 256);
+  im2col_s2_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), total, H, W, C / 8,
+                                               pad_lo, Ho, Wo);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversions at the boundary ([B,C,T,H,W] fp32 <-> [(B T) H W, C] fp16/fp32)
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int C, int T, long long HW,
+                                    int c_off, int ldo) {
+  const long long total = (long long)B * C * T * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % HW;
+    long long r = i / HW;
+    const int t = (int)(r % T); r /= T;
+    const int c = (int)(r % C);
+    const long long b = r / C;
+    out[((b * T + t) * HW + p) * ldo + c_off + c] = __float2half_rn(x[i]);
+  }
+}
+int nchw_to_nhwc_f16(const float* x, __half* out, int B, int C, int T, long long HW, int c_off, int ldo, cudaStream_t stream) {
+  VC_REQUIRE(x && out, "nchw_to_nhwc: null pointer");
+  const long long total = (long long)B * C * T * HW;
+  const int blocks = (int)min((long long)sm_count() * 16, (total + 255) / 256);
+  nchw_to_nhwc_kernel<<<blocks, 256, 0, stream>>>(x, out, B, C, T, HW, c_off, ldo);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+__global__ void nhwc_to_ncthw_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int B, int C, int T, long long HW) {
+  const long long total = (long long)B * C * T * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % HW;
+    long long r = i / HW;
+    const int t = (int)(r % T); r /= T;
+    const int c = (int)(r % C);
+    const long long b = r / C;
+    out[i] = x[((b * T + t) * HW + p) * ldx + c];
+  }
+}
+int nhwc_to_ncthw_f32(const float* x, int ldx, float* out, int B, int C, int T, long long HW, cudaStream_t stream) {
+  VC_REQUIRE(x && out, "nhwc_to_ncthw: null pointer");
+  const long long total = (long long)B * C * T * HW;
+  const int blocks = (int)min((long long)sm_count() * 16, (total + 255) / 256);
+  nhwc_to_ncthw_kernel<<<blocks, 256, 0, stream>>>(x, ldx, out, B, C, T, HW);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+__global__ void nhwc_to_nchw_h_kernel(const __half* __restrict__ x, int ldx, float* __restrict__ out, int N, int C, long long HW) {
+  const long long total = (long long)N * C * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % HW;
+    const long long r = i / HW;
+    const int c = (int)(r % C);
+    const long long n = r / C;
+    out[i] = __half2float(x[(n * HW + p) * ldx + c]);
+  }
+}
+int nhwc_to_nchw_f32_from_f16(const __half* x, int ldx, float* out, int N, int C, long long HW, cudaStream_t stream) {
+  VC_REQUIRE(x && out, "nhwc_to_nchw: null pointer");
+  const long long total = (long long)N * C * HW;
+  const int blocks = (int)min((long long)sm_count() * 16, (total + 255) / 256);
+  nhwc_to_nchw_h_kernel<<<blocks, 256, 0, stream>>>(x, ldx, out, N, C, HW);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+__global__ void cast_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2half_rn(x[i]);
+}
+int cast_f32_to_f16(const float* x, __half* out, long long n, cudaStream_t stream) {
+  VC_REQUIRE(x && out, "cast: null pointer");
+  const int blocks = (int)min((long long)sm_count() * 16, (n + 255) / 256);
+  cast_kernel<<<blocks, 256, 0, stream>>>(x, out, n);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+__global__ void add_kernel(const __half2* __restrict__ a, const __half2* __restrict__ b, __half2* __restrict__ out, long long n2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const float2 x = __half22float2(a[i]), y = __half22float2(b[i]);
+    out[i] = __floats2half2_rn(x.x + y.x, x.y + y.y);
+  }
+}
+int add_rows_f16(const __half* a, const __half* b, __half* out, long long n, cudaStream_t stream) {
+  VC_REQUIRE(a && b && out && n % 2 == 0, "add: bad args");
+  const int blocks = (int)min((long long)sm_count() * 16, (n / 2 + 255) / 256);
+  add_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __half2*>(a), reinterpret_cast<const __half2*>(b),
+                                         reinterpret_cast<__half2*>(out), n / 2);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// time / fps embedding pieces (utils_diffusion.py:8-28, openaimodel3d.py:549-577, :218): fp32, M is 1..B
+// ------------------------------------------------------------------------------------------------
+__global__ void small_linear_kernel(const float* __restrict__ x, int rows, int K, const float* __restrict__ W,
+                                    const float* __restrict__ bias, int N, int act_in, float* __restrict__ out,
+                                    const float* __restrict__ add) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows * N) return;
+  const int r = warp / N, n = warp % N;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float xv = x[(long long)r * K + k];
+    if (act_in == 1) xv = xv / (1.0f + expf(-xv));
+    acc += xv * W[(long long)n * K + k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    float y = acc + (bias ? bias[n] : 0.f);
+    if (add) y += add[(long long)r * N + n];
+    out[(long long)r * N + n] = y;
+  }
+}
+int small_linear_f32(const float* x, int rows, int K, const float* W, const float* bias, int N, int act_in, float* out,
+                     const float* add, cudaStream_t stream) {
+  VC_REQUIRE(x && W && out && rows > 0 && N > 0 && K > 0, "small_linear: bad args");
+  const long long warps = (long long)rows * N;
+  const int blocks = (int)((warps * 32 + 255) / 256);
+  small_linear_kernel<<<blocks, 256, 0, stream>>>(x, rows, K, W, bias, N, act_in, out, add);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, int n, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int r = i / half, j = i % half;
+  // freqs = exp(-ln(10000) * j / half) evaluated in fp32 exactly as torch does
+  const float freq = expf(-9.210340371976184f * (float)j / (float)half);
+  const float arg = (float)t[r] * freq;
+  out[(long long)r * dim + j] = cosf(arg);
+  out[(long long)r * dim + half + j] = sinf(arg);
+  if ((dim & 1) && j == 0) out[(long long)r * dim + dim - 1] = 0.f;
+}
+int timestep_embedding_f32(const long long* t, int n, int dim, float* out, cudaStream_t stream) {
+  VC_REQUIRE(t && out && n > 0 && dim >= 2, "timestep_embedding: bad args");
+  const int total = n * (dim / 2);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, stream>>>(t, n, dim, out);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused DDIM update (ddim.py:228-281 + utils_diffusion.py:147-158), v-parameterisation, batch 1 per call.
+// pass 1: double-precision sums for the two unbiased stds; pass 2: elementwise update.
+// ------------------------------------------------------------------------------------------------
+__global__ void ddim_stats_kernel(const float* __restrict__ vc_, const float* __restrict__ vu, long long n, float cfg, double* ws) {
+  double s1 = 0, q1 = 0, s2 = 0, q2 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float c = vc_[i], u = vu[i];
+    const float m = u + cfg * (c - u);
+    s1 += c; q1 += (double)c * c;
+    s2 += m; q2 += (double)m * m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o); q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(ws + 0, s1); atomicAdd(ws + 1, q1); atomicAdd(ws + 2, s2); atomicAdd(ws + 3, q2);
+  }
+}
+__global__ void ddim_apply_kernel(const float* __restrict__ x, const float* __restrict__ vc_, const float* __restrict__ vu,
+                                  const float* __restrict__ noise, float* __restrict__ x_prev, float* __restrict__ pred_x0,
+                                  long long n, DdimStepScalars s, const double* ws) {
+  float factor = 1.f;
+  if (s.use_cfg && s.guidance_rescale > 0.f) {
+    const double dn = (double)n;
+    const double var_t = (ws[1] - ws[0] * ws[0] / dn) / (dn - 1.0);
+    const double var_c = (ws[3] - ws[2] * ws[2] / dn) / (dn - 1.0);
+    factor = (float)sqrt(var_t > 0 ? var_t : 0.0) / (float)sqrt(var_c > 0 ? var_c : 0.0);
+  }
+  const float rescale = s.prev_scale_t / s.scale_t;
+  const float dir_c = sqrtf(1.f - s.a_prev - s.sigma_t * s.sigma_t);
+  const float sq_ap = sqrtf(s.a_prev);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float c = vc_[i];
+    float m = c;
+    if (s.use_cfg) {
+      const float u = vu[i];
+      m = u + s.cfg_scale * (c - u);
+      if (s.guidance_rescale > 0.f) m = s.guidance_rescale * (m * factor) + (1.f - s.guidance_rescale) * m;
+    }
+    const float xi = x[i];
+    const float e_t = s.sqrt_ac_t * m + s.sqrt_1mac_t * xi;
+    float p0 = s.sqrt_ac_t * xi - s.sqrt_1mac_t * m;
+    p0 *= rescale;
+    pred_x0[i] = p0;
+    x_prev[i] = sq_ap * p0 + dir_c * e_t + s.sigma_t * noise[i];
+  }
+}
+int ddim_update(const float* x, const float* v_cond, const float* v_uncond, const float* noise, float* x_prev, float* pred_x0,
+                long long n, const DdimStepScalars& s, double* ws, cudaStream_t stream) {
+  VC_REQUIRE(x && v_cond && noise && x_prev && pred_x0 && ws && n > 1, "ddim_update: bad args");
+  VC_REQUIRE(!s.use_cfg || v_uncond, "ddim_update: CFG needs the unconditional output");
+  const int blocks = (int)min((long long)sm_count() * 4, (n + 255) / 256);
+  if (s.use_cfg && s.guidance_rescale > 0.f) {
+    VC_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4 * sizeof(double), stream));
+    ddim_stats_kernel<<<blocks, 256, 0, stream>>>(v_cond, v_uncond, n, s.cfg_scale, ws);
+    VC_CHECK_CUDA(cudaGetLastError());
+  }
+  ddim_apply_kernel<<<blocks, 256, 0, stream>>>(x, v_cond, v_uncond, noise, x_prev, pred_x0, n, s, ws);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+}  // namespace vc

@@ -1,0 +1,223 @@
+// HBM-bound normalisation kernels on channels-last fp16 activations.
+//   groupnorm_nhwc : GroupNorm(32) (+SiLU) over [samples, rows, C]; C may be the concat of two tensors.
+//                    pass 1 = per-CTA partial (sum, sumsq) per group (deterministic, no atomics to global),
+//                    pass 2 = finalize stats in smem + normalise/affine/SiLU with 16-byte vector I/O.
+//   layernorm_rows : LayerNorm over the last dim, one warp per token row, values held in registers.
+// Reference semantics: lvdm/basics.py:76-87 (fp32 GroupNorm), attention.py:265,331 (eps 1e-6),
+// openaimodel3d.py:256-265 (5-D GroupNorm in TemporalConvBlock), torch.nn.LayerNorm (eps 1e-5).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vc {
+
+static constexpr int GN_MAX_SPLITS = 512;
+
+size_t groupnorm_ws_bytes(int samples) { return (size_t)samples * GN_MAX_SPLITS * 64 * sizeof(float); }
+
+struct GnGeom {
+  int C, C1, C2, vecs, ppi, cg, splits;
+  long long rows, rows_per_split;
+};
+
+__device__ __forceinline__ uint4 gn_load(const __half* x1, const __half* x2, const GnGeom& g, long long sample, long long row, int c) {
+  const long long r = sample * g.rows + row;
+  const __half* p = (c < g.C1) ? (x1 + r * g.C1 + c) : (x2 + r * g.C2 + (c - g.C1));
+  return *reinterpret_cast<const uint4*>(p);
+}
+
+__global__ void __launch_bounds__(1024) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+                                                        float* __restrict__ partial) {
+  extern __shared__ float red[];   // [2*C]
+  const int tid = threadIdx.x;
+  const int v = tid % g.vecs, pl = tid / g.vecs;
+  const int split = blockIdx.x, sample = blockIdx.y;
+  for (int i = tid; i < 2 * g.C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float s[8], ss[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
+  const long long r0 = (long long)split * g.rows_per_split;
+  const long long r1 = min(g.rows, r0 + g.rows_per_split);
+  for (long long r = r0 + pl; r < r1; r += g.ppi) {
+    const uint4 u = gn_load(x1, x2, g, sample, r, v * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h[e]);
+      s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
+      s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    atomicAdd(&red[v * 8 + e], s[e]);
+    atomicAdd(&red[g.C + v * 8 + e], ss[e]);
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int grp = tid >> 1, which = tid & 1;
+    float acc = 0.f;
+    for (int c = grp * g.cg; c < (grp + 1) * g.cg; ++c) acc += red[which * g.C + c];
+    partial[((long long)sample * g.splits + split) * 64 + tid] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(1024) gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+                                                        const float* __restrict__ partial, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
+  __shared__ float mean_s[32], rstd_s[32];
+  const int tid = threadIdx.x;
+  const int sample = blockIdx.y;
+  if (tid < 32) {
+    double sum = 0.0, sq = 0.0;
+    const float* pp = partial + (long long)sample * g.splits * 64;
+    for (int sp = 0; sp < g.splits; ++sp) {
+      sum += pp[sp * 64 + tid * 2];
+      sq += pp[sp * 64 + tid * 2 + 1];
+    }
+    const double n = (double)g.rows * g.cg;
+    const double m = sum / n;
+    double var = sq / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean_s[tid] = (float)m;
+    rstd_s[tid] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int v = tid % g.vecs, pl = tid / g.vecs;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = v * 8 + e;
+    const int grp = c / g.cg;
+    const float a = rstd_s[grp] * gamma[c];
+    sc[e] = a;
+    sh[e] = beta[c] - mean_s[grp] * a;
+  }
+  const long long r0 = (long long)blockIdx.x * g.rows_per_split;
+  const long long r1 = min(g.rows, r0 + g.rows_per_split);
+  for (long long r = r0 + pl; r < r1; r += g.ppi) {
+    const uint4 u = gn_load(x1, x2, g, sample, r, v * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __half22float2(h[e]);
+      f[2 * e] = t.x; f[2 * e + 1] = t.y;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float y = f[e] * sc[e] + sh[e];
+      f[e] = silu ? silu_f(y) : y;
+    }
+    uint4 o;
+    o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
+    o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + ((long long)sample * g.rows + r) * g.C + v * 8) = o;
+  }
+}
+
+int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample,
+                   const float* gamma, const float* beta, float eps, int silu, __half* out, float* partial_ws,
+                   size_t ws_bytes, cudaStream_t stream) {
+  const int C = C1 + (x2 ? C2 : 0);
+  VC_REQUIRE(x1 && out && gamma && beta && partial_ws, "groupnorm: null pointer");
+  VC_REQUIRE(C % 32 == 0 && C1 % 8 == 0 && (!x2 || C2 % 8 == 0) && C <= 8192, "groupnorm: unsupported channels C1=%d C2=%d", C1, C2);
+  VC_REQUIRE(samples >= 1 && rows_per_sample >= 1, "groupnorm: empty input");
+  GnGeom g;
+  g.C = C; g.C1 = C1; g.C2 = x2 ? C2 : 0;
+  g.vecs = C / 8;
+  g.ppi = 512 / g.vecs > 0 ? 512 / g.vecs : 1;
+  g.cg = C / 32;
+  g.rows = rows_per_sample;
+  int splits = (2 * sm_count() + samples - 1) / samples;
+  const long long max_useful = (rows_per_sample + g.ppi - 1) / g.ppi;
+  if (splits > max_useful) splits = (int)max_useful;
+  if (splits > GN_MAX_SPLITS) splits = GN_MAX_SPLITS;
+  if (splits < 1) splits = 1;
+  g.splits = splits;
+  g.rows_per_split = (rows_per_sample + splits - 1) / splits;
+  VC_REQUIRE(ws_bytes >= (size_t)samples * splits * 64 * sizeof(float), "groupnorm: workspace too small");
+  const int threads = g.vecs * g.ppi;
+  dim3 grid(splits, samples);
+  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(x1, x2, g, partial_ws);
+  VC_CHECK_CUDA(cudaGetLastError());
+  gn_apply_kernel<<<grid, threads, 0, stream>>>(x1, x2, g, partial_ws, gamma, beta, eps, silu, out);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, __half* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int vecs = C >> 3;
+  float f[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < vecs) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + v * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = __half22float2(h[e]);
+        f[i][2 * e] = t.x; f[i][2 * e + 1] = t.y;
+        sum += t.x + t.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < vecs) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = f[i][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < vecs) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = (f[i][e] - mean) * rstd * __ldg(gamma + v * 8 + e) + __ldg(beta + v * 8 + e);
+      uint4 o;
+      o.x = pack_half2(y[0], y[1]); o.y = pack_half2(y[2], y[3]);
+      o.z = pack_half2(y[4], y[5]); o.w = pack_half2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(out + row * C + v * 8) = o;
+    }
+  }
+}
+
+int layernorm_rows(const __half* x, long long rows, int C, const float* gamma, const float* beta, float eps, __half* out,
+                   cudaStream_t stream) {
+  VC_REQUIRE(x && out && gamma && beta, "layernorm: null pointer");
+  VC_REQUIRE(C % 8 == 0 && C <= 2048 && rows > 0, "layernorm: unsupported C=%d rows=%lld", C, rows);
+  const int wpb = 8;
+  const long long blocks = (rows + wpb - 1) / wpb;
+  const int vecs = C / 8;
+  if (vecs <= 64)
+    layernorm_kernel<2><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, gamma, beta, eps, out);
+  else if (vecs <= 160)
+    layernorm_kernel<5><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, gamma, beta, eps, out);
+  else
+    layernorm_kernel<8><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, gamma, beta, eps, out);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+}  // namespace vc

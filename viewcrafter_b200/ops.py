@@ -1,0 +1,337 @@
+"""Torch-tensor wrappers over the C ABI (include/vc_b200.h).  PyTorch is only the allocator / stream provider.
+
+Activation convention: channels-last fp16 matrices ``[rows, C]`` where a row is a pixel of a frame
+(``rows = frames*H*W`` in (frame, y, x) order) or a token.  Every function raises on failure; nothing here
+falls back to a PyTorch implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AttnDesc, DdimScalars, GemmDesc, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk16(t: torch.Tensor, name: str):
+    if t.dtype != torch.float16 or not t.is_cuda:
+        raise _lib.VcError(f"{name}: expected a CUDA fp16 tensor, got {t.dtype} on {t.device}")
+
+
+# ----------------------------------------------------------------------------------------------------
+# weight packing (host side, once per load_state_dict)
+# ----------------------------------------------------------------------------------------------------
+def pack_conv3x3(w: torch.Tensor, k_pad: int = 0) -> torch.Tensor:
+    """[Cout,Cin,3,3] -> fp16 [9*Cout, Cin(+pad)], tap = ky*3+kx (tap shift dx=kx-1, dy=ky-1)."""
+    co, ci = w.shape[0], w.shape[1]
+    p = w.permute(2, 3, 0, 1).reshape(9 * co, ci)
+    if k_pad > ci:
+        p = torch.nn.functional.pad(p, (0, k_pad - ci))
+    return p.to(torch.float16).contiguous()
+
+
+def pack_conv_temporal(w: torch.Tensor) -> torch.Tensor:
+    """Conv3d weight [Cout,Cin,3,1,1] -> fp16 [3*Cout, Cin], tap = kt."""
+    co, ci = w.shape[0], w.shape[1]
+    return w.reshape(co, ci, 3).permute(2, 0, 1).reshape(3 * co, ci).to(torch.float16).contiguous()
+
+
+def pack_linear(w: torch.Tensor) -> torch.Tensor:
+    """[N,K] or 1x1 conv [N,K,1(,1)] -> fp16 [N,K]."""
+    return w.reshape(w.shape[0], w.shape[1]).to(torch.float16).contiguous()
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor):
+    """GEGLU proj [2*inner, C]: interleave value/gate rows per N tile so the epilogue sees both (attention.py:415-422)."""
+    inner = w.shape[0] // 2
+    bn = _lib.load().vc_gemm_tile_n(2 * inner, 1)
+    half = bn // 2
+    idx = []
+    for t in range(2 * inner // bn):
+        idx.extend(range(t * half, (t + 1) * half))
+        idx.extend(range(inner + t * half, inner + (t + 1) * half))
+    idx = torch.tensor(idx, device=w.device)
+    return w[idx].to(torch.float16).contiguous(), b[idx].float().contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------
+# tensor-core ops
+# ----------------------------------------------------------------------------------------------------
+def _gemm(desc: GemmDesc):
+    check(_lib.load().vc_gemm_tap(C.byref(desc), _stream()), "vc_gemm_tap")
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+           geglu: bool = False, out: Optional[torch.Tensor] = None, out_f32: bool = False,
+           x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = [x|x2] @ w.T (+bias) (GEGLU) (+res).  x: [M,K1] fp16 (row pitch = x.stride(0)), w: [N,K] fp16."""
+    _chk16(x, "linear.x"); _chk16(w, "linear.w")
+    M, K1 = x.shape
+    N, K = w.shape
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, n_out), device=x.device, dtype=torch.float32 if out_f32 else torch.float16)
+    d = GemmDesc()
+    d.a, d.lda = x.data_ptr(), x.stride(0)
+    if x2 is not None:
+        d.a2, d.lda2 = x2.data_ptr(), x2.stride(0)
+        assert K1 + x2.shape[1] == K
+    else:
+        assert K1 == K, (K1, K)
+    d.X, d.Y, d.Z, d.bx, d.by = M, 1, 1, 128, 1
+    d.K, d.K1, d.w, d.N, d.num_taps = K, K1, w.data_ptr(), N, 1
+    if out_f32:
+        d.out_f32 = out.data_ptr()
+    else:
+        d.out = out.data_ptr()
+    d.ldo = out.stride(0)
+    d.bias = _ptr(bias)
+    if res is not None:
+        d.res, d.ldr = res.data_ptr(), res.stride(0)
+    d.geglu = int(geglu)
+    _gemm(d)
+    return out
+
+
+def _conv_box(H: int, W: int):
+    if W >= 128:
+        return 128, 1
+    if 128 % W != 0:
+        raise _lib.VcError(f"conv: width {W} must divide 128 or be a multiple of it")
+    return W, 128 // W
+
+
+def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w9: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            res: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None, bias_z_div: int = 0,
+            out_f32: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution on [frames*H*W, Cin] rows; w9 = pack_conv3x3(weight)."""
+    _chk16(x, "conv3x3.x"); _chk16(w9, "conv3x3.w")
+    M, K1 = x.shape
+    assert M == frames * H * W, (M, frames, H, W)
+    K = w9.shape[1]
+    N = w9.shape[0] // 9
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else torch.float16)
+    d = GemmDesc()
+    d.a, d.lda = x.data_ptr(), x.stride(0)
+    if x2 is not None:
+        d.a2, d.lda2 = x2.data_ptr(), x2.stride(0)
+        assert K1 + x2.shape[1] == K
+    else:
+        assert K1 == K, (K1, K)
+    d.X, d.Y, d.Z = W, H, frames
+    d.bx, d.by = _conv_box(H, W)
+    d.K, d.K1, d.w, d.N, d.num_taps = K, K1, w9.data_ptr(), N, 9
+    for t in range(9):
+        d.tap_dx[t] = t % 3 - 1
+        d.tap_dy[t] = t // 3 - 1
+    if out_f32:
+        d.out_f32 = out.data_ptr()
+    else:
+        d.out = out.data_ptr()
+    d.ldo = out.stride(0)
+    d.bias, d.bias_z_div = _ptr(bias), bias_z_div
+    if res is not None:
+        d.res, d.ldr = res.data_ptr(), res.stride(0)
+    _gemm(d)
+    return out
+
+
+def conv_temporal(x: torch.Tensor, B: int, T: int, HW: int, w3: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                  res: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Conv3d (3,1,1) pad (1,0,0) on [(B T) HW, C] rows: three row-shifted GEMM taps; batches never mix (Z = B)."""
+    _chk16(x, "conv_temporal.x")
+    M, K = x.shape
+    assert M == B * T * HW
+    N = w3.shape[0] // 3
+    out = torch.empty((M, N), device=x.device, dtype=torch.float16)
+    d = GemmDesc()
+    d.a, d.lda = x.data_ptr(), x.stride(0)
+    d.X, d.Y, d.Z, d.bx, d.by = T * HW, 1, B, 128, 1
+    d.K, d.K1, d.w, d.N, d.num_taps = K, K, w3.data_ptr(), N, 3
+    for t in range(3):
+        d.tap_dx[t] = (t - 1) * HW
+        d.tap_dy[t] = 0
+    d.out, d.ldo = out.data_ptr(), out.stride(0)
+    d.bias = _ptr(bias)
+    if res is not None:
+        d.res, d.ldr = res.data_ptr(), res.stride(0)
+    _gemm(d)
+    return out
+
+
+def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, Nq: int, Nk: int, heads: int,
+               kv_shared: bool = False, scale: float = 0.125, out: Optional[torch.Tensor] = None,
+               accumulate: bool = False) -> torch.Tensor:
+    """softmax(q k^T scale) v per head (d=64).  q: [B*Nq, >=heads*64] view, k/v: [Bk*Nk, ...] views (Bk=1 if shared)."""
+    _chk16(q, "attn.q"); _chk16(k, "attn.k"); _chk16(v, "attn.v")
+    if out is None:
+        out = torch.empty((B * Nq, heads * 64), device=q.device, dtype=torch.float16)
+    d = AttnDesc()
+    d.q, d.ldq = q.data_ptr(), q.stride(0)
+    d.k, d.ldk = k.data_ptr(), k.stride(0)
+    d.v, d.ldv = v.data_ptr(), v.stride(0)
+    assert k.stride(0) == v.stride(0)
+    d.out, d.ldo = out.data_ptr(), out.stride(0)
+    d.B, d.heads, d.Nq, d.Nk = B, heads, Nq, Nk
+    d.kv_batch_stride = 0 if kv_shared else Nk * k.stride(0)
+    d.scale = scale
+    d.accumulate = int(accumulate)
+    check(_lib.load().vc_flash_attn_d64(C.byref(d), _stream()), "vc_flash_attn_d64")
+    return out
+
+
+def temporal_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, T: int, sites: int, heads: int,
+                  scale: float = 0.125) -> torch.Tensor:
+    _chk16(q, "tattn.q")
+    out = torch.empty((T * sites, heads * 64), device=q.device, dtype=torch.float16)
+    assert q.stride(0) == k.stride(0) == v.stride(0)
+    check(_lib.load().vc_temporal_attn(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
+                                       T, sites, heads, scale, _stream()), "vc_temporal_attn")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# normalisation / data movement
+# ----------------------------------------------------------------------------------------------------
+_gn_ws = {}
+
+
+def _gn_workspace(device, samples: int) -> torch.Tensor:
+    need = _lib.load().vc_groupnorm_ws_bytes(samples)
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), device=device, dtype=torch.uint8)
+        _gn_ws[key] = ws
+    return ws
+
+
+def groupnorm(x: torch.Tensor, samples: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
+              x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(32) (+SiLU) over ``samples`` groups of rows; [x|x2] concatenated along channels."""
+    _chk16(x, "groupnorm.x")
+    rows, C1 = x.shape
+    C2 = 0 if x2 is None else x2.shape[1]
+    assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
+    out = torch.empty((rows, C1 + C2), device=x.device, dtype=torch.float16)
+    ws = _gn_workspace(x.device, samples)
+    check(_lib.load().vc_groupnorm_nhwc(x.data_ptr(), C1, _ptr(x2), C2, samples, rows // samples, gamma.data_ptr(), beta.data_ptr(),
+                                        eps, int(silu), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "vc_groupnorm_nhwc")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _chk16(x, "layernorm.x")
+    assert x.is_contiguous()
+    out = torch.empty_like(x)
+    check(_lib.load().vc_layernorm(x.data_ptr(), x.shape[0], x.shape[1], gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(),
+                                   _stream()), "vc_layernorm")
+    return out
+
+
+def upsample2x(x: torch.Tensor, N: int, H: int, W: int) -> torch.Tensor:
+    _chk16(x, "upsample.x")
+    Cc = x.shape[1]
+    out = torch.empty((N * 4 * H * W, Cc), device=x.device, dtype=torch.float16)
+    check(_lib.load().vc_upsample2x_nhwc(x.data_ptr(), out.data_ptr(), N, H, W, Cc, _stream()), "vc_upsample2x_nhwc")
+    return out
+
+
+def im2col_s2(x: torch.Tensor, N: int, H: int, W: int, pad_lo: int = 1) -> tuple:
+    _chk16(x, "im2col.x")
+    Cc = x.shape[1]
+    Ho, Wo = (H + 2 * pad_lo - 3) // 2 + 1, (W + 2 * pad_lo - 3) // 2 + 1
+    out = torch.empty((N * Ho * Wo, 9 * Cc), device=x.device, dtype=torch.float16)
+    check(_lib.load().vc_im2col3x3_s2(x.data_ptr(), out.data_ptr(), N, H, W, Cc, pad_lo, Ho, Wo, _stream()), "vc_im2col3x3_s2")
+    return out, Ho, Wo
+
+
+def ncthw_to_rows(x: torch.Tensor, out: torch.Tensor, c_off: int = 0):
+    """fp32 [B,C,T,H,W] -> fp16 rows [(B T H W), ld] at channel offset c_off ('b c t h w -> (b t) h w c')."""
+    B, Cc, T, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    check(_lib.load().vc_ncthw_f32_to_rows_f16(x.data_ptr(), out.data_ptr(), B, Cc, T, H * W, c_off, out.stride(0), _stream()),
+          "vc_ncthw_f32_to_rows_f16")
+
+
+def rows_to_ncthw(x: torch.Tensor, B: int, Cc: int, T: int, H: int, W: int) -> torch.Tensor:
+    assert x.dtype == torch.float32
+    out = torch.empty((B, Cc, T, H, W), device=x.device, dtype=torch.float32)
+    check(_lib.load().vc_rows_f32_to_ncthw(x.data_ptr(), x.stride(0), out.data_ptr(), B, Cc, T, H * W, _stream()),
+          "vc_rows_f32_to_ncthw")
+    return out
+
+
+def rows_f16_to_nchw(x: torch.Tensor, N: int, Cc: int, H: int, W: int) -> torch.Tensor:
+    _chk16(x, "rows_f16_to_nchw.x")
+    out = torch.empty((N, Cc, H, W), device=x.device, dtype=torch.float32)
+    check(_lib.load().vc_rows_f16_to_nchw_f32(x.data_ptr(), x.stride(0), out.data_ptr(), N, Cc, H * W, _stream()),
+          "vc_rows_f16_to_nchw_f32")
+    return out
+
+
+def cast_f16(x: torch.Tensor) -> torch.Tensor:
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    check(_lib.load().vc_cast_f32_to_f16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "vc_cast_f32_to_f16")
+    return out
+
+
+def add_f16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(a)
+    check(_lib.load().vc_add_f16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), "vc_add_f16")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# embedding MLP + DDIM update
+# ----------------------------------------------------------------------------------------------------
+def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    assert t.dtype == torch.int64 and t.is_cuda
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.float32)
+    check(_lib.load().vc_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream()), "vc_timestep_embedding")
+    return out
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], silu_in: bool = False,
+                 add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert x.dtype == torch.float32 and w.dtype == torch.float32 and x.is_contiguous() and w.is_contiguous()
+    out = torch.empty((x.shape[0], w.shape[0]), device=x.device, dtype=torch.float32)
+    check(_lib.load().vc_small_linear_f32(x.data_ptr(), x.shape[0], x.shape[1], w.data_ptr(), _ptr(b), w.shape[0], int(silu_in),
+                                          out.data_ptr(), _ptr(add), _stream()), "vc_small_linear_f32")
+    return out
+
+
+_ddim_ws = {}
+
+
+def ddim_update(x, v_cond, v_uncond, noise, sc: dict):
+    """Fused ddim.py:228-281.  sc: cfg_scale, guidance_rescale, sqrt_ac_t, sqrt_1mac_t, a_prev, sigma_t, scale_t, prev_scale_t."""
+    for t in (x, v_cond, noise):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    s = DdimScalars()
+    use_cfg = v_uncond is not None and sc["cfg_scale"] != 1.0
+    s.cfg_scale, s.guidance_rescale = sc["cfg_scale"], sc["guidance_rescale"] if use_cfg else 0.0
+    s.sqrt_ac_t, s.sqrt_1mac_t = sc["sqrt_ac_t"], sc["sqrt_1mac_t"]
+    s.a_prev, s.sigma_t, s.scale_t, s.prev_scale_t = sc["a_prev"], sc["sigma_t"], sc["scale_t"], sc["prev_scale_t"]
+    s.use_cfg = int(use_cfg)
+    ws = _ddim_ws.get(x.device)
+    if ws is None:
+        ws = torch.zeros(4, device=x.device, dtype=torch.float64)
+        _ddim_ws[x.device] = ws
+    x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
+    check(_lib.load().vc_ddim_update(x.data_ptr(), v_cond.data_ptr(), _ptr(v_uncond) if use_cfg else None, noise.data_ptr(),
+                                     x_prev.data_ptr(), pred_x0.data_ptr(), x.numel(), C.byref(s), ws.data_ptr(), _stream()),
+          "vc_ddim_update")
+    return x_prev, pred_x0
