@@ -1,0 +1,99 @@
+"""U-Net parity on the GPU: viewcrafter_b200.UNetModel (CUDA kernels via the C ABI) vs
+  (a) golden outputs of the UNMODIFIED reference UNetModel (tests/golden/unet_*.npz, fp32 CPU), and
+  (b) the CPU oracle on the same seeded inputs.
+
+Tolerance (stated, see DESIGN.md "Numerics"): activations are fp16 with fp32 accumulation, the reference runs the
+same graph under torch.cuda.amp.autocast (fp16 GEMMs, fp32 norms).  For these synthetic weights the output has
+std ~0.5-0.6; we require max|err| <= 0.04 and mean|err| <= 0.004 against the fp32 reference, i.e. < 7% / 0.7% of
+the output std -- the level autocast itself sits at for a ~150-GEMM-deep fp16 network.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+UNET_KW = dict(in_channels=8, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
+               num_res_blocks=2, channel_mult=[1, 2, 4, 4], dropout=0.1, num_head_channels=64,
+               transformer_depth=1, context_dim=1024, use_linear=True, use_checkpoint=False,
+               temporal_conv=True, temporal_attention=True, temporal_selfatt_only=True,
+               use_relative_position=False, use_causal_attention=False, temporal_length=16,
+               addition_attention=True, image_cross_attention=True, default_fs=10, fs_condition=True)
+
+MAX_ERR, MEAN_ERR = 0.04, 0.004
+
+
+def _build(over, shapes, seed):
+    from oracle import synth
+    from viewcrafter_b200.unet import UNetModel
+    kw = dict(UNET_KW); kw.update(over)
+    m = UNetModel(**kw)
+    sd = synth.synth_state_dict(shapes, seed)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
+
+
+@pytest.mark.parametrize("name", ["mc64_T4", "mc64_T16", "mc128_T3"])
+def test_unet_matches_reference_golden(golden_dir, name):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    g = np.load(os.path.join(golden_dir, f"unet_{name}.npz"))
+    shapes = [(n, tuple(s)) for n, s in json.loads(str(g["shapes"]))]
+    m, _ = _build(json.loads(str(g["kwargs"])), shapes, seed=3)
+    y = m(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), context=torch.from_numpy(g["ctx"]).cuda(),
+          fs=torch.from_numpy(g["fs"]).cuda())
+    err = (y.cpu() - torch.from_numpy(g["y"])).abs()
+    print(f"{name}: max err {float(err.max()):.4g} mean err {float(err.mean()):.4g} ref std {float(g['y'].std()):.3g}")
+    assert y.shape == g["y"].shape and torch.isfinite(y).all()
+    assert float(err.max()) <= MAX_ERR and float(err.mean()) <= MEAN_ERR
+
+
+def test_unet_batch2_and_default_fs_vs_oracle():
+    """B=2 (two independent latents/contexts) with fs=None (default_fs path) against the CPU oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import lvdm_oracle as O
+    from oracle import synth
+    from viewcrafter_b200.unet import UNetModel
+    kw = dict(UNET_KW); kw.update(model_channels=64)
+    m = UNetModel(**kw)
+    shapes = synth.module_shapes(m)
+    m, sd = _build(dict(model_channels=64), shapes, seed=9)
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(2, 8, 5, 8, 8, generator=g)
+    ctx = torch.randn(2, 333, 1024, generator=g)
+    t = torch.tensor([999, 19])
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, ctx, None, default_fs=10)
+    y = m(x.cuda(), t.cuda(), context=ctx.cuda())
+    err = (y.cpu() - ref).abs()
+    print(f"B=2: max err {float(err.max()):.4g} mean err {float(err.mean()):.4g}")
+    assert float(err.max()) <= MAX_ERR and float(err.mean()) <= MEAN_ERR
+
+
+def test_unet_full_width_block_stack_vs_oracle():
+    """Real channel widths (model_channels=320: 5/10/20 heads, N tiles of 160/256, K split 1280+640...) at a tiny
+    spatial size so the fp32 CPU oracle finishes in seconds."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import lvdm_oracle as O
+    from oracle import synth
+    from viewcrafter_b200.unet import UNetModel
+    m = UNetModel(**UNET_KW)
+    shapes = synth.module_shapes(m)
+    del m
+    m, sd = _build({}, shapes, seed=12)
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(1, 8, 3, 8, 16, generator=g)
+    ctx = torch.randn(1, 333, 1024, generator=g)
+    t, fs = torch.tensor([499]), torch.tensor([10])
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, ctx, fs)
+    y = m(x.cuda(), t.cuda(), context=ctx.cuda(), fs=fs.cuda())
+    err = (y.cpu() - ref).abs()
+    print(f"mc320: max err {float(err.max()):.4g} mean err {float(err.mean()):.4g} ref std {float(ref.std()):.3g}")
+    assert float(err.max()) <= MAX_ERR and float(err.mean()) <= MEAN_ERR

@@ -1,0 +1,435 @@
+"""Drop-in ``UNetModel`` (reference: lvdm/modules/networks/openaimodel3d.py:281-603).
+
+Same constructor kwargs, same ``forward(x, timesteps, context, features_adapter, fs, **kw)`` and the same
+state-dict keys/shapes so the reference checkpoint loads with ``strict=True``.  The
+``torch.nn`` modules below are *parameter holders only*: ``forward`` never calls them.  All arithmetic runs in
+libvc_b200.so on channels-last fp16 activations (``rows = (b t) h w``, columns = channels):
+
+    ResBlock            -> GroupNorm+SiLU kernel, 9-tap tcgen05 GEMM (+emb bias), again, 1x1 skip GEMM fused as
+                           residual, then 4x [5-D GroupNorm+SiLU, 3-tap temporal GEMM]          (:210-279)
+    SpatialTransformer  -> GroupNorm, proj_in GEMM, LN, fused-QKV GEMM, tcgen05 flash attention, out-proj GEMM
+                           (+res), LN, q GEMM, text + image cross attention (accumulate), LN, GEGLU GEMM, FF GEMM,
+                           proj_out GEMM (+x_in)                                                  (attention.py:249-310)
+    TemporalTransformer -> same with the temporal (T<=32) attention kernel, no transposes: tokens stay in
+                           (t, h, w) row order and the kernel strides over t                      (attention.py:313-412)
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _zero(m: nn.Module) -> nn.Module:
+    for p in m.parameters():
+        nn.init.zeros_(p)
+    return m
+
+
+def _unsupported(flag: str):
+    raise NotImplementedError(f"viewcrafter_b200.UNetModel: option {flag} is not on the ViewCrafter inference path")
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter holders (names are load-bearing, incl. the upstream 'temopral_conv' spelling)
+# --------------------------------------------------------------------------------------------------
+class _Attn(nn.Module):
+    def __init__(self, dim: int, ctx_dim: Optional[int], heads: int, image_branch: bool):
+        super().__init__()
+        inner = heads * 64
+        kd = ctx_dim or dim
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_k = nn.Linear(kd, inner, bias=False)
+        self.to_v = nn.Linear(kd, inner, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(0.0))
+        if image_branch:
+            self.to_k_ip = nn.Linear(kd, inner, bias=False)
+            self.to_v_ip = nn.Linear(kd, inner, bias=False)
+
+
+class _GEGLU(nn.Module):
+    def __init__(self, dim, inner):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner * 2)
+
+
+class _FF(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.Sequential(_GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim))
+
+
+class _TBlock(nn.Module):
+    def __init__(self, dim, heads, ctx_dim, image_branch):
+        super().__init__()
+        self.attn1 = _Attn(dim, None, heads, False)
+        self.ff = _FF(dim)
+        self.attn2 = _Attn(dim, ctx_dim, heads, image_branch)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+
+
+class _Transformer(nn.Module):
+    """kind 'S' (SpatialTransformer) or 'T' (TemporalTransformer); conv1d=True gives init_attn's Conv1d projections."""
+
+    def __init__(self, kind, channels, heads, depth, ctx_dim, image_branch, conv1d=False):
+        super().__init__()
+        self.kind, self.channels, self.heads = kind, channels, heads
+        inner = heads * 64
+        self.norm = nn.GroupNorm(32, channels, eps=1e-6, affine=True)
+        mk = (lambda i, o: nn.Conv1d(i, o, 1)) if conv1d else nn.Linear
+        self.proj_in = mk(channels, inner)
+        self.transformer_blocks = nn.ModuleList([
+            _TBlock(inner, heads, ctx_dim if kind == "S" else None, image_branch and kind == "S") for _ in range(depth)])
+        self.proj_out = _zero(mk(inner, channels))
+
+
+class _TemporalConv(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        conv = lambda: nn.Conv3d(c, c, (3, 1, 1), padding=(1, 0, 0))
+        self.conv1 = nn.Sequential(nn.GroupNorm(32, c), nn.SiLU(), conv())
+        self.conv2 = nn.Sequential(nn.GroupNorm(32, c), nn.SiLU(), nn.Dropout(0.0), conv())
+        self.conv3 = nn.Sequential(nn.GroupNorm(32, c), nn.SiLU(), nn.Dropout(0.0), conv())
+        self.conv4 = nn.Sequential(nn.GroupNorm(32, c), nn.SiLU(), nn.Dropout(0.0), _zero(conv()))
+
+
+class _Res(nn.Module):
+    def __init__(self, cin, emb_ch, cout, temporal):
+        super().__init__()
+        self.cin, self.cout = cin, cout
+        self.in_layers = nn.Sequential(nn.GroupNorm(32, cin), nn.SiLU(), nn.Conv2d(cin, cout, 3, padding=1))
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_ch, cout))
+        self.out_layers = nn.Sequential(nn.GroupNorm(32, cout), nn.SiLU(), nn.Dropout(0.0),
+                                        _zero(nn.Conv2d(cout, cout, 3, padding=1)))
+        self.skip_connection = nn.Identity() if cin == cout else nn.Conv2d(cin, cout, 1)
+        if temporal:
+            self.temopral_conv = _TemporalConv(cout)
+
+
+class _Down(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.op = nn.Conv2d(c, c, 3, stride=2, padding=1)
+
+
+class _Up(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+
+class _Stage(nn.Sequential):
+    pass
+
+
+# --------------------------------------------------------------------------------------------------
+class UNetModel(nn.Module):
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0.0,
+                 channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, context_dim=None, use_scale_shift_norm=False,
+                 resblock_updown=False, num_heads=-1, num_head_channels=-1, transformer_depth=1, use_linear=False,
+                 use_checkpoint=False, temporal_conv=False, tempspatial_aware=False, temporal_attention=True,
+                 use_relative_position=True, use_causal_attention=False, temporal_length=None, use_fp16=False,
+                 addition_attention=False, temporal_selfatt_only=True, image_cross_attention=False,
+                 image_cross_attention_scale_learnable=False, default_fs=4, fs_condition=False):
+        super().__init__()
+        if num_head_channels != 64:
+            _unsupported("num_head_channels != 64 (the attention kernels are specialised for head_dim 64)")
+        for bad, name in ((use_scale_shift_norm, "use_scale_shift_norm"), (resblock_updown, "resblock_updown"),
+                          (tempspatial_aware, "tempspatial_aware"), (use_relative_position, "use_relative_position"),
+                          (use_causal_attention, "use_causal_attention"), (not use_linear, "use_linear=False"),
+                          (not conv_resample, "conv_resample=False"), (dims != 2, "dims != 2"),
+                          (not temporal_selfatt_only, "temporal_selfatt_only=False"),
+                          (image_cross_attention_scale_learnable, "image_cross_attention_scale_learnable")):
+            if bad:
+                _unsupported(name)
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_res_blocks, self.attention_resolutions, self.channel_mult = num_res_blocks, attention_resolutions, channel_mult
+        self.dropout, self.use_checkpoint = dropout, use_checkpoint
+        self.temporal_attention, self.temporal_length = temporal_attention, temporal_length
+        self.addition_attention, self.image_cross_attention = addition_attention, image_cross_attention
+        self.default_fs, self.fs_condition = default_fs, fs_condition
+        self.dtype = torch.float16 if use_fp16 else torch.float32
+        mc, ted = model_channels, model_channels * 4
+
+        mlp = lambda: nn.Sequential(nn.Linear(mc, ted), nn.SiLU(), nn.Linear(ted, ted))
+        self.time_embed = mlp()
+        if fs_condition:
+            self.fps_embedding = mlp()
+            _zero(self.fps_embedding[-1])
+
+        def attn_layers(ch):
+            heads = ch // 64
+            layers = [_Transformer("S", ch, heads, transformer_depth, context_dim, image_cross_attention)]
+            if temporal_attention:
+                layers.append(_Transformer("T", ch, heads, transformer_depth, None, False))
+            return layers
+
+        self.input_blocks = nn.ModuleList([_Stage(nn.Conv2d(in_channels, mc, 3, padding=1))])
+        if addition_attention:
+            self.init_attn = _Stage(_Transformer("T", mc, 8, transformer_depth, None, False, conv1d=True))
+        skip_ch, ch, ds = [mc], mc, 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers: List[nn.Module] = [_Res(ch, ted, mult * mc, temporal_conv)]
+                ch = mult * mc
+                if ds in attention_resolutions:
+                    layers += attn_layers(ch)
+                self.input_blocks.append(_Stage(*layers))
+                skip_ch.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(_Stage(_Down(ch)))
+                skip_ch.append(ch)
+                ds *= 2
+        mid: List[nn.Module] = [_Res(ch, ted, ch, temporal_conv),
+                                _Transformer("S", ch, ch // 64, transformer_depth, context_dim, image_cross_attention)]
+        if temporal_attention:
+            mid.append(_Transformer("T", ch, ch // 64, transformer_depth, None, False))
+        mid.append(_Res(ch, ted, ch, temporal_conv))
+        self.middle_block = _Stage(*mid)
+        self.output_blocks = nn.ModuleList()
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [_Res(ch + skip_ch.pop(), ted, mult * mc, temporal_conv)]
+                ch = mult * mc
+                if ds in attention_resolutions:
+                    layers += attn_layers(ch)
+                if level and i == num_res_blocks:
+                    layers.append(_Up(ch))
+                    ds //= 2
+                self.output_blocks.append(_Stage(*layers))
+        self.out = nn.Sequential(nn.GroupNorm(32, ch), nn.SiLU(), _zero(nn.Conv2d(mc, out_channels, 3, padding=1)))
+
+        self._packed = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
+
+    # ------------------------------------------------------------------------------------------
+    # weight packing: fp32 checkpoint tensors -> kernel layouts (fp16 K-major GEMM operands, fp32 norm/bias)
+    # ------------------------------------------------------------------------------------------
+    def invalidate_packed(self):
+        self._packed = None
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    @staticmethod
+    def _f32(t):
+        return t.detach().float().contiguous()
+
+    def _pack_res(self, m: _Res):
+        f = self._f32
+        P = dict(kind="R", cin=m.cin, cout=m.cout)
+        P["gn1"] = (f(m.in_layers[0].weight), f(m.in_layers[0].bias))
+        P["w1"] = ops.pack_conv3x3(m.in_layers[2].weight.detach())
+        P["emb_w"] = f(m.emb_layers[1].weight)
+        P["emb_b"] = f(m.emb_layers[1].bias + m.in_layers[2].bias)       # conv1 bias folded into the per-batch emb row
+        P["gn2"] = (f(m.out_layers[0].weight), f(m.out_layers[0].bias))
+        P["w2"] = ops.pack_conv3x3(m.out_layers[3].weight.detach())
+        P["b2"] = f(m.out_layers[3].bias)
+        if isinstance(m.skip_connection, nn.Conv2d):
+            P["skip_w"] = ops.pack_linear(m.skip_connection.weight.detach())
+            P["skip_b"] = f(m.skip_connection.bias)
+        if hasattr(m, "temopral_conv"):
+            tc = m.temopral_conv
+            P["tconv"] = [(f(seq[0].weight), f(seq[0].bias), ops.pack_conv_temporal(seq[-1].weight.detach()), f(seq[-1].bias))
+                          for seq in (tc.conv1, tc.conv2, tc.conv3, tc.conv4)]
+        return P
+
+    def _pack_tf(self, m: _Transformer):
+        f = self._f32
+        P = dict(kind=m.kind, heads=m.heads, C=m.channels)
+        P["gn"] = (f(m.norm.weight), f(m.norm.bias))
+        P["in_w"], P["in_b"] = ops.pack_linear(m.proj_in.weight.detach()), f(m.proj_in.bias)
+        P["out_w"], P["out_b"] = ops.pack_linear(m.proj_out.weight.detach()), f(m.proj_out.bias)
+        blocks = []
+        for b in m.transformer_blocks:
+            Q = {}
+            for i, ln in enumerate((b.norm1, b.norm2, b.norm3), 1):
+                Q[f"ln{i}"] = (f(ln.weight), f(ln.bias))
+            a1, a2 = b.attn1, b.attn2
+            Q["qkv1"] = torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0).detach().to(torch.float16).contiguous()
+            Q["o1_w"], Q["o1_b"] = ops.pack_linear(a1.to_out[0].weight.detach()), f(a1.to_out[0].bias)
+            if m.kind == "T":
+                Q["qkv2"] = torch.cat([a2.to_q.weight, a2.to_k.weight, a2.to_v.weight], 0).detach().to(torch.float16).contiguous()
+            else:
+                Q["q2"] = ops.pack_linear(a2.to_q.weight.detach())
+                Q["kv_txt"] = torch.cat([a2.to_k.weight, a2.to_v.weight], 0).detach().to(torch.float16).contiguous()
+                if hasattr(a2, "to_k_ip"):
+                    Q["kv_img"] = torch.cat([a2.to_k_ip.weight, a2.to_v_ip.weight], 0).detach().to(torch.float16).contiguous()
+            Q["o2_w"], Q["o2_b"] = ops.pack_linear(a2.to_out[0].weight.detach()), f(a2.to_out[0].bias)
+            Q["ff1_w"], Q["ff1_b"] = ops.pack_geglu(b.ff.net[0].proj.weight.detach(), b.ff.net[0].proj.bias.detach())
+            Q["ff2_w"], Q["ff2_b"] = ops.pack_linear(b.ff.net[2].weight.detach()), f(b.ff.net[2].bias)
+            blocks.append(Q)
+        P["blocks"] = blocks
+        return P
+
+    def _pack_stage(self, stage: nn.Sequential):
+        f = self._f32
+        out = []
+        for m in stage:
+            if isinstance(m, _Res):
+                out.append(self._pack_res(m))
+            elif isinstance(m, _Transformer):
+                out.append(self._pack_tf(m))
+            elif isinstance(m, _Down):
+                w = m.op.weight.detach()
+                out.append(dict(kind="D", w=w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.float16).contiguous(), b=f(m.op.bias)))
+            elif isinstance(m, _Up):
+                out.append(dict(kind="U", w=ops.pack_conv3x3(m.conv.weight.detach()), b=f(m.conv.bias)))
+            elif isinstance(m, nn.Conv2d):
+                out.append(dict(kind="C", w=ops.pack_conv3x3(m.weight.detach(), k_pad=8), b=f(m.bias), cin=m.in_channels))
+            else:
+                raise TypeError(type(m))
+        return out
+
+    def _pack(self):
+        f = self._f32
+        dev = self.time_embed[0].weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("viewcrafter_b200.UNetModel runs only on a CUDA (sm_100a) device; there is no CPU path")
+        P = dict(device=dev)
+        P["time"] = [f(self.time_embed[0].weight), f(self.time_embed[0].bias), f(self.time_embed[2].weight), f(self.time_embed[2].bias)]
+        if self.fs_condition:
+            P["fps"] = [f(self.fps_embedding[0].weight), f(self.fps_embedding[0].bias), f(self.fps_embedding[2].weight), f(self.fps_embedding[2].bias)]
+        P["input"] = [self._pack_stage(s) for s in self.input_blocks]
+        if self.addition_attention:
+            P["init_attn"] = self._pack_stage(self.init_attn)
+        P["middle"] = self._pack_stage(self.middle_block)
+        P["output"] = [self._pack_stage(s) for s in self.output_blocks]
+        P["out_gn"] = (f(self.out[0].weight), f(self.out[0].bias))
+        P["out_w"], P["out_b"] = ops.pack_conv3x3(self.out[2].weight.detach()), f(self.out[2].bias)
+        self._packed = P
+        return P
+
+    # ------------------------------------------------------------------------------------------
+    # block executors (operate on row matrices)
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _res(P, h, skip, emb, B, T, H, W):
+        BT, HW = B * T, H * W
+        a = ops.groupnorm(h, BT, *P["gn1"], 1e-5, True, x2=skip)
+        bias1 = ops.small_linear(emb, P["emb_w"], P["emb_b"], silu_in=True)            # [B, Cout] = emb_layers + conv1 bias
+        h1 = ops.conv3x3(a, BT, H, W, P["w1"], bias=bias1, bias_z_div=T)
+        b = ops.groupnorm(h1, BT, *P["gn2"], 1e-5, True)
+        if "skip_w" in P:
+            xs = ops.linear(h, P["skip_w"], bias=P["skip_b"], x2=skip)
+        else:
+            xs = h
+        h2 = ops.conv3x3(b, BT, H, W, P["w2"], bias=P["b2"], res=xs)
+        if "tconv" in P:
+            t = h2
+            for i, (g, be, w3, b3) in enumerate(P["tconv"]):
+                t = ops.groupnorm(t, B, g, be, 1e-5, True)                                # statistics over (C/32, T, H, W)
+                t = ops.conv_temporal(t, B, T, HW, w3, bias=b3, res=h2 if i == 3 else None)
+            h2 = t
+        return h2
+
+    @staticmethod
+    def _spatial_tf(P, h, ctx, B, T, H, W):
+        BT, HW, heads = B * T, H * W, P["heads"]
+        C = heads * 64
+        x = ops.linear(ops.groupnorm(h, BT, *P["gn"], 1e-6, False), P["in_w"], bias=P["in_b"])
+        for Q in P["blocks"]:
+            qkv = ops.linear(ops.layernorm(x, *Q["ln1"]), Q["qkv1"])
+            a = ops.flash_attn(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], BT, HW, HW, heads)
+            x = ops.linear(a, Q["o1_w"], bias=Q["o1_b"], res=x)
+            q = ops.linear(ops.layernorm(x, *Q["ln2"]), Q["q2"])
+            a = torch.empty_like(q)
+            for b in range(B):
+                rows = slice(b * T * HW, (b + 1) * T * HW)
+                kv = ops.linear(ctx["text"][b], Q["kv_txt"])                            # [77, 2C]
+                ops.flash_attn(q[rows], kv[:, :C], kv[:, C:], T, HW, kv.shape[0], heads, kv_shared=True, out=a[rows])
+                if "kv_img" in Q and ctx["img"] is not None:
+                    ki = ops.linear(ctx["img"][b], Q["kv_img"])                         # [256, 2C] or [T*16, 2C]
+                    if ctx["img_per_frame"]:
+                        ops.flash_attn(q[rows], ki[:, :C], ki[:, C:], T, HW, ki.shape[0] // T, heads, out=a[rows], accumulate=True)
+                    else:
+                        ops.flash_attn(q[rows], ki[:, :C], ki[:, C:], T, HW, ki.shape[0], heads, kv_shared=True, out=a[rows], accumulate=True)
+            x = ops.linear(a, Q["o2_w"], bias=Q["o2_b"], res=x)
+            g = ops.linear(ops.layernorm(x, *Q["ln3"]), Q["ff1_w"], bias=Q["ff1_b"], geglu=True)
+            x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x)
+        return ops.linear(x, P["out_w"], bias=P["out_b"], res=h)
+
+    @staticmethod
+    def _temporal_tf(P, h, B, T, H, W):
+        HW, heads = H * W, P["heads"]
+        C = heads * 64
+        x = ops.linear(ops.groupnorm(h, B, *P["gn"], 1e-6, False), P["in_w"], bias=P["in_b"])
+        for Q in P["blocks"]:
+            for ln, wqkv, ow, ob in (("ln1", "qkv1", "o1_w", "o1_b"), ("ln2", "qkv2", "o2_w", "o2_b")):
+                qkv = ops.linear(ops.layernorm(x, *Q[ln]), Q[wqkv])
+                a = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=torch.float16)
+                for b in range(B):
+                    rows = slice(b * T * HW, (b + 1) * T * HW)
+                    a[rows] = ops.temporal_attn(qkv[rows, :C], qkv[rows, C:2 * C], qkv[rows, 2 * C:], T, HW, heads)
+                x = ops.linear(a, Q[ow], bias=Q[ob], res=x)
+            g = ops.linear(ops.layernorm(x, *Q["ln3"]), Q["ff1_w"], bias=Q["ff1_b"], geglu=True)
+            x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x)
+        return ops.linear(x, P["out_w"], bias=P["out_b"], res=h)
+
+    def _run_stage(self, stage, h, skip, emb, ctx, B, T, H, W):
+        for P in stage:
+            k = P["kind"]
+            if k == "R":
+                h = self._res(P, h, skip, emb, B, T, H, W)
+                skip = None
+            elif k == "S":
+                h = self._spatial_tf(P, h, ctx, B, T, H, W)
+            elif k == "T":
+                h = self._temporal_tf(P, h, B, T, H, W)
+            elif k == "D":
+                cols, H, W = ops.im2col_s2(h, B * T, H, W)
+                h = ops.linear(cols, P["w"], bias=P["b"])
+            elif k == "U":
+                h = ops.conv3x3(ops.upsample2x(h, B * T, H, W), B * T, 2 * H, 2 * W, P["w"], bias=P["b"])
+                H, W = 2 * H, 2 * W
+            elif k == "C":
+                h = ops.conv3x3(h, B * T, H, W, P["w"], bias=P["b"])
+        return h, H, W
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, timesteps, context=None, features_adapter=None, fs=None, **kwargs):
+        """x [B,in_channels,T,H,W], timesteps [B] long, context [B,L,context_dim], fs [B] long -> [B,out_channels,T,H,W]
+        in x.dtype (openaimodel3d.py:548-603).  Extra kwargs are accepted and ignored like the reference does."""
+        if features_adapter is not None:
+            _unsupported("features_adapter")
+        P = self._packed or self._pack()
+        B, Cin, T, H, W = x.shape
+        dev = x.device
+        x32 = x.float().contiguous()
+        # --- embeddings (fp32) : time_embed(t) + fps_embedding(fs), one row per batch element (frame-invariant) ---
+        ts = timesteps.to(device=dev, dtype=torch.int64).contiguous()
+        tw = P["time"]
+        emb = ops.small_linear(ops.small_linear(ops.timestep_embedding(ts, self.model_channels), tw[0], tw[1]), tw[2], tw[3], silu_in=True)
+        if self.fs_condition:
+            if fs is None:
+                fs = torch.full((B,), self.default_fs, dtype=torch.int64, device=dev)
+            fw = P["fps"]
+            f1 = ops.small_linear(ops.timestep_embedding(fs.to(device=dev, dtype=torch.int64).contiguous(), self.model_channels), fw[0], fw[1])
+            emb = ops.small_linear(f1, fw[2], fw[3], silu_in=True, add=emb)
+        # --- context: text[:77] | image tokens; per-frame image tokens when L == 77 + 16*T (openaimodel3d.py:556-560) ---
+        ctx16 = ops.cast_f16(context.float().contiguous())
+        L = context.shape[1]
+        ctx = dict(text=[ctx16[b, :77] for b in range(B)], img=[ctx16[b, 77:] for b in range(B)] if L > 77 else None,
+                   img_per_frame=(L == 77 + T * 16))
+        # --- input latent -> rows [(b t) h w, Cin padded to 8] ---
+        cin_pad = max(8, (Cin + 7) // 8 * 8)
+        h = torch.zeros((B * T * H * W, cin_pad), device=dev, dtype=torch.float16) if cin_pad != Cin else \
+            torch.empty((B * T * H * W, cin_pad), device=dev, dtype=torch.float16)
+        ops.ncthw_to_rows(x32, h, 0)
+
+        hs = []
+        for i, stage in enumerate(P["input"]):
+            h, H, W = self._run_stage(stage, h, None, emb, ctx, B, T, H, W)
+            if i == 0 and self.addition_attention:
+                h, H, W = self._run_stage(P["init_attn"], h, None, emb, ctx, B, T, H, W)
+            hs.append(h)
+        h, H, W = self._run_stage(P["middle"], h, None, emb, ctx, B, T, H, W)
+        for stage in P["output"]:
+            h, H, W = self._run_stage(stage, h, hs.pop(), emb, ctx, B, T, H, W)
+        y = ops.conv3x3(ops.groupnorm(h, B * T, *P["out_gn"], 1e-5, True), B * T, H, W, P["out_w"], bias=P["out_b"], out_f32=True)
+        return ops.rows_to_ncthw(y, B, self.out_channels, T, H, W).to(x.dtype)
