@@ -89,6 +89,9 @@ int vc_groupnorm_nhwc(const void* x1, int32_t C1, const void* x2, int32_t C2, in
 int vc_layernorm(const void* x, int64_t rows, int32_t C, const float* gamma, const float* beta, float eps, void* out,
                  void* stream);
 
+/* row softmax of fp32 scores (pre-scaled by `scale`) to fp16 probabilities: the VAE AttnBlock, ae_modules.py:66-68 */
+int vc_softmax_rows_f32(const float* x, int64_t rows, int64_t cols, float scale, void* out, void* stream);
+
 /* ---- data movement ----------------------------------------------------------------------------------------------- */
 int vc_upsample2x_nhwc(const void* x, void* out, int32_t N, int32_t H, int32_t W, int32_t C, void* stream); /* F.interpolate nearest x2 */
 int vc_im2col3x3_s2(const void* x, void* out, int32_t N, int32_t H, int32_t W, int32_t C, int32_t pad_lo, int32_t Ho, int32_t Wo,

@@ -4,7 +4,7 @@
 
 Tolerance (stated, see DESIGN.md "Numerics"): activations are fp16 with fp32 accumulation, the reference runs the
 same graph under torch.cuda.amp.autocast (fp16 GEMMs, fp32 norms).  For these synthetic weights the output has
-std ~0.5-0.6; we require max|err| <= 0.04 and mean|err| <= 0.004 against the fp32 reference, i.e. < 7% / 0.7% of
+std ~0.5-0.6; we require max|err| <= 0.02 and mean|err| <= 0.003 against the fp32 reference (measured: 0.007 / 0.0012), i.e. < 4% / 0.6% of
 the output std -- the level autocast itself sits at for a ~150-GEMM-deep fp16 network.
 """
 import json
@@ -23,7 +23,7 @@ UNET_KW = dict(in_channels=8, out_channels=4, model_channels=320, attention_reso
                use_relative_position=False, use_causal_attention=False, temporal_length=16,
                addition_attention=True, image_cross_attention=True, default_fs=10, fs_condition=True)
 
-MAX_ERR, MEAN_ERR = 0.04, 0.004
+MAX_ERR, MEAN_ERR = 0.02, 0.003
 
 
 def _build(over, shapes, seed):

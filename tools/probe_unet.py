@@ -3,7 +3,7 @@ import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from viewcrafter_b200.unet import UNetModel
-from tests.test_unet_gpu import UNET_KW
+from viewcrafter_b200.configs import UNET_PARAMS as UNET_KW
 
 T, H, W = [int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (25, 72, 128))]
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 3

@@ -98,6 +98,11 @@ int vc_add_f16(const void* a, const void* b, void* out, int64_t n, void* stream)
   return add_rows_f16(H(a), H(b), HM(out), n, ST(stream));
 }
 
+int vc_softmax_rows_f32(const float* x, int64_t rows, int64_t cols, float scale, void* out, void* stream) {
+  COUNT(1);
+  return softmax_rows_f32(x, rows, cols, scale, HM(out), ST(stream));
+}
+
 int vc_timestep_embedding(const int64_t* t, int32_t n, int32_t dim, float* out, void* stream) {
   COUNT(1);
   return timestep_embedding_f32(reinterpret_cast<const long long*>(t), n, dim, out, ST(stream));

@@ -375,4 +375,41 @@ int ddim_update(const float* x, const float* v_cond, const float* v_uncond, cons
   return VC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// row softmax (fp32 scores -> fp16 probabilities) for the VAE's single-head d=512 AttnBlock (ae_modules.py:66-68)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, long long cols, float scale, __half* __restrict__ out) {
+  __shared__ float red[8];
+  const float* xr = x + (long long)blockIdx.x * cols;
+  __half* orow = out + (long long)blockIdx.x * cols;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  float m = -INFINITY;
+  for (long long i = tid; i < cols; i += 256) m = fmaxf(m, xr[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[w] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float l = 0.f;
+  for (long long i = tid; i < cols; i += 256) l += __expf((xr[i] - m) * scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if (lane == 0) red[w] = l;
+  __syncthreads();
+  l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) l += red[i];
+  const float inv = 1.f / l;
+  for (long long i = tid; i < cols; i += 256) orow[i] = __float2half_rn(__expf((xr[i] - m) * scale) * inv);
+}
+int softmax_rows_f32(const float* x, long long rows, long long cols, float scale, __half* out, cudaStream_t stream) {
+  VC_REQUIRE(x && out && rows > 0 && cols > 0 && scale > 0.f, "softmax_rows: bad args");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, stream>>>(x, cols, scale, out);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
 }  // namespace vc

@@ -1,0 +1,172 @@
+"""Drop-in ``DDIMSampler`` (reference: lvdm/models/samplers/ddim.py:10-281).
+
+Same constructor, ``make_schedule`` / ``sample`` / ``ddim_sampling`` / ``p_sample_ddim`` signatures and return values
+(``(samples, {'x_inter': [...], 'pred_x0': [...]})``).  Host logic (schedule tables, loop, RNG draws with the same
+shapes in the same order) is Python; everything after the two ``apply_model`` calls of a step -- CFG combine,
+guidance rescale (two global unbiased stds), v->(eps, x0), dynamic rescale, x_{t-1} -- is ONE fused CUDA update
+(vc_ddim_update).  ``batch_cfg=True`` runs cond+uncond as a single B=2 U-Net forward.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops, schedule
+
+
+class DDIMSampler(object):
+    def __init__(self, model, schedule="linear", batch_cfg: bool = False, **kwargs):
+        super().__init__()
+        self.model = model
+        self.ddpm_num_timesteps = model.num_timesteps
+        self.schedule = schedule
+        self.counter = 0
+        self.batch_cfg = batch_cfg
+
+    def register_buffer(self, name, attr):
+        if isinstance(attr, torch.Tensor) and attr.device != self._device():
+            attr = attr.to(self._device())
+        setattr(self, name, attr)
+
+    def _device(self):
+        return self.model.betas.device
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
+        m = self.model
+        self.ddim_timesteps = schedule.ddim_timesteps(ddim_discretize, ddim_num_steps, self.ddpm_num_timesteps)
+        ac = m.alphas_cumprod
+        assert ac.shape[0] == self.ddpm_num_timesteps, 'alphas have to be defined for each timestep'
+        ac_cpu = ac.detach().to(torch.float32).cpu()
+        self.use_dynamic_rescale = bool(getattr(m, "use_dynamic_rescale", False))
+        if self.use_dynamic_rescale:
+            arr = m.scale_arr.detach().float().cpu()
+            self.ddim_scale_arr = arr[self.ddim_timesteps]
+            self.ddim_scale_arr_prev = torch.cat([arr[0:1], self.ddim_scale_arr[:-1]])
+        f32dev = lambda x: x.clone().detach().to(torch.float32).to(self._device())
+        self.register_buffer('betas', f32dev(m.betas))
+        self.register_buffer('alphas_cumprod', f32dev(ac))
+        self.register_buffer('alphas_cumprod_prev', f32dev(m.alphas_cumprod_prev))
+        self.register_buffer('sqrt_alphas_cumprod', f32dev(torch.sqrt(ac_cpu)))
+        self.register_buffer('sqrt_one_minus_alphas_cumprod', f32dev(torch.sqrt(1. - ac_cpu)))
+        sigmas, alphas, alphas_prev = schedule.ddim_parameters(ac_cpu, self.ddim_timesteps, ddim_eta)
+        self.ddim_sigmas, self.ddim_alphas, self.ddim_alphas_prev = sigmas, alphas, alphas_prev
+        self.ddim_sqrt_one_minus_alphas = np.sqrt(1. - alphas)
+        # host copies of the model tables gathered by timestep t in the v-parameterisation (ddpm3d.py:239-251)
+        self._sqrt_ac = m.sqrt_alphas_cumprod.detach().float().cpu()
+        self._sqrt_1mac = m.sqrt_one_minus_alphas_cumprod.detach().float().cpu()
+        if verbose:
+            print(f'Selected timesteps for ddim sampler: {self.ddim_timesteps}')
+
+    def step_scalars(self, index: int, step: int) -> dict:
+        """The per-step fp32 scalars exactly as p_sample_ddim materialises them with torch.full (ddim.py:253-266)."""
+        r = schedule.f32
+        d = dict(a_t=r(self.ddim_alphas[index]), a_prev=r(self.ddim_alphas_prev[index]), sigma_t=r(self.ddim_sigmas[index]),
+                 sqrt_one_minus_at=r(self.ddim_sqrt_one_minus_alphas[index]),
+                 sqrt_ac_t=float(self._sqrt_ac[step]), sqrt_1mac_t=float(self._sqrt_1mac[step]))
+        if self.use_dynamic_rescale:
+            d["scale_t"], d["prev_scale_t"] = r(self.ddim_scale_arr[index]), r(self.ddim_scale_arr_prev[index])
+        else:
+            d["scale_t"] = d["prev_scale_t"] = 1.0
+        return d
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None,
+               quantize_x0=False, eta=0., mask=None, x0=None, temperature=1., noise_dropout=0., score_corrector=None,
+               corrector_kwargs=None, verbose=True, schedule_verbose=False, x_T=None, log_every_t=100,
+               unconditional_guidance_scale=1., unconditional_conditioning=None, precision=None, fs=None,
+               timestep_spacing='uniform', guidance_rescale=0.0, **kwargs):
+        if conditioning is not None:
+            first = conditioning[list(conditioning.keys())[0]] if isinstance(conditioning, dict) else conditioning
+            try:
+                cbs = first.shape[0]
+            except AttributeError:
+                cbs = first[0].shape[0]
+            if cbs != batch_size:
+                print(f"Warning: Got {cbs} conditionings but batch-size is {batch_size}")
+        self.make_schedule(ddim_num_steps=S, ddim_discretize=timestep_spacing, ddim_eta=eta, verbose=schedule_verbose)
+        if len(shape) == 3:
+            size = (batch_size, *shape)
+        elif len(shape) == 4:
+            size = (batch_size, *shape)
+        else:
+            raise ValueError(f"shape must be (C,H,W) or (C,T,H,W), got {shape}")
+        return self.ddim_sampling(conditioning, size, callback=callback, img_callback=img_callback, quantize_denoised=quantize_x0,
+                                  mask=mask, x0=x0, ddim_use_original_steps=False, noise_dropout=noise_dropout,
+                                  temperature=temperature, score_corrector=score_corrector, corrector_kwargs=corrector_kwargs,
+                                  x_T=x_T, log_every_t=log_every_t, unconditional_guidance_scale=unconditional_guidance_scale,
+                                  unconditional_conditioning=unconditional_conditioning, verbose=verbose, precision=precision,
+                                  fs=fs, guidance_rescale=guidance_rescale, **kwargs)
+
+    @torch.no_grad()
+    def ddim_sampling(self, cond, shape, x_T=None, ddim_use_original_steps=False, callback=None, timesteps=None,
+                      quantize_denoised=False, mask=None, x0=None, img_callback=None, log_every_t=100, temperature=1.,
+                      noise_dropout=0., score_corrector=None, corrector_kwargs=None, unconditional_guidance_scale=1.,
+                      unconditional_conditioning=None, verbose=True, precision=None, fs=None, guidance_rescale=0.0, **kwargs):
+        if ddim_use_original_steps or timesteps is not None:
+            raise NotImplementedError("viewcrafter_b200.DDIMSampler: only the DDIM sub-sequence path is implemented")
+        if mask is not None:
+            raise NotImplementedError("viewcrafter_b200.DDIMSampler: mask/x0 blending is not on the ViewCrafter path (mask=None)")
+        device = self._device()
+        b = shape[0]
+        img = torch.randn(shape, device=device) if x_T is None else x_T
+        steps = self.ddim_timesteps
+        total = steps.shape[0]
+        intermediates = {'x_inter': [img], 'pred_x0': [img]}
+        kwargs.pop("clean_cond", None)
+        for i, step in enumerate(np.flip(steps)):
+            index = total - i - 1
+            ts = torch.full((b,), int(step), device=device, dtype=torch.long)
+            img, pred_x0 = self.p_sample_ddim(img, cond, ts, index=index, quantize_denoised=quantize_denoised,
+                                              temperature=temperature, noise_dropout=noise_dropout,
+                                              score_corrector=score_corrector, corrector_kwargs=corrector_kwargs,
+                                              unconditional_guidance_scale=unconditional_guidance_scale,
+                                              unconditional_conditioning=unconditional_conditioning, fs=fs,
+                                              guidance_rescale=guidance_rescale, _step=int(step), **kwargs)
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(pred_x0, i)
+            if index % log_every_t == 0 or index == total - 1:
+                intermediates['x_inter'].append(img)
+                intermediates['pred_x0'].append(pred_x0)
+        return img, intermediates
+
+    def _apply_both(self, x, t, c, uc, kwargs):
+        """cond + uncond as one B=2 forward when every conditioning entry can be stacked; else two calls (ddim.py:223-224)."""
+        if self.batch_cfg and isinstance(c, dict) and isinstance(uc, dict) and c.keys() == uc.keys():
+            cat = {k: [torch.cat([a, u], 0) for a, u in zip(c[k], uc[k])] for k in c}
+            kw = {k: (torch.cat([v, v], 0) if isinstance(v, torch.Tensor) and v.dim() >= 1 and v.shape[0] == x.shape[0] else v)
+                  for k, v in kwargs.items()}
+            out = self.model.apply_model(torch.cat([x, x], 0), torch.cat([t, t], 0), cat, **kw)
+            n = x.shape[0]
+            return out[:n].contiguous(), out[n:].contiguous()
+        return self.model.apply_model(x, t, c, **kwargs), self.model.apply_model(x, t, uc, **kwargs)
+
+    @torch.no_grad()
+    def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
+                      temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
+                      unconditional_guidance_scale=1., unconditional_conditioning=None, uc_type=None,
+                      conditional_guidance_scale_temporal=None, mask=None, x0=None, guidance_rescale=0.0, _step=None, **kwargs):
+        if use_original_steps or quantize_denoised or score_corrector is not None or noise_dropout > 0.:
+            raise NotImplementedError("viewcrafter_b200.DDIMSampler: option not on the ViewCrafter inference path")
+        if getattr(self.model, "parameterization", "v") != "v":
+            raise NotImplementedError("viewcrafter_b200.DDIMSampler: only the v-parameterisation is implemented")
+        if x.shape[0] != 1 and guidance_rescale > 0.0 and unconditional_conditioning is not None:
+            raise NotImplementedError("guidance rescale statistics are per sample; run batch size 1 (configs/infer_config.py:35)")
+        step = int(t[0].item()) if _step is None else _step
+        if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
+            v_c, v_u = self.model.apply_model(x, t, c, **kwargs), None
+        else:
+            if not isinstance(c, (torch.Tensor, dict)):
+                raise NotImplementedError
+            v_c, v_u = self._apply_both(x, t, c, unconditional_conditioning, kwargs)
+        sc = self.step_scalars(index, step)
+        sc["cfg_scale"], sc["guidance_rescale"] = float(unconditional_guidance_scale), float(guidance_rescale)
+        shape = (1, *x.shape[1:]) if repeat_noise else x.shape
+        noise = torch.randn(shape, device=x.device)                      # same draw as lvdm/common.py:31-34
+        if repeat_noise:
+            noise = noise.repeat(x.shape[0], *((1,) * (x.dim() - 1)))
+        if temperature != 1.:
+            noise = noise * temperature
+        return ops.ddim_update(x.float().contiguous(), v_c.float().contiguous(), None if v_u is None else v_u.float().contiguous(),
+                               noise.contiguous(), sc)

@@ -240,6 +240,14 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
+def softmax_rows(x: torch.Tensor, scale: float) -> torch.Tensor:
+    """softmax(x*scale, dim=-1) of fp32 scores -> fp16."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    check(_lib.load().vc_softmax_rows_f32(x.data_ptr(), x.shape[0], x.shape[1], scale, out.data_ptr(), _stream()), "vc_softmax_rows_f32")
+    return out
+
+
 def upsample2x(x: torch.Tensor, N: int, H: int, W: int) -> torch.Tensor:
     _chk16(x, "upsample.x")
     Cc = x.shape[1]
