@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- DDIM denoise-steps/sec of the ViewCrafter hot path on B200 (contract: task brief, BASELINE.json).
+
+    python bench.py --gpus 1 --steps 4 --warmup 3                 # our arm, headline workload 25x4x72x128
+    python bench.py --impl reference --steps 2 --warmup 1         # the reference's algorithm on the host CPU cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # frame/CFG-sharded, N in {2,4,8}
+
+One "step" = one DDIMSampler.p_sample_ddim: 2 U-Net forwards (cond + uncond, CFG 7.5), guidance rescale 0.7,
+v-prediction update with eta=1 noise.  Data is synthetic (random-init weights of the shipped architecture with the
+zero-initialised tensors re-drawn, random latents / render-latents / context), as BASELINE.md config 3 specifies.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "ViewCrafter_25": dict(T=25, H=72, W=128, base_scale=0.3, px="576x1024"),
+    "ViewCrafter_25_512": dict(T=25, H=40, W=64, base_scale=0.7, px="320x512"),
+    "ViewCrafter_16": dict(T=16, H=72, W=128, base_scale=0.3, px="576x1024"),
+}
+UNET_FWD_TFLOP = {"ViewCrafter_25": 82.76, "ViewCrafter_25_512": 20.19, "ViewCrafter_16": 52.34}   # SURVEY.md 8(d) / BASELINE.md 2
+A100_README_STEPS_PER_S = {"ViewCrafter_25": 50 / 120.0, "ViewCrafter_25_512": 50 / 50.0, "ViewCrafter_16": 50 / 75.0}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops_burst=d["bf16_tflops"], tflops_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def build_model(wl, device):
+    from viewcrafter_b200.configs import UNET_PARAMS
+    from viewcrafter_b200.diffusion import LatentDiffusion
+    torch.manual_seed(0)
+    with torch.device(device):
+        model = LatentDiffusion(UNET_PARAMS, None, base_scale=wl["base_scale"])
+    g = torch.Generator(device=device).manual_seed(1)
+    with torch.no_grad():
+        for p in model.parameters():                       # zero-init layers would make the network output exactly 0
+            if float(p.detach().abs().max()) == 0.0:
+                p.copy_(torch.randn(p.shape, generator=g, device=device) * 0.02)
+    return model.eval()
+
+
+def synthetic_inputs(wl, device, pinned=False):
+    g = torch.Generator().manual_seed(2)
+    T, H, W = wl["T"], wl["H"], wl["W"]
+    mk = lambda *s: torch.randn(*s, generator=g)
+    host = dict(x_T=mk(1, 4, T, H, W), c_concat=mk(1, 4, T, H, W), ctx_c=mk(1, 333, 1024), ctx_u=mk(1, 333, 1024))
+    if pinned:
+        host = {k: v.pin_memory() for k, v in host.items()}
+    dev = {k: v.to(device) for k, v in host.items()}
+    return host, dev
+
+
+def conds(d, fs):
+    c = {"c_crossattn": [d["ctx_c"]], "c_concat": [d["c_concat"]]}
+    uc = {"c_crossattn": [d["ctx_u"]], "c_concat": [d["c_concat"]]}
+    return c, uc
+
+
+def time_kernel(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def kernel_rooflines(wl, device, peaks):
+    """Dominant kernels timed alone with CUDA events on the launching (current) stream; operands exceed L2 (126 MB)."""
+    from viewcrafter_b200 import ops
+    T, H, W = wl["T"], wl["H"], wl["W"]
+    M, C = T * H * W, 320
+    x = torch.randn(M, C, device=device).half()
+    w9 = (torch.randn(9 * C, C, device=device) * 0.02).half()
+    t_conv = time_kernel(lambda: ops.conv3x3(x, T, H, W, w9))
+    fl_conv = 2.0 * M * 9 * C * C
+    heads = 5
+    qkv = torch.randn(M, 3 * C, device=device).half()
+    t_att = time_kernel(lambda: ops.flash_attn(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], T, H * W, H * W, heads))
+    fl_att = 4.0 * T * heads * (H * W) ** 2 * 64
+    gam, bet = torch.ones(C, device=device), torch.zeros(C, device=device)
+    t_gn = time_kernel(lambda: ops.groupnorm(x, T, gam, bet, 1e-5, True))
+    by_gn = 2.0 * M * C * 2                                     # algorithmic: read once + write once, fp16
+    r = {
+        "roofline": {"kernel": "gemm_tap_kernel<160> (3x3 conv 320->320 @%dx%dx%d)" % (T, H, W), "bound": "tensor",
+                     "achieved": fl_conv / t_conv / 1e12, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+                     "frac": fl_conv / t_conv / 1e12 / peaks["tflops_burst"], "traffic": None, "ms": t_conv * 1e3,
+                     "peak_source": peaks["src"] + " cuBLAS bf16 burst"},
+        "roofline_attention": {"kernel": "flash_attn_d64_kernel (spatial self-attn, %d heads, N=%d)" % (heads, H * W), "bound": "tensor",
+                               "achieved": fl_att / t_att / 1e12, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+                               "frac": fl_att / t_att / 1e12 / peaks["tflops_burst"], "traffic": None, "ms": t_att * 1e3},
+        "roofline_groupnorm": {"kernel": "gn_stats_kernel+gn_apply_kernel (GroupNorm32+SiLU, C=320)", "bound": "hbm",
+                               "achieved": by_gn / t_gn / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": by_gn / t_gn / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms": t_gn * 1e3},
+    }
+    return r
+
+
+def cpu_oracle_sample(wl, sd_cpu, steps, warmup, workload_name):
+    """The reference's algorithm (oracle port, fp32 torch-CPU, all host threads) on a bounded sample of the workload:
+    one CFG DDIM step at a reduced latent size; scaled to headline-equivalent steps/s by the analytical FLOP ratio."""
+    from oracle import lvdm_oracle as O
+    from viewcrafter_b200.configs import UNET_PARAMS
+    from viewcrafter_b200.flops import unet_forward_flops
+    from viewcrafter_b200.unet import UNetModel
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    T, Hs, Ws = wl["T"], 8, 16
+    with torch.device("meta"):
+        meta = UNetModel(**UNET_PARAMS)
+    f_sample = 2 * unet_forward_flops(meta, T, Hs, Ws)["total"]
+    f_full = 2 * unet_forward_flops(meta, T, wl["H"], wl["W"])["total"]
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 4, T, Hs, Ws, generator=g)
+    cc = torch.randn(1, 4, T, Hs, Ws, generator=g)
+    ctx_c, ctx_u = torch.randn(1, 333, 1024, generator=g), torch.randn(1, 333, 1024, generator=g)
+    sched = O.model_schedule(base_scale=wl["base_scale"])
+    tab = O.ddim_tables(sched, 50, "uniform_trailing", 1.0)
+    fs = torch.tensor([10])
+
+    def one_step(index):
+        step = int(tab["timesteps"][index])
+        ts = torch.full((1,), step, dtype=torch.long)
+        xc = torch.cat([x, cc], 1)
+        with torch.no_grad():
+            v_c = O.unet_forward(sd_cpu, xc, ts, ctx_c, fs)
+            v_u = O.unet_forward(sd_cpu, xc, ts, ctx_u, fs)
+        sc = O.step_scalars(tab, index)
+        return O.ddim_update(x, v_c, v_u, sc, sched["sqrt_alphas_cumprod"][step].item(),
+                             sched["sqrt_one_minus_alphas_cumprod"][step].item(), torch.randn(x.shape, generator=g), 7.5, 0.7)
+
+    for i in range(warmup):
+        one_step(49 - i)
+    t0 = time.time()
+    for i in range(steps):
+        one_step(49 - warmup - i)
+    dt = (time.time() - t0) / max(steps, 1)
+    value = 1.0 / (dt * f_full / f_sample)
+    sample = ("one CFG DDIM step (2 U-Net forwards, full-width weights, fp32) at latent %dx4x%dx%d = %.3f TFLOP, %.2f s/step on %d threads; "
+              "scaled by the FLOP ratio %.1f to the %s workload" % (T, Hs, Ws, f_sample / 1e12, dt, cores, f_full / f_sample, workload_name))
+    return value, dt, cores, sample
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ViewCrafter_25", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch-cfg", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "DDIM denoise-steps/sec @ %sx%df" % (wl["px"], wl["T"])
+    config = {"workload": "%s: latent 1x4x%dx%dx%d, CFG 7.5 (2 U-Net forwards/step), guidance_rescale 0.7, eta 1.0, 50-step uniform_trailing schedule"
+                          % (args.workload, wl["T"], wl["H"], wl["W"]),
+              "l2": "working set per forward (tens of GB of activations, 2.9 GB weights) exceeds the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import synth
+        from viewcrafter_b200.configs import UNET_PARAMS
+        from viewcrafter_b200.unet import UNetModel
+        with torch.device("meta"):
+            shapes = [(k, tuple(v.shape)) for k, v in UNetModel(**UNET_PARAMS).state_dict().items()]
+        sd = synth.synth_state_dict(shapes, seed=0)
+        value, dt, cores, sample = cpu_oracle_sample(wl, sd, args.steps, args.warmup, args.workload)
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    from viewcrafter_b200 import _lib
+    from viewcrafter_b200.ddim import DDIMSampler
+    lib = _lib.load()
+    peaks = measured_peaks()
+
+    model = build_model(wl, device)
+    if world > 1:
+        from viewcrafter_b200 import parallel
+        parallel.shard_model(model, dist, rank, world)
+    sampler = DDIMSampler(model, batch_cfg=not args.no_batch_cfg)
+    sampler.make_schedule(50, "uniform_trailing", 1.0, verbose=False)
+    host, dev = synthetic_inputs(wl, device, pinned=True)
+    c, uc = conds(dev, None)
+    fs = torch.tensor([10], device=device, dtype=torch.long)
+    order = np.flip(sampler.ddim_timesteps)
+
+    def run_step(x, i, cc=c, uu=uc):
+        i = i % 50
+        index = 50 - i - 1
+        ts = torch.full((1,), int(order[i]), device=device, dtype=torch.long)
+        return sampler.p_sample_ddim(x, cc, ts, index=index, unconditional_guidance_scale=7.5, unconditional_conditioning=uu,
+                                     fs=fs, guidance_rescale=0.7, _step=int(order[i]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    x = dev["x_T"]
+    for i in range(args.warmup):
+        x, _ = run_step(x, i)
+    barrier()
+    lib.vc_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for i in range(args.steps):
+            x, _ = run_step(x, args.warmup + i)
+        e1.record()
+        barrier()
+    launches = int(lib.vc_launch_count())
+    t_dev = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=device, dtype=torch.float64)
+    finite = bool(torch.isfinite(x).all())
+
+    # ---- end to end through the sampler API with HOST buffers: H2D of the step inputs + D2H of x_{t-1} every step ----
+    out_host = torch.empty_like(host["x_T"]).pin_memory()
+    x_host = host["x_T"]
+    h2d = sum(host[k].numel() * 4 for k in ("x_T", "c_concat", "ctx_c", "ctx_u"))
+    d2h = out_host.numel() * 4
+
+    def e2e_step(i):
+        d = {k: host[k].to(device, non_blocking=True) for k in ("c_concat", "ctx_c", "ctx_u")}
+        xd = x_host.to(device, non_blocking=True)
+        cc, uu = conds(d, None)
+        xn, _ = run_step(xd, i, cc, uu)
+        out_host.copy_(xn, non_blocking=True)
+        torch.cuda.current_stream().synchronize()             # the caller reads the result
+        return out_host
+
+    for i in range(min(args.warmup, 2)):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(args.warmup + i)
+    f1.record()
+    barrier()
+    t_e2e = torch.tensor([f0.elapsed_time(f1) * 1e-3], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = args.steps / float(t_dev)
+    e2e_value = args.steps / float(t_e2e)
+    line = {"metric": metric, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16 (fp32 accumulate; fp32 norms/softmax/update)", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clk.summary(), "finite": finite,
+            "step_tflops": {"achieved": 2 * UNET_FWD_TFLOP[args.workload] * value, "peak_sustained": peaks["tflops_sustained"],
+                            "frac": 2 * UNET_FWD_TFLOP[args.workload] * value / peaks["tflops_sustained"],
+                            "note": "reference-algorithm FLOPs (SURVEY.md 8d: %.2f TFLOP per U-Net forward) / measured step time" % UNET_FWD_TFLOP[args.workload]},
+            "published_context": {"a100_readme_steps_per_s": A100_README_STEPS_PER_S[args.workload],
+                                  "speedup_vs_a100_readme": value / A100_README_STEPS_PER_S[args.workload],
+                                  "note": "README.md:117-122 (A100 40GB, whole-pipeline time / 50 steps); other hardware, so vs_baseline stays null"}}
+    if world == 1:
+        line.update(kernel_rooflines(wl, device, peaks))
+        if not args.no_cpu_baseline:
+            sd_cpu = {k: v.detach().float().cpu() for k, v in model.model.diffusion_model.state_dict().items()}
+            v, dt, cores, sample = cpu_oracle_sample(wl, sd_cpu, 1, 1, args.workload)
+            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

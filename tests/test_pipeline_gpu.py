@@ -1,0 +1,107 @@
+"""End-to-end parity on the GPU: DDIMSampler.sample over the CUDA U-Net and AutoencoderKL.decode vs the CPU oracle and
+the reference-generated golden fixtures.  Tolerances as in test_unet_gpu.py (fp16 activations, fp32 accumulate)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_smoke_entry_point():
+    _need_gpu()
+    from viewcrafter_b200 import selfcheck
+    e1, e2 = selfcheck.run_smoke(verbose=True)
+    assert e1 < 0.03 and e2 < 0.03
+
+
+def test_vae_decode_matches_reference_golden(golden_dir):
+    _need_gpu()
+    from oracle import synth
+    from viewcrafter_b200.autoencoder import AutoencoderKL
+    from viewcrafter_b200.configs import VAE_DDCONFIG
+    g = np.load(os.path.join(golden_dir, "vae_ch32.npz"))
+    vae = AutoencoderKL(dict(VAE_DDCONFIG, ch=32), None, 4)
+    shapes = [(n, tuple(s)) for n, s in json.loads(str(g["shapes"]))]
+    sd = {"decoder." + k: v for k, v in synth.synth_state_dict(shapes, seed=4).items()}
+    sd.update({"post_quant_conv." + k: v for k, v in synth.synth_state_dict([("weight", (4, 4, 1, 1)), ("bias", (4,))], 4).items()})
+    missing, unexpected = vae.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("encoder.", "quant_conv.")) for k in missing)
+    vae = vae.cuda().eval()
+    y = vae.decode(torch.from_numpy(g["z"]).cuda())
+    err = (y.cpu() - torch.from_numpy(g["y"])).abs()
+    print(f"vae ch32: max err {float(err.max()):.4g} mean {float(err.mean()):.4g} ref std {float(g['y'].std()):.3g}")
+    assert y.shape == g["y"].shape
+    assert float(err.max()) <= 0.03 and float(err.mean()) <= 0.003
+
+
+def test_vae_decode_full_width_vs_oracle():
+    """ch=128 (512/512/256/128 channel levels, d=512 attention) on a 16x24 latent: oracle finishes in seconds."""
+    _need_gpu()
+    from oracle import lvdm_oracle as O
+    from oracle import synth
+    from viewcrafter_b200.autoencoder import AutoencoderKL
+    from viewcrafter_b200.configs import VAE_DDCONFIG
+    vae = AutoencoderKL(VAE_DDCONFIG, None, 4)
+    sd = synth.synth_state_dict(synth.module_shapes(vae), seed=31)
+    vae.load_state_dict(sd, strict=True)
+    vae = vae.cuda().eval()
+    z = torch.randn(2, 4, 16, 24, generator=torch.Generator().manual_seed(32))
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = O.vae_decode(sd, z)
+    y = vae.decode(z.cuda())
+    err = (y.cpu() - ref).abs()
+    print(f"vae ch128: max err {float(err.max()):.4g} mean {float(err.mean()):.4g} ref std {float(ref.std()):.3g}")
+    assert float(err.max()) <= 0.03 * max(1.0, float(ref.std())) and float(err.mean()) <= 0.003 * max(1.0, float(ref.std()))
+
+
+@pytest.mark.parametrize("batch_cfg", [False, True])
+def test_ddim_sample_three_steps_vs_oracle(batch_cfg):
+    """DDIMSampler.sample (S=3, eta=1, CFG 7.5, rescale 0.7) with identical x_T and per-step noise on both sides."""
+    _need_gpu()
+    from oracle import lvdm_oracle as O
+    from oracle import synth
+    from viewcrafter_b200.configs import UNET_PARAMS
+    from viewcrafter_b200.ddim import DDIMSampler
+    from viewcrafter_b200.diffusion import LatentDiffusion
+    ucfg = dict(UNET_PARAMS); ucfg.update(model_channels=64)
+    model = LatentDiffusion(ucfg, None, base_scale=0.7)
+    unet = model.model.diffusion_model
+    sd = synth.synth_state_dict(synth.module_shapes(unet), seed=41)
+    unet.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(42)
+    T, H, W, S = 5, 8, 8, 3
+    shape = (1, 4, T, H, W)
+    x_T, cc = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    ctx_c, ctx_u = torch.randn(1, 333, 1024, generator=g), torch.randn(1, 333, 1024, generator=g)
+    fs = torch.tensor([10])
+    c = {"c_crossattn": [ctx_c.cuda()], "c_concat": [cc.cuda()]}
+    uc = {"c_crossattn": [ctx_u.cuda()], "c_concat": [cc.cuda()]}
+    sampler = DDIMSampler(model, batch_cfg=batch_cfg)
+    torch.manual_seed(43)
+    out, inter = sampler.sample(S=S, batch_size=1, shape=shape[1:], conditioning=c, eta=1.0, verbose=False, x_T=x_T.cuda(),
+                                unconditional_guidance_scale=7.5, unconditional_conditioning=uc, fs=fs.cuda(),
+                                timestep_spacing="uniform_trailing", guidance_rescale=0.7)
+    torch.manual_seed(43)
+    noises = [torch.randn(shape, device="cuda").cpu() for _ in range(S)]
+    sched = O.model_schedule(base_scale=0.7)
+
+    def model_fn(x, t, cond):
+        with torch.no_grad():
+            return O.unet_forward(sd, torch.cat([x, cc], 1), t, cond, fs)
+
+    ref, ref_inter = O.ddim_sample(model_fn, sched, shape, S, ctx_c, ctx_u, x_T, noises)
+    err = (out.cpu() - ref).abs()
+    print(f"ddim S=3 batch_cfg={batch_cfg}: max err {float(err.max()):.4g} mean {float(err.mean()):.4g} ref std {float(ref.std()):.3g}")
+    assert list(sampler.ddim_timesteps) == [332, 666, 999]
+    assert len(inter["x_inter"]) == len(ref_inter["x_inter"])
+    assert float(err.max()) <= 0.05 and float(err.mean()) <= 0.006

@@ -1,0 +1,67 @@
+"""smoke(): one tiny invocation of the hot path on cuda:0 checked against the CPU oracle
+(one CFG DDIM step = 2 U-Net forwards + fused update, then a VAE decode of the result)."""
+from __future__ import annotations
+
+import torch
+
+
+def run_smoke(verbose: bool = True):
+    from oracle import lvdm_oracle as O          # checker only (allowed in smoke())
+    from oracle import synth
+    from .configs import UNET_PARAMS, VAE_DDCONFIG
+    from .ddim import DDIMSampler
+    from .diffusion import LatentDiffusion
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("smoke() needs cuda:0 (no CPU fallback exists)")
+    torch.cuda.set_device(0)
+    ucfg = dict(UNET_PARAMS); ucfg.update(model_channels=64)
+    vcfg = dict(ddconfig=dict(VAE_DDCONFIG, ch=32), embed_dim=4)
+    model = LatentDiffusion(ucfg, vcfg, base_scale=0.3)
+    unet, vae = model.model.diffusion_model, model.first_stage_model
+    sd_u = synth.synth_state_dict(synth.module_shapes(unet), seed=21)
+    sd_v = synth.synth_state_dict(synth.module_shapes(vae), seed=22)
+    unet.load_state_dict(sd_u, strict=True)
+    vae.load_state_dict(sd_v, strict=True)
+    model = model.cuda().eval()
+
+    g = torch.Generator().manual_seed(23)
+    T, H, W = 4, 8, 16
+    x = torch.randn(1, 4, T, H, W, generator=g)
+    cc = torch.randn(1, 4, T, H, W, generator=g)
+    ctx_c, ctx_u = torch.randn(1, 333, 1024, generator=g), torch.randn(1, 333, 1024, generator=g)
+    fs = torch.tensor([10])
+    dev = lambda t: t.cuda()
+    c = {"c_crossattn": [dev(ctx_c)], "c_concat": [dev(cc)]}
+    uc = {"c_crossattn": [dev(ctx_u)], "c_concat": [dev(cc)]}
+
+    sampler = DDIMSampler(model)
+    sampler.make_schedule(5, "uniform_trailing", 1.0, verbose=False)
+    index, step = 2, int(sampler.ddim_timesteps[2])
+    ts = torch.full((1,), step, dtype=torch.long, device="cuda")
+    torch.manual_seed(24)
+    x_prev, pred_x0 = sampler.p_sample_ddim(dev(x), c, ts, index=index, unconditional_guidance_scale=7.5,
+                                            unconditional_conditioning=uc, fs=dev(fs), guidance_rescale=0.7)
+    torch.manual_seed(24)
+    noise = torch.randn(x.shape, device="cuda").cpu()            # the draw p_sample_ddim made
+
+    sched = O.model_schedule(base_scale=0.3)
+    tab = O.ddim_tables(sched, 5, "uniform_trailing", 1.0)
+    xc = torch.cat([x, cc], 1)
+    tcpu = torch.full((1,), step, dtype=torch.long)
+    with torch.no_grad():
+        v_c = O.unet_forward(sd_u, xc, tcpu, ctx_c, fs)
+        v_u = O.unet_forward(sd_u, xc, tcpu, ctx_u, fs)
+    ref_prev, ref_x0 = O.ddim_update(x, v_c, v_u, O.step_scalars(tab, index), sched["sqrt_alphas_cumprod"][step].item(),
+                                     sched["sqrt_one_minus_alphas_cumprod"][step].item(), noise, 7.5, 0.7)
+    e1 = float((x_prev.cpu() - ref_prev).abs().max())
+    img = model.decode_first_stage(pred_x0)
+    with torch.no_grad():
+        ref_img = O.decode_first_stage(sd_v, ref_x0)
+    e2 = float((img.cpu() - ref_img).abs().max())
+    if verbose:
+        print(f"smoke: DDIM step max|err| {e1:.4g} (x_prev std {float(ref_prev.std()):.3g}); "
+              f"VAE decode max|err| {e2:.4g} (image std {float(ref_img.std()):.3g})")
+    assert torch.isfinite(x_prev).all() and torch.isfinite(img).all()
+    assert e1 < 0.05 and e2 < 0.05, (e1, e2)
+    return e1, e2
