@@ -42,6 +42,7 @@ typedef struct vc_gemm_desc {
   int32_t bx, by;                    /* 128-row tile = bx * by pixels (by > 1 requires bx == X)          */
   int32_t K, K1;                     /* reduction per tap; K1 = channels served by `a` (== K if no a2)   */
   const void* w;                     /* fp16 weights [num_taps*N, K], K contiguous                       */
+  int32_t ldw;                       /* row pitch of w in elements (0 = K)                               */
   int32_t N;
   int32_t num_taps;                  /* 1 (linear), 3 (temporal conv), 9 (3x3 conv)                      */
   int32_t tap_dx[9], tap_dy[9];      /* per-tap shift of the tile origin along X / Y                     */

@@ -1,0 +1,117 @@
+"""Host logic of the drop-in classes on the CPU: the CUDA ops are replaced by the torch test double (tests/fake_ops.py)
+and the whole UNetModel / AutoencoderKL / DDIMSampler wiring is checked against the reference-generated goldens and the
+oracle.  This does not test the kernels (the -m gpu suite does); it tests packing, layouts, block order and loops."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lvdm_oracle as O
+from oracle import synth
+from tests import fake_ops
+from viewcrafter_b200.configs import UNET_PARAMS, VAE_DDCONFIG
+
+
+@pytest.fixture
+def cpu_ops(monkeypatch):
+    fake_ops.install(monkeypatch)
+    return fake_ops
+
+
+def test_product_refuses_cpu_without_the_double():
+    from viewcrafter_b200 import _lib
+    from viewcrafter_b200.unet import UNetModel
+    m = UNetModel(**dict(UNET_PARAMS, model_channels=64)).eval()
+    with pytest.raises(_lib.VcError):
+        m(torch.zeros(1, 8, 2, 8, 8), torch.tensor([1]), context=torch.zeros(1, 333, 1024))
+
+
+@pytest.mark.parametrize("name", ["mc64_T4", "mc64_T16"])
+def test_unet_wiring_matches_reference_golden(cpu_ops, golden_dir, name):
+    from viewcrafter_b200.unet import UNetModel
+    g = np.load(os.path.join(golden_dir, f"unet_{name}.npz"))
+    shapes = [(n, tuple(s)) for n, s in json.loads(str(g["shapes"]))]
+    kw = dict(UNET_PARAMS); kw.update(json.loads(str(g["kwargs"])))
+    m = UNetModel(**kw).eval()
+    m.load_state_dict(synth.synth_state_dict(shapes, 3), strict=True)
+    y = m(torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), context=torch.from_numpy(g["ctx"]), fs=torch.from_numpy(g["fs"]))
+    err = (y - torch.from_numpy(g["y"])).abs()
+    assert float(err.max()) < 0.02 and float(err.mean()) < 0.003, (float(err.max()), float(err.mean()))
+
+
+def test_unet_batch2_wiring(cpu_ops):
+    from viewcrafter_b200.unet import UNetModel
+    m = UNetModel(**dict(UNET_PARAMS, model_channels=64)).eval()
+    sd = synth.synth_state_dict(synth.module_shapes(m), 9)
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(10)
+    x, ctx, t = torch.randn(2, 8, 3, 8, 8, generator=g), torch.randn(2, 333, 1024, generator=g), torch.tensor([999, 19])
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, ctx, None, default_fs=10)
+    err = (m(x, t, context=ctx) - ref).abs()
+    assert float(err.max()) < 0.02, float(err.max())
+
+
+def test_vae_decode_wiring_matches_reference_golden(cpu_ops, golden_dir):
+    from viewcrafter_b200.autoencoder import AutoencoderKL
+    g = np.load(os.path.join(golden_dir, "vae_ch32.npz"))
+    vae = AutoencoderKL(dict(VAE_DDCONFIG, ch=32), None, 4).eval()
+    shapes = [(n, tuple(s)) for n, s in json.loads(str(g["shapes"]))]
+    sd = {"decoder." + k: v for k, v in synth.synth_state_dict(shapes, seed=4).items()}
+    sd.update({"post_quant_conv." + k: v for k, v in synth.synth_state_dict([("weight", (4, 4, 1, 1)), ("bias", (4,))], 4).items()})
+    missing, unexpected = vae.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("encoder.", "quant_conv.")) for k in missing)
+    y = vae.decode(torch.from_numpy(g["z"]))
+    err = (y - torch.from_numpy(g["y"])).abs()
+    assert y.shape == g["y"].shape and float(err.max()) < 0.03, float(err.max())
+
+
+@pytest.mark.parametrize("batch_cfg", [False, True])
+def test_sampler_and_wrapper_wiring_vs_oracle(cpu_ops, batch_cfg):
+    from viewcrafter_b200.ddim import DDIMSampler
+    from viewcrafter_b200.diffusion import LatentDiffusion
+    model = LatentDiffusion(dict(UNET_PARAMS, model_channels=64), dict(ddconfig=dict(VAE_DDCONFIG, ch=32), embed_dim=4), base_scale=0.7).eval()
+    unet = model.model.diffusion_model
+    sd = synth.synth_state_dict(synth.module_shapes(unet), seed=41)
+    unet.load_state_dict(sd, strict=True)
+    sdv = synth.synth_state_dict(synth.module_shapes(model.first_stage_model), seed=44)
+    model.first_stage_model.load_state_dict(sdv, strict=True)
+    g = torch.Generator().manual_seed(42)
+    T, H, W, S = 3, 8, 8, 2
+    shape = (1, 4, T, H, W)
+    x_T, cc = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    ctx_c, ctx_u = torch.randn(1, 333, 1024, generator=g), torch.randn(1, 333, 1024, generator=g)
+    fs = torch.tensor([10])
+    c = {"c_crossattn": [ctx_c], "c_concat": [cc]}
+    uc = {"c_crossattn": [ctx_u], "c_concat": [cc]}
+    sampler = DDIMSampler(model, batch_cfg=batch_cfg)
+    torch.manual_seed(43)
+    out, inter = sampler.sample(S=S, batch_size=1, shape=shape[1:], conditioning=c, eta=1.0, verbose=False, x_T=x_T,
+                                unconditional_guidance_scale=7.5, unconditional_conditioning=uc, fs=fs,
+                                timestep_spacing="uniform_trailing", guidance_rescale=0.7)
+    torch.manual_seed(43)
+    noises = [torch.randn(shape) for _ in range(S)]
+    sched = O.model_schedule(base_scale=0.7)
+
+    def model_fn(x, t, cond):
+        with torch.no_grad():
+            return O.unet_forward(sd, torch.cat([x, cc], 1), t, cond, fs)
+
+    ref, _ = O.ddim_sample(model_fn, sched, shape, S, ctx_c, ctx_u, x_T, noises)
+    err = (out - ref).abs()
+    assert float(err.max()) < 0.15 and float(err.mean()) < 0.02, (float(err.max()), float(err.mean()))   # CFG 7.5 amplifies the fp16 U-Net error ~16x
+    img = model.decode_first_stage(out)
+    with torch.no_grad():
+        ref_img = O.decode_first_stage(sdv, ref)
+    assert img.shape == (1, 3, T, 8 * H, 8 * W)
+    assert float((img - ref_img).abs().mean()) < 0.03 * max(1.0, float(ref_img.std()))
+
+
+def test_latent_diffusion_builds_inside_cuda_device_context_guard():
+    """model_buffers must not depend on torch's default device (bench builds the model under torch.device('cuda'))."""
+    from viewcrafter_b200 import schedule
+    with torch.device("meta"):
+        b = schedule.model_buffers(base_scale=0.3)
+    assert b["alphas_cumprod"].device.type == "cpu" and b["alphas_cumprod"].shape[0] == 1000

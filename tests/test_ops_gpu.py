@@ -278,3 +278,17 @@ def test_ddim_update_matches_oracle(ops, cfg, gr):
         xp, x0 = ops.ddim_update(x.cuda(), vc_.cuda(), vu.cuda(), nz.cuda(), d)
         close(xp.cpu(), ref_prev, 2e-5, rtol=2e-5, what=f"x_prev index {index}")
         close(x0.cpu(), ref_x0, 2e-5, rtol=2e-5, what=f"pred_x0 index {index}")
+
+
+def test_linear_strided_weight_view(ops):
+    """w may be a column slice of a wider matrix (the VAE attention uses K = fused-QK[:, C:] as the 'weight')."""
+    M, C = 300, 512
+    qk = rnd(M, 2 * C, seed=70)
+    ref = qk[:, :C].float() @ qk[:, C:].float().t()
+    out = ops.linear(qk[:, :C], qk[:, C:], out_f32=True)
+    close(out, ref, 2e-2, rtol=2e-3, what="strided w")
+
+
+def test_softmax_rows(ops):
+    x = rnd(200, 1000, seed=71, dtype=torch.float32, scale=20.0)
+    close(ops.softmax_rows(x, 0.044), torch.softmax(x * 0.044, -1), 1e-4, rtol=2e-3, what="softmax_rows")

@@ -20,7 +20,7 @@ class VcError(RuntimeError):
 class GemmDesc(C.Structure):
     _fields_ = [("a", C.c_void_p), ("lda", C.c_int32), ("a2", C.c_void_p), ("lda2", C.c_int32),
                 ("X", C.c_int32), ("Y", C.c_int32), ("Z", C.c_int32), ("bx", C.c_int32), ("by", C.c_int32),
-                ("K", C.c_int32), ("K1", C.c_int32), ("w", C.c_void_p), ("N", C.c_int32), ("num_taps", C.c_int32),
+                ("K", C.c_int32), ("K1", C.c_int32), ("w", C.c_void_p), ("ldw", C.c_int32), ("N", C.c_int32), ("num_taps", C.c_int32),
                 ("tap_dx", C.c_int32 * 9), ("tap_dy", C.c_int32 * 9),
                 ("out", C.c_void_p), ("out_f32", C.c_void_p), ("ldo", C.c_int32),
                 ("bias", C.c_void_p), ("bias_z_div", C.c_int32), ("res", C.c_void_p), ("ldr", C.c_int32),

@@ -161,8 +161,7 @@ class AutoencoderKL(nn.Module):
                     o_w=ops.pack_linear(m.proj_out.weight.detach()), o_b=f(m.proj_out.bias))
 
     def _pack(self):
-        if self.device.type != "cuda":
-            raise RuntimeError("viewcrafter_b200.AutoencoderKL.decode runs only on a CUDA (sm_100a) device; there is no CPU path")
+        ops.require_cuda(self.device, "viewcrafter_b200.AutoencoderKL.decode")
         f = self._f32
         d = self.decoder
         zc = self.post_quant_conv.weight.shape[1]

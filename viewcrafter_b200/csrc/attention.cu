@@ -2,10 +2,14 @@
 //
 // Used for the spatial self-attention (Nq = Nk = H*W up to 9216) and the text / image cross-attention
 // (Nk = 77 / 256) of lvdm/modules/attention.py:81-144.  One CTA owns 128 query rows of one (batch, head)
-// and streams 128-key tiles:   S = Q K^T  (SS MMA, fp32 in TMEM)  ->  online softmax by 128 threads, one row
-// each (exp2 domain)  ->  P (fp16) written back to TMEM  ->  O += P V  (TS MMA, A from TMEM, V MN-major in
-// smem).  K/V tiles arrive by TMA through a 2-stage mbarrier ring.  Two CTAs are co-resident per SM so one
-// CTA's MUFU-bound softmax overlaps the other's MMAs.
+// and streams 128-key tiles:
+//     S = Q K^T          SS MMA, fp32 accumulator in TMEM
+//     online softmax     128 threads, one query row each: the whole 128-wide S row is pulled into registers with
+//                        four back-to-back tcgen05.ld and ONE wait; exp2 domain; the running maximum is only
+//                        refreshed when it grew by more than 2^8 ("lazy rescale"), so O is rarely touched
+//     P (fp16) -> TMEM, O += P V   TS MMA (A from TMEM, V tile MN-major in smem)
+// The next tile's Q K^T is issued as soon as S sits in registers, so the tensor pipe works underneath the
+// MUFU-bound softmax; K/V tiles arrive by TMA through a 2-stage mbarrier ring.  Two CTAs are co-resident per SM.
 //
 // Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2..5 = softmax /
 // correction / epilogue (TMEM lane quadrant = warp % 4).
@@ -28,6 +32,13 @@ struct AttnParams {
 static constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64;
 static constexpr int ATT_TILE_BYTES = 128 * 64 * 2;                    // 16 KB
 static constexpr int ATT_SMEM = ATT_TILE_BYTES * 5 + 1024 + 256;       // Q + 2x(K,V) + slack + barriers
+static constexpr float ATT_LAZY = 8.0f;                                // rescale only if the max grew by > 2^8
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -38,10 +49,11 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;    // [2]
   uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_final = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_full = bars + 5;     // MMA -> softmax: S tile ready
+  uint64_t* s_free = bars + 6;     // softmax -> MMA: S tile copied to registers (128 arrivals)
+  uint64_t* p_full = bars + 7;     // softmax -> MMA: P written, O corrected (128 arrivals)
+  uint64_t* o_done = bars + 8;     // MMA -> softmax: P V of the tile retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_BM, head = blockIdx.y, b = blockIdx.z;
@@ -56,8 +68,9 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
     mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
     mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
     mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
     mbar_init(p_full, 128);
-    mbar_init(o_final, 1);
+    mbar_init(o_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -87,120 +100,155 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);      // B = V is MN-major
-      mbar_wait(q_full, 0);
       const uint32_t aQ = smem_u32(sQ);
-      for (int j = 0; j < ntiles; ++j) {
+      auto issue_qk = [&](int j) {
         const int s = j & 1;
         mbar_wait(&kv_full[s], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t aK = smem_u32(sKV + s * 2 * ATT_TILE_BYTES);
-        const uint32_t aV = aK + ATT_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k)
           umma_ss(tS, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc_qk, k > 0 ? 1u : 0u);
         umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) {                       // next S as soon as this one has been copied out of TMEM
+          mbar_wait(s_free, j & 1);
+          issue_qk(j + 1);
+        }
         mbar_wait(p_full, j & 1);
         tc_fence_after();
+        const uint32_t aV = smem_u32(sKV + (j & 1) * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)
           umma_ts(tO, tP + k * 8, umma_desc_sw128(aV + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&kv_empty[s]);
+        umma_commit(&kv_empty[j & 1]);
+        umma_commit(o_done);
       }
-      umma_commit(o_final);
     }
   } else {
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const float sl2 = p.scale_log2;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < ntiles; ++j) {
       const int valid = min(ATT_BN, p.Nk - j * ATT_BN);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row maximum
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld32(tS + lane_off, s0);
+      tmem_ld32(tS + lane_off + 32, s1);
+      tmem_ld32(tS + lane_off + 64, s2);
+      tmem_ld32(tS + lane_off + 96, s3);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(s_free);
+
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_off + c * 32, v);
-        tc_wait_ld();
+      if (valid == ATT_BN) {
 #pragma unroll
         for (int e = 0; e < 32; ++e)
-          if (c * 32 + e < valid) mx = fmaxf(mx, __uint_as_float(v[e]));
+          mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(s0[e]), __uint_as_float(s1[e])), fmaxf(__uint_as_float(s2[e]), __uint_as_float(s3[e]))));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          if (e >= valid) s0[e] = 0xff800000u;            // -inf: masked keys get probability 0
+          if (32 + e >= valid) s1[e] = 0xff800000u;
+          if (64 + e >= valid) s2[e] = 0xff800000u;
+          if (96 + e >= valid) s3[e] = 0xff800000u;
+          mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(s0[e]), __uint_as_float(s1[e])), fmaxf(__uint_as_float(s2[e]), __uint_as_float(s3[e]))));
+        }
       }
-      const float m_new = fmaxf(m, mx * p.scale_log2);
-      const float alpha = exp2f(m - m_new);
-      l *= alpha;
-      // pass 2: probabilities -> P (fp16 pairs) in TMEM
+      const float m_cand = fmaxf(m, mx * sl2);
+      const bool need = (m_cand - m) > ATT_LAZY;          // j == 0: m = -inf -> true
+      float alpha = 1.f;
+      if (need) {
+        alpha = ex2f(m - m_cand);                         // 0 at j == 0
+        l *= alpha;
+        m = m_cand;
+      }
+      const float neg_m = -m;
+      float psum = 0.f;
+      // probabilities, packed in place: s0[0..15] <- s0, s0[16..31] <- s1, s2[0..15] <- s2, s2[16..31] <- s3
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const float a0 = ex2f(fmaf(__uint_as_float(s0[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s0[e + 1]), sl2, neg_m));
+        psum += a0 + a1;
+        s0[e / 2] = pack_half2(a0, a1);
+      }
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const float a0 = ex2f(fmaf(__uint_as_float(s1[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s1[e + 1]), sl2, neg_m));
+        psum += a0 + a1;
+        s0[16 + e / 2] = pack_half2(a0, a1);
+      }
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const float a0 = ex2f(fmaf(__uint_as_float(s2[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s2[e + 1]), sl2, neg_m));
+        psum += a0 + a1;
+        s2[e / 2] = pack_half2(a0, a1);
+      }
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const float a0 = ex2f(fmaf(__uint_as_float(s3[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s3[e + 1]), sl2, neg_m));
+        psum += a0 + a1;
+        s2[16 + e / 2] = pack_half2(a0, a1);
+      }
+      l += psum;
+      if (j > 0) {
+        mbar_wait(o_done, (j - 1) & 1);                  // P V of the previous tile retired: P and O may be touched
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {             // warp-uniform: tcgen05.ld/st are warp-collective
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t pk[32];
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + lane_off + c * 32, v);
+            tc_wait_ld();
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = half * 2 + cc;
-          uint32_t v[32];
-          tmem_ld32(tS + lane_off + c * 32, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = (c * 32 + e < valid) ? exp2f(__uint_as_float(v[e]) * p.scale_log2 - m_new) : 0.f;
-            const float p1 = (c * 32 + e + 1 < valid) ? exp2f(__uint_as_float(v[e + 1]) * p.scale_log2 - m_new) : 0.f;
-            l += p0 + p1;
-            pk[cc * 16 + e / 2] = pack_half2(p0, p1);
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st32(tO + lane_off + c * 32, v);
           }
         }
-        tmem_st32(tP + lane_off + half * 32, pk);
       }
-      // correction: O *= alpha (PV of the previous tile has retired: it was issued before this tile's QK)
-      if (j > 0) {
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tO + lane_off + c * 32, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-          tmem_st32(tO + lane_off + c * 32, v);
-        }
-      }
-      m = m_new;
+      tmem_st32(tP + lane_off, s0);
+      tmem_st32(tP + lane_off + 32, s2);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(p_full);
     }
     // epilogue
-    mbar_wait(o_final, 0);
+    mbar_wait(o_done, (ntiles - 1) & 1);
     tc_fence_after();
     const float inv = 1.f / l;
     const int row = q0 + r;
     __half* op = p.out + ((long long)b * p.Nq + row) * p.ldo + head * ATT_D;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      __syncwarp();
-      tmem_ld32(tO + lane_off + c * 32, v);
-      tc_wait_ld();
-      if (row < p.Nq) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32(tO + lane_off, v0);
+    tmem_ld32(tO + lane_off + 32, v1);
+    tc_wait_ld();
+    if (row < p.Nq) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
+      for (int g = 0; g < 8; ++g) {
+        float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]) * inv;
-          uint4* dst = reinterpret_cast<uint4*>(op + c * 32 + g * 8);
-          if (p.accumulate) {
-            const uint4 u = *dst;
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(g < 4 ? v0[g * 8 + e] : v1[(g - 4) * 8 + e]) * inv;
+        uint4* dst = reinterpret_cast<uint4*>(op + g * 8);
+        if (p.accumulate) {
+          const uint4 u = *dst;
+          const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 t = __half22float2(h[e]);
-              f[2 * e] += t.x; f[2 * e + 1] += t.y;
-            }
+          for (int e = 0; e < 4; ++e) {
+            const float2 t = __half22float2(h[e]);
+            f[2 * e] += t.x; f[2 * e + 1] += t.y;
           }
-          uint4 o;
-          o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
-          o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
-          *dst = o;
         }
+        uint4 o;
+        o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
+        o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
+        *dst = o;
       }
     }
   }

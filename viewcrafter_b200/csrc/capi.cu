@@ -29,7 +29,7 @@ int vc_gemm_tap(const vc_gemm_desc* c, void* stream) {
   GemmDesc d;
   d.a = H(c->a); d.lda = c->lda; d.a2 = H(c->a2); d.lda2 = c->lda2;
   d.X = c->X; d.Y = c->Y; d.Z = c->Z; d.bx = c->bx; d.by = c->by;
-  d.K = c->K; d.K1 = c->K1; d.w = H(c->w); d.N = c->N; d.num_taps = c->num_taps;
+  d.K = c->K; d.K1 = c->K1; d.w = H(c->w); d.ldw = c->ldw; d.N = c->N; d.num_taps = c->num_taps;
   for (int i = 0; i < 9; ++i) { d.tap_dx[i] = c->tap_dx[i]; d.tap_dy[i] = c->tap_dy[i]; }
   d.out = HM(c->out); d.out_f32 = reinterpret_cast<float*>(c->out_f32); d.ldo = c->ldo;
   d.bias = c->bias; d.bias_z_div = c->bias_z_div; d.res = H(c->res); d.ldr = c->ldr; d.geglu = c->geglu;

@@ -137,96 +137,56 @@ __global__ void __launch_bounds__(192, 2) gemm_tap_kernel(const __grid_constant_
       umma_commit(tmem_full_bar);     // accumulator complete
     }
   } else {
-    // ---------------- epilogue: one accumulator row per thread ----------------
+    // ---------------- epilogue ----------------
+    // TMEM -> registers (one accumulator row per thread, 32 columns at a time) -> (+bias / GEGLU) -> fp32 staging tile in
+    // the now idle pipeline smem -> re-read so that 4 lanes cover 64 contiguous bytes of one output row (full 32-byte
+    // sectors for the residual load and the store) -> + residual -> fp16 / fp32 store.
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;
-    const int x = x0 + (r % p.bx), y = y0 + (r / p.bx);
-    const bool row_ok = (x < p.X) && (y < p.Y);
-    const long long orow = ((long long)z * p.Y + y) * p.X + x;
+    constexpr int SROW = 36;                      // staging row pitch in floats (32 + 4 pad: conflict-free 128-bit access)
+    float* stage = reinterpret_cast<float*>(smem) + q * 32 * SROW;
     const float* bias = p.bias ? p.bias + (long long)(p.bias_z_div > 0 ? z / p.bias_z_div : 0) * p.N : nullptr;
+    const int rsub = lane >> 2, piece = lane & 3;
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int HALF = BN / 2;
+    const int nchunks = p.geglu ? HALF / 32 : BN / 32;
+    const int n_out = p.geglu ? p.N / 2 : p.N;
+    const int ocol0 = p.geglu ? n_tile * HALF : n0;
 
-    if (!p.geglu) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+    for (int c = 0; c < nchunks; ++c) {
+      float f[32];
+      __syncwarp();
+      if (!p.geglu) {
         uint32_t v[32];
-        __syncwarp();
         tmem_ld32(trow + c * 32, v);
         tc_wait_ld();
         const int nb = n0 + c * 32;
-        if (!row_ok || nb >= p.N) continue;
-        float f[32];
+        if (nb >= p.N) break;                      // warp-uniform
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (nb + 32 <= p.N) {
-          if (bias) {
+        if (bias) {
+          if (nb + 32 <= p.N) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
               f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
-          }
-          if (p.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + orow * p.ldr + nb);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = rp[j];   // plain load: res may alias out (in-place residual)
-              const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 t = __half22float2(h[e]);
-                f[j * 8 + e * 2] += t.x;
-                f[j * 8 + e * 2 + 1] += t.y;
-              }
-            }
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + nb);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>(p.out + orow * p.ldo + nb);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              u.x = pack_half2(f[j * 8 + 0], f[j * 8 + 1]);
-              u.y = pack_half2(f[j * 8 + 2], f[j * 8 + 3]);
-              u.z = pack_half2(f[j * 8 + 4], f[j * 8 + 5]);
-              u.w = pack_half2(f[j * 8 + 6], f[j * 8 + 7]);
-              op[j] = u;
-            }
-          }
-        } else {
-          // ragged N tail (e.g. the 320->4 output conv): predicated scalar path, fully unrolled so f[] stays in registers
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (nb + j < p.N) {
-              float t = f[j];
-              if (bias) t += bias[nb + j];
-              if (p.res) t += __half2float(p.res[orow * p.ldr + nb + j]);
-              if (p.out_f32) p.out_f32[orow * p.ldo + nb + j] = t;
-              else p.out[orow * p.ldo + nb + j] = __float2half_rn(t);
-            }
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) f[j] += __ldg(bias + nb + j);
           }
         }
-      }
-    } else {
-      // GEGLU: tile columns [0,BN/2) are values, [BN/2,BN) the matching gates (weights were interleaved per tile).
-      constexpr int HALF = BN / 2;
-      const int ob = n_tile * HALF;
-#pragma unroll 1
-      for (int c = 0; c < HALF / 32; ++c) {
+      } else {
+        // GEGLU: tile columns [0,BN/2) are values, [BN/2,BN) the matching gates (weights were interleaved per tile).
         uint32_t a[32], g[32];
-        __syncwarp();
         tmem_ld32(trow + c * 32, a);
         tmem_ld32(trow + HALF + c * 32, g);
         tc_wait_ld();
-        if (!row_ok) continue;
-        const int nv = n0 + c * 32;          // bias index of the value columns inside the permuted weight
-        float f[32];
+        const int nv = n0 + c * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float va = __uint_as_float(a[j]), vg = __uint_as_float(g[j]);
@@ -234,17 +194,55 @@ __global__ void __launch_bounds__(192, 2) gemm_tap_kernel(const __grid_constant_
             va += __ldg(bias + nv + j);
             vg += __ldg(bias + nv + HALF + j);
           }
-          f[j] = va * gelu_erf_f(vg);
+          f[j] = va * gelu_erf_fast(vg);
         }
-        uint4* op = reinterpret_cast<uint4*>(p.out + orow * p.ldo + ob + c * 32);
+      }
+      float4* srow = reinterpret_cast<float4*>(stage + lane * SROW);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack_half2(f[j * 8 + 0], f[j * 8 + 1]);
-          u.y = pack_half2(f[j * 8 + 2], f[j * 8 + 3]);
-          u.z = pack_half2(f[j * 8 + 4], f[j * 8 + 5]);
-          u.w = pack_half2(f[j * 8 + 6], f[j * 8 + 7]);
-          op[j] = u;
+      for (int j = 0; j < 8; ++j) srow[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      __syncwarp();
+      const int col = ocol0 + c * 32 + piece * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = 8 * i + rsub;
+        const int R = q * 32 + rr;
+        const int x = x0 + (R % p.bx), y = y0 + (R / p.bx);
+        if (x >= p.X || y >= p.Y || col >= n_out) continue;
+        const long long orow = ((long long)z * p.Y + y) * p.X + x;
+        const float4 lo = *reinterpret_cast<const float4*>(stage + rr * SROW + piece * 8);
+        const float4 hi = *reinterpret_cast<const float4*>(stage + rr * SROW + piece * 8 + 4);
+        float o[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        if (col + 8 <= n_out && (p.ldo & 7) == 0) {
+          if (p.res) {
+            const uint4 u = *reinterpret_cast<const uint4*>(p.res + orow * p.ldr + col);   // plain load: res may alias out
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = __half22float2(h[e]);
+              o[2 * e] += t.x; o[2 * e + 1] += t.y;
+            }
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + col);
+            op[0] = make_float4(o[0], o[1], o[2], o[3]);
+            op[1] = make_float4(o[4], o[5], o[6], o[7]);
+          } else {
+            uint4 u;
+            u.x = pack_half2(o[0], o[1]); u.y = pack_half2(o[2], o[3]);
+            u.z = pack_half2(o[4], o[5]); u.w = pack_half2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(p.out + orow * p.ldo + col) = u;
+          }
+        } else {
+          // ragged N tail / unaligned pitch (e.g. the 320->4 output conv): predicated scalar path
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (col + e < n_out) {
+              float t = o[e];
+              if (p.res) t += __half2float(p.res[orow * p.ldr + col + e]);
+              if (p.out_f32) p.out_f32[orow * p.ldo + col + e] = t;
+              else p.out[orow * p.ldo + col + e] = __float2half_rn(t);
+            }
+          }
         }
       }
     }
@@ -320,7 +318,7 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   const int BN = pick_bn(d.N, d.geglu);
   {
     uint64_t dims[2] = {(uint64_t)d.K, (uint64_t)d.num_taps * d.N};
-    uint64_t str[1] = {(uint64_t)d.K * 2};
+    uint64_t str[1] = {(uint64_t)(d.ldw > 0 ? d.ldw : d.K) * 2};
     uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
     int rc = encode_tmap_f16(&p.tmap_b, d.w, 2, dims, str, box);
     if (rc) return rc;

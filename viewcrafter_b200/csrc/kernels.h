@@ -14,6 +14,7 @@ struct GemmDesc {
   int bx = 128, by = 1;           // TMA box: bx*by == 128 rows per tile
   int K = 0, K1 = 0;              // reduction length per tap; K1 = part served by `a`
   const __half* w = nullptr;      // weights [num_taps*N, K] fp16, K contiguous
+  int ldw = 0;                    // row pitch of w in elements (0 = K)
   int N = 0;
   int num_taps = 1;
   int tap_dx[9] = {0}; int tap_dy[9] = {0};

@@ -38,14 +38,23 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const __half* __restrict
   for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
   const long long r0 = (long long)split * g.rows_per_split;
   const long long r1 = min(g.rows, r0 + g.rows_per_split);
-  for (long long r = r0 + pl; r < r1; r += g.ppi) {
-    const uint4 u = gn_load(x1, x2, g, sample, r, v * 8);
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
+  // 4 independent 16-byte loads in flight per thread (the kernel is pure streaming: latency must be covered by MLP)
+  for (long long r = r0 + pl; r < r1; r += 4ll * g.ppi) {
+    uint4 u[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(h[e]);
-      s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
-      s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
+    for (int i = 0; i < 4; ++i) {
+      const long long ri = r + (long long)i * g.ppi;
+      u[i] = ri < r1 ? gn_load(x1, x2, g, sample, ri, v * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
+        s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
+      }
     }
   }
 #pragma unroll
@@ -95,24 +104,34 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const __half* __restrict
   }
   const long long r0 = (long long)blockIdx.x * g.rows_per_split;
   const long long r1 = min(g.rows, r0 + g.rows_per_split);
-  for (long long r = r0 + pl; r < r1; r += g.ppi) {
-    const uint4 u = gn_load(x1, x2, g, sample, r, v * 8);
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
-    float f[8];
+  for (long long r = r0 + pl; r < r1; r += 4ll * g.ppi) {
+    uint4 u[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 t = __half22float2(h[e]);
-      f[2 * e] = t.x; f[2 * e + 1] = t.y;
+    for (int i = 0; i < 4; ++i) {
+      const long long ri = r + (long long)i * g.ppi;
+      if (ri < r1) u[i] = gn_load(x1, x2, g, sample, ri, v * 8);
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float y = f[e] * sc[e] + sh[e];
-      f[e] = silu ? silu_f(y) : y;
+    for (int i = 0; i < 4; ++i) {
+      const long long ri = r + (long long)i * g.ppi;
+      if (ri >= r1) break;
+      const __half2* h = reinterpret_cast<const __half2*>(&u[i]);
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = __half22float2(h[e]);
+        f[2 * e] = t.x; f[2 * e + 1] = t.y;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float y = f[e] * sc[e] + sh[e];
+        f[e] = silu ? silu_f(y) : y;
+      }
+      uint4 o;
+      o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
+      o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(out + ((long long)sample * g.rows + ri) * g.C + v * 8) = o;
     }
-    uint4 o;
-    o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
-    o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(out + ((long long)sample * g.rows + r) * g.C + v * 8) = o;
   }
 }
 
@@ -147,58 +166,77 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int sampl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent warps: each warp walks rows with a grid stride and keeps TWO rows in flight (all their 16-byte loads are
+// issued before the first reduction) so the DRAM latency is covered by memory-level parallelism, not by block churn.
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, __half* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int vecs = C >> 3;
-  float f[MAXV][8];
-  float sum = 0.f;
+  const float invC = 1.f / (float)C;
+  for (long long row0 = gw * 2; row0 < rows; row0 += nwarps * 2) {
+    uint4 raw[2][MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < vecs) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + v * 8);
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
+    for (int rr = 0; rr < 2; ++rr) {
+      const long long row = row0 + rr;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 t = __half22float2(h[e]);
-        f[i][2 * e] = t.x; f[i][2 * e + 1] = t.y;
-        sum += t.x + t.y;
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        raw[rr][i] = (row < rows && v < vecs) ? *reinterpret_cast<const uint4*>(x + row * C + v * 8) : make_uint4(0, 0, 0, 0);
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)C;
-  float sq = 0.f;
+    for (int rr = 0; rr < 2; ++rr) {
+      const long long row = row0 + rr;
+      if (row >= rows) break;                                   // warp-uniform
+      float f[MAXV][8];
+      float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < vecs) {
+      for (int i = 0; i < MAXV; ++i) {
+        const __half2* h = reinterpret_cast<const __half2*>(&raw[rr][i]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = f[i][e] - mean;
-        sq += d * d;
+        for (int e = 0; e < 4; ++e) {
+          const float2 t = __half22float2(h[e]);
+          f[i][2 * e] = t.x; f[i][2 * e + 1] = t.y;
+          sum += t.x + t.y;                                     // out-of-range vectors were loaded as zeros
+        }
       }
-    }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / (float)C + eps);
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * invC;
+      float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < vecs) {
-      float y[8];
+      for (int i = 0; i < MAXV; ++i) {
+        if (lane + i * 32 < vecs) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = (f[i][e] - mean) * rstd * __ldg(gamma + v * 8 + e) + __ldg(beta + v * 8 + e);
-      uint4 o;
-      o.x = pack_half2(y[0], y[1]); o.y = pack_half2(y[2], y[3]);
-      o.z = pack_half2(y[4], y[5]); o.w = pack_half2(y[6], y[7]);
-      *reinterpret_cast<uint4*>(out + row * C + v * 8) = o;
+          for (int e = 0; e < 8; ++e) {
+            const float d = f[i][e] - mean;
+            sq += d * d;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * invC + eps);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < vecs) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float y[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = (f[i][e] - mean) * rstd * gg[e] + bb[e];
+          uint4 o;
+          o.x = pack_half2(y[0], y[1]); o.y = pack_half2(y[2], y[3]);
+          o.z = pack_half2(y[4], y[5]); o.w = pack_half2(y[6], y[7]);
+          *reinterpret_cast<uint4*>(out + row * C + v * 8) = o;
+        }
+      }
     }
   }
 }
@@ -208,7 +246,9 @@ int layernorm_rows(const __half* x, long long rows, int C, const float* gamma, c
   VC_REQUIRE(x && out && gamma && beta, "layernorm: null pointer");
   VC_REQUIRE(C % 8 == 0 && C <= 2048 && rows > 0, "layernorm: unsupported C=%d rows=%lld", C, rows);
   const int wpb = 8;
-  const long long blocks = (rows + wpb - 1) / wpb;
+  long long blocks = (rows + 2 * wpb - 1) / (2 * wpb);
+  const long long cap = (long long)sm_count() * 8;              // 8 x 256 threads = 64 warps per SM
+  if (blocks > cap) blocks = cap;
   const int vecs = C / 8;
   if (vecs <= 64)
     layernorm_kernel<2><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, gamma, beta, eps, out);

@@ -23,6 +23,12 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def require_cuda(device, who: str):
+    """The product has no CPU path: anything not on a CUDA device is an error, not a fallback."""
+    if torch.device(device).type != "cuda":
+        raise _lib.VcError(f"{who} runs only on a CUDA (sm_100a) device; there is no CPU path")
+
+
 def _chk16(t: torch.Tensor, name: str):
     if t.dtype != torch.float16 or not t.is_cuda:
         raise _lib.VcError(f"{name}: expected a CUDA fp16 tensor, got {t.dtype} on {t.device}")
@@ -90,6 +96,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         assert K1 == K, (K1, K)
     d.X, d.Y, d.Z, d.bx, d.by = M, 1, 1, 128, 1
     d.K, d.K1, d.w, d.N, d.num_taps = K, K1, w.data_ptr(), N, 1
+    d.ldw = w.stride(0)                                  # w may be a column slice of a wider matrix (e.g. K of a fused QK)
     if out_f32:
         d.out_f32 = out.data_ptr()
     else:

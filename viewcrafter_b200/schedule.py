@@ -12,7 +12,7 @@ import torch
 
 
 def linear_betas(n: int, start: float, end: float) -> np.ndarray:
-    return (torch.linspace(start ** 0.5, end ** 0.5, n, dtype=torch.float64) ** 2).numpy()
+    return (torch.linspace(start ** 0.5, end ** 0.5, n, dtype=torch.float64, device="cpu") ** 2).numpy()
 
 
 def zero_terminal_snr(betas: np.ndarray) -> np.ndarray:
@@ -29,7 +29,7 @@ def model_buffers(timesteps=1000, linear_start=0.00085, linear_end=0.012, zero_s
     if zero_snr:
         betas = zero_terminal_snr(betas)
     ac = np.cumprod(1.0 - betas, axis=0)
-    t32 = lambda a: torch.tensor(a, dtype=torch.float32)
+    t32 = lambda a: torch.tensor(a, dtype=torch.float32, device="cpu")
     out = dict(betas=t32(betas), alphas_cumprod=t32(ac), alphas_cumprod_prev=t32(np.append(1.0, ac[:-1])),
                sqrt_alphas_cumprod=t32(np.sqrt(ac)), sqrt_one_minus_alphas_cumprod=t32(np.sqrt(1.0 - ac)))
     if dynamic_rescale:

