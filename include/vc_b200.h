@@ -86,6 +86,14 @@ size_t vc_groupnorm_ws_bytes(int32_t samples);
 int vc_groupnorm_nhwc(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t samples, int64_t rows_per_sample,
                       const float* gamma, const float* beta, float eps, int32_t silu, void* out, void* ws, size_t ws_bytes,
                       void* stream);
+/* Split form for GroupNorm statistics that span several GPUs (site-sharded 5-D GroupNorm of the temporal blocks):
+ * pass 1 writes (sum, sumsq) per group to stats[samples][32][2]; the caller all-reduces that buffer (NCCL); pass 2
+ * normalises with the global row count stat_rows. */
+int vc_groupnorm_stats(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t samples, int64_t rows_per_sample, float* stats,
+                       void* ws, size_t ws_bytes, void* stream);
+int vc_groupnorm_apply(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t samples, int64_t rows_per_sample,
+                       const float* stats, int64_t stat_rows, const float* gamma, const float* beta, float eps, int32_t silu, void* out,
+                       void* stream);
 /* nn.LayerNorm over the last dim (attention.py:233-235), fp16 in/out, fp32 statistics */
 int vc_layernorm(const void* x, int64_t rows, int32_t C, const float* gamma, const float* beta, float eps, void* out,
                  void* stream);

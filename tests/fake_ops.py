@@ -131,6 +131,25 @@ def groupnorm(x, samples, gamma, beta, eps, silu, x2=None):
     return _h(y.permute(0, 2, 1).reshape(rows, C))
 
 
+def groupnorm_stats(x, samples):
+    rows, C = x.shape
+    a = x.float().reshape(samples, rows // samples, 32, C // 32)
+    return torch.stack([a.sum(dim=(1, 3)), (a * a).sum(dim=(1, 3))], dim=-1).contiguous()
+
+
+def groupnorm_apply(x, samples, stats, stat_rows, gamma, beta, eps, silu):
+    rows, C = x.shape
+    n = stat_rows * (C // 32)
+    mean = stats[..., 0] / n
+    var = (stats[..., 1] / n - mean * mean).clamp_min(0)
+    a = x.float().reshape(samples, rows // samples, 32, C // 32)
+    y = (a - mean[:, None, :, None]) * torch.rsqrt(var + eps)[:, None, :, None]
+    y = y.reshape(samples, rows // samples, C) * gamma + beta
+    if silu:
+        y = F.silu(y)
+    return _h(y.reshape(rows, C))
+
+
 def layernorm(x, gamma, beta, eps=1e-5):
     return _h(F.layer_norm(x.float(), (x.shape[1],), gamma, beta, eps))
 

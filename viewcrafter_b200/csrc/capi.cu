@@ -62,6 +62,17 @@ int vc_groupnorm_nhwc(const void* x1, int32_t C1, const void* x2, int32_t C2, in
   return groupnorm_nhwc(H(x1), C1, H(x2), C2, samples, rows_per_sample, gamma, beta, eps, silu, HM(out),
                         reinterpret_cast<float*>(ws), ws_bytes, ST(stream));
 }
+int vc_groupnorm_stats(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t samples, int64_t rows_per_sample, float* stats,
+                       void* ws, size_t ws_bytes, void* stream) {
+  COUNT(2);
+  return groupnorm_stats(H(x1), C1, H(x2), C2, samples, rows_per_sample, stats, reinterpret_cast<float*>(ws), ws_bytes, ST(stream));
+}
+int vc_groupnorm_apply(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t samples, int64_t rows_per_sample,
+                       const float* stats, int64_t stat_rows, const float* gamma, const float* beta, float eps, int32_t silu, void* out,
+                       void* stream) {
+  COUNT(1);
+  return groupnorm_apply(H(x1), C1, H(x2), C2, samples, rows_per_sample, stats, stat_rows, gamma, beta, eps, silu, HM(out), ST(stream));
+}
 int vc_layernorm(const void* x, int64_t rows, int32_t C, const float* gamma, const float* beta, float eps, void* out, void* stream) {
   COUNT(1);
   return layernorm_rows(H(x), rows, C, gamma, beta, eps, HM(out), ST(stream));

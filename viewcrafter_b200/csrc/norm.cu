@@ -17,6 +17,8 @@ size_t groupnorm_ws_bytes(int samples) { return (size_t)samples * GN_MAX_SPLITS 
 struct GnGeom {
   int C, C1, C2, vecs, ppi, cg, splits;
   long long rows, rows_per_split;
+  int stat_splits;        // partial-statistics records per sample the apply pass sums
+  long long stat_rows;    // rows the statistics cover (== rows, or the global row count when sharded across GPUs)
 };
 
 __device__ __forceinline__ uint4 gn_load(const __half* x1, const __half* x2, const GnGeom& g, long long sample, long long row, int c) {
@@ -79,12 +81,12 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const __half* __restrict
   const int sample = blockIdx.y;
   if (tid < 32) {
     double sum = 0.0, sq = 0.0;
-    const float* pp = partial + (long long)sample * g.splits * 64;
-    for (int sp = 0; sp < g.splits; ++sp) {
+    const float* pp = partial + (long long)sample * g.stat_splits * 64;
+    for (int sp = 0; sp < g.stat_splits; ++sp) {
       sum += pp[sp * 64 + tid * 2];
       sq += pp[sp * 64 + tid * 2 + 1];
     }
-    const double n = (double)g.rows * g.cg;
+    const double n = (double)g.stat_rows * g.cg;
     const double m = sum / n;
     double var = sq / n - m * m;
     if (var < 0.0) var = 0.0;
@@ -135,14 +137,11 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const __half* __restrict
   }
 }
 
-int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample,
-                   const float* gamma, const float* beta, float eps, int silu, __half* out, float* partial_ws,
-                   size_t ws_bytes, cudaStream_t stream) {
+static int gn_geometry(GnGeom& g, const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample) {
   const int C = C1 + (x2 ? C2 : 0);
-  VC_REQUIRE(x1 && out && gamma && beta && partial_ws, "groupnorm: null pointer");
+  VC_REQUIRE(x1, "groupnorm: null pointer");
   VC_REQUIRE(C % 32 == 0 && C1 % 8 == 0 && (!x2 || C2 % 8 == 0) && C <= 8192, "groupnorm: unsupported channels C1=%d C2=%d", C1, C2);
   VC_REQUIRE(samples >= 1 && rows_per_sample >= 1, "groupnorm: empty input");
-  GnGeom g;
   g.C = C; g.C1 = C1; g.C2 = x2 ? C2 : 0;
   g.vecs = C / 8;
   g.ppi = 512 / g.vecs > 0 ? 512 / g.vecs : 1;
@@ -155,12 +154,63 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int sampl
   if (splits < 1) splits = 1;
   g.splits = splits;
   g.rows_per_split = (rows_per_sample + splits - 1) / splits;
-  VC_REQUIRE(ws_bytes >= (size_t)samples * splits * 64 * sizeof(float), "groupnorm: workspace too small");
+  g.stat_splits = splits;
+  g.stat_rows = rows_per_sample;
+  return VC_OK;
+}
+
+int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample,
+                   const float* gamma, const float* beta, float eps, int silu, __half* out, float* partial_ws,
+                   size_t ws_bytes, cudaStream_t stream) {
+  VC_REQUIRE(out && gamma && beta && partial_ws, "groupnorm: null pointer");
+  GnGeom g;
+  int rc = gn_geometry(g, x1, C1, x2, C2, samples, rows_per_sample);
+  if (rc) return rc;
+  VC_REQUIRE(ws_bytes >= (size_t)samples * g.splits * 64 * sizeof(float), "groupnorm: workspace too small");
   const int threads = g.vecs * g.ppi;
-  dim3 grid(splits, samples);
-  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(x1, x2, g, partial_ws);
+  dim3 grid(g.splits, samples);
+  gn_stats_kernel<<<grid, threads, 2 * g.C * sizeof(float), stream>>>(x1, x2, g, partial_ws);
   VC_CHECK_CUDA(cudaGetLastError());
   gn_apply_kernel<<<grid, threads, 0, stream>>>(x1, x2, g, partial_ws, gamma, beta, eps, silu, out);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// Split form for statistics that span several GPUs (site-sharded 5-D GroupNorm): pass 1 leaves (sum, sumsq) per group in
+// stats[samples][32][2]; the caller all-reduces that tiny buffer; pass 2 normalises with the global row count.
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int splits, float* __restrict__ stats) {
+  const int sample = blockIdx.x, t = threadIdx.x;   // 64 threads
+  float acc = 0.f;
+  for (int sp = 0; sp < splits; ++sp) acc += partial[((long long)sample * splits + sp) * 64 + t];
+  stats[sample * 64 + t] = acc;
+}
+
+int groupnorm_stats(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample, float* stats,
+                    float* partial_ws, size_t ws_bytes, cudaStream_t stream) {
+  VC_REQUIRE(stats && partial_ws, "groupnorm_stats: null pointer");
+  GnGeom g;
+  int rc = gn_geometry(g, x1, C1, x2, C2, samples, rows_per_sample);
+  if (rc) return rc;
+  VC_REQUIRE(ws_bytes >= (size_t)samples * g.splits * 64 * sizeof(float), "groupnorm: workspace too small");
+  dim3 grid(g.splits, samples);
+  gn_stats_kernel<<<grid, g.vecs * g.ppi, 2 * g.C * sizeof(float), stream>>>(x1, x2, g, partial_ws);
+  VC_CHECK_CUDA(cudaGetLastError());
+  gn_finalize_kernel<<<samples, 64, 0, stream>>>(partial_ws, g.splits, stats);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+int groupnorm_apply(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample,
+                    const float* stats, long long stat_rows, const float* gamma, const float* beta, float eps, int silu, __half* out,
+                    cudaStream_t stream) {
+  VC_REQUIRE(out && gamma && beta && stats && stat_rows >= rows_per_sample, "groupnorm_apply: bad args");
+  GnGeom g;
+  int rc = gn_geometry(g, x1, C1, x2, C2, samples, rows_per_sample);
+  if (rc) return rc;
+  g.stat_splits = 1;
+  g.stat_rows = stat_rows;
+  dim3 grid(g.splits, samples);
+  gn_apply_kernel<<<grid, g.vecs * g.ppi, 0, stream>>>(x1, x2, g, stats, gamma, beta, eps, silu, out);
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;
 }

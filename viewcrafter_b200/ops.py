@@ -111,10 +111,11 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 
 def _conv_box(H: int, W: int):
-    if W >= 128:
+    # widths that divide 128 pack 128/W image rows into one 128-pixel tile; every other width falls back to one
+    # (partially filled, TMA zero-filled) tile per 128-pixel row segment -- correct for any W, full speed for the
+    # shipped widths (8..128 at the U-Net levels, 128..1024 in the VAE)
+    if W >= 128 or 128 % W != 0:
         return 128, 1
-    if 128 % W != 0:
-        raise _lib.VcError(f"conv: width {W} must divide 128 or be a multiple of it")
     return W, 128 // W
 
 
@@ -235,6 +236,29 @@ def groupnorm(x: torch.Tensor, samples: int, gamma: torch.Tensor, beta: torch.Te
     ws = _gn_workspace(x.device, samples)
     check(_lib.load().vc_groupnorm_nhwc(x.data_ptr(), C1, _ptr(x2), C2, samples, rows // samples, gamma.data_ptr(), beta.data_ptr(),
                                         eps, int(silu), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "vc_groupnorm_nhwc")
+    return out
+
+
+def groupnorm_stats(x: torch.Tensor, samples: int) -> torch.Tensor:
+    """Pass 1 of the split GroupNorm: fp32 [samples, 32, 2] = (sum, sumsq) per group over this rank's rows."""
+    _chk16(x, "groupnorm_stats.x")
+    rows, C1 = x.shape
+    assert x.is_contiguous()
+    stats = torch.empty((samples, 32, 2), device=x.device, dtype=torch.float32)
+    ws = _gn_workspace(x.device, samples)
+    check(_lib.load().vc_groupnorm_stats(x.data_ptr(), C1, None, 0, samples, rows // samples, stats.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), _stream()), "vc_groupnorm_stats")
+    return stats
+
+
+def groupnorm_apply(x: torch.Tensor, samples: int, stats: torch.Tensor, stat_rows: int, gamma: torch.Tensor, beta: torch.Tensor,
+                    eps: float, silu: bool) -> torch.Tensor:
+    """Pass 2: normalise with (all-reduced) statistics that cover ``stat_rows`` rows per sample."""
+    _chk16(x, "groupnorm_apply.x")
+    rows, C1 = x.shape
+    out = torch.empty_like(x)
+    check(_lib.load().vc_groupnorm_apply(x.data_ptr(), C1, None, 0, samples, rows // samples, stats.data_ptr(), stat_rows,
+                                         gamma.data_ptr(), beta.data_ptr(), eps, int(silu), out.data_ptr(), _stream()), "vc_groupnorm_apply")
     return out
 
 

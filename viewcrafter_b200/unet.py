@@ -203,6 +203,7 @@ class UNetModel(nn.Module):
         self.out = nn.Sequential(nn.GroupNorm(32, ch), nn.SiLU(), _zero(nn.Conv2d(mc, out_channels, 3, padding=1)))
 
         self._packed = None
+        self._comm = None           # set by viewcrafter_b200.parallel.shard_model for frame-sharded multi-GPU execution
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     # ------------------------------------------------------------------------------------------
@@ -307,7 +308,7 @@ class UNetModel(nn.Module):
     # block executors (operate on row matrices)
     # ------------------------------------------------------------------------------------------
     @staticmethod
-    def _res(P, h, skip, emb, B, T, H, W):
+    def _res(P, h, skip, emb, B, T, H, W, comm=None):
         BT, HW = B * T, H * W
         a = ops.groupnorm(h, BT, *P["gn1"], 1e-5, True, x2=skip)
         bias1 = ops.small_linear(emb, P["emb_w"], P["emb_b"], silu_in=True)            # [B, Cout] = emb_layers + conv1 bias
@@ -319,12 +320,23 @@ class UNetModel(nn.Module):
             xs = h
         h2 = ops.conv3x3(b, BT, H, W, P["w2"], bias=P["b2"], res=xs)
         if "tconv" in P:
-            t = h2
+            # TemporalConvBlock: needs every frame of a pixel -> (optionally) transpose frames<->sites across GPUs
+            t = ident = comm.to_sites(h2, B, HW) if comm else h2
+            Tg, HWl = (comm.T, HW // comm.world) if comm else (T, HW)
             for i, (g, be, w3, b3) in enumerate(P["tconv"]):
-                t = ops.groupnorm(t, B, g, be, 1e-5, True)                                # statistics over (C/32, T, H, W)
-                t = ops.conv_temporal(t, B, T, HW, w3, bias=b3, res=h2 if i == 3 else None)
-            h2 = t
+                t = UNetModel._gn5d(t, B, g, be, 1e-5, True, comm, Tg * HW)               # statistics over (C/32, T, H, W)
+                t = ops.conv_temporal(t, B, Tg, HWl, w3, bias=b3, res=ident if i == 3 else None)
+            h2 = comm.to_frames(t, B, HW) if comm else t
         return h2
+
+    @staticmethod
+    def _gn5d(x, B, gamma, beta, eps, silu, comm, stat_rows):
+        """GroupNorm whose statistics span all frames (and, when sharded, all GPUs: one tiny all-reduce of [B,32,2])."""
+        if not comm:
+            return ops.groupnorm(x, B, gamma, beta, eps, silu)
+        st = ops.groupnorm_stats(x, B)
+        comm.all_reduce(st)
+        return ops.groupnorm_apply(x, B, st, stat_rows, gamma, beta, eps, silu)
 
     @staticmethod
     def _spatial_tf(P, h, ctx, B, T, H, W):
@@ -353,32 +365,35 @@ class UNetModel(nn.Module):
         return ops.linear(x, P["out_w"], bias=P["out_b"], res=h)
 
     @staticmethod
-    def _temporal_tf(P, h, B, T, H, W):
+    def _temporal_tf(P, h, B, T, H, W, comm=None):
         HW, heads = H * W, P["heads"]
         C = heads * 64
-        x = ops.linear(ops.groupnorm(h, B, *P["gn"], 1e-6, False), P["in_w"], bias=P["in_b"])
+        Tg, HWl = (comm.T, HW // comm.world) if comm else (T, HW)
+        t_in = comm.to_sites(h, B, HW) if comm else h
+        x = ops.linear(UNetModel._gn5d(t_in, B, *P["gn"], 1e-6, False, comm, Tg * HW), P["in_w"], bias=P["in_b"])
         for Q in P["blocks"]:
             for ln, wqkv, ow, ob in (("ln1", "qkv1", "o1_w", "o1_b"), ("ln2", "qkv2", "o2_w", "o2_b")):
                 qkv = ops.linear(ops.layernorm(x, *Q[ln]), Q[wqkv])
                 a = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=torch.float16)
                 for b in range(B):
-                    rows = slice(b * T * HW, (b + 1) * T * HW)
-                    a[rows] = ops.temporal_attn(qkv[rows, :C], qkv[rows, C:2 * C], qkv[rows, 2 * C:], T, HW, heads)
+                    rows = slice(b * Tg * HWl, (b + 1) * Tg * HWl)
+                    a[rows] = ops.temporal_attn(qkv[rows, :C], qkv[rows, C:2 * C], qkv[rows, 2 * C:], Tg, HWl, heads)
                 x = ops.linear(a, Q[ow], bias=Q[ob], res=x)
             g = ops.linear(ops.layernorm(x, *Q["ln3"]), Q["ff1_w"], bias=Q["ff1_b"], geglu=True)
             x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x)
-        return ops.linear(x, P["out_w"], bias=P["out_b"], res=h)
+        out = ops.linear(x, P["out_w"], bias=P["out_b"], res=t_in)
+        return comm.to_frames(out, B, HW) if comm else out
 
     def _run_stage(self, stage, h, skip, emb, ctx, B, T, H, W):
         for P in stage:
             k = P["kind"]
             if k == "R":
-                h = self._res(P, h, skip, emb, B, T, H, W)
+                h = self._res(P, h, skip, emb, B, T, H, W, self._comm)
                 skip = None
             elif k == "S":
                 h = self._spatial_tf(P, h, ctx, B, T, H, W)
             elif k == "T":
-                h = self._temporal_tf(P, h, B, T, H, W)
+                h = self._temporal_tf(P, h, B, T, H, W, self._comm)
             elif k == "D":
                 cols, H, W = ops.im2col_s2(h, B * T, H, W)
                 h = ops.linear(cols, P["w"], bias=P["b"])
@@ -397,6 +412,11 @@ class UNetModel(nn.Module):
         if features_adapter is not None:
             _unsupported("features_adapter")
         P = self._packed or self._pack()
+        comm = self._comm
+        T_all = x.shape[2]
+        if comm:                                   # frame sharding: this rank owns frames [f0, f1) for every spatial op
+            f0, f1 = comm.bind(T_all)
+            x_full, x = x, x[:, :, f0:f1]
         B, Cin, T, H, W = x.shape
         dev = x.device
         x32 = x.float().contiguous()
@@ -413,8 +433,10 @@ class UNetModel(nn.Module):
         # --- context: text[:77] | image tokens; per-frame image tokens when L == 77 + 16*T (openaimodel3d.py:556-560) ---
         ctx16 = ops.cast_f16(context.float().contiguous())
         L = context.shape[1]
-        ctx = dict(text=[ctx16[b, :77] for b in range(B)], img=[ctx16[b, 77:] for b in range(B)] if L > 77 else None,
-                   img_per_frame=(L == 77 + T * 16))
+        per_frame = (L == 77 + T_all * 16)
+        img_lo, img_hi = (77 + 16 * f0, 77 + 16 * f1) if (comm and per_frame) else (77, L)
+        ctx = dict(text=[ctx16[b, :77] for b in range(B)], img=[ctx16[b, img_lo:img_hi] for b in range(B)] if L > 77 else None,
+                   img_per_frame=per_frame)
         # --- input latent -> rows [(b t) h w, Cin padded to 8] ---
         cin_pad = max(8, (Cin + 7) // 8 * 8)
         h = torch.zeros((B * T * H * W, cin_pad), device=dev, dtype=torch.float16) if cin_pad != Cin else \
@@ -431,4 +453,7 @@ class UNetModel(nn.Module):
         for stage in P["output"]:
             h, H, W = self._run_stage(stage, h, hs.pop(), emb, ctx, B, T, H, W)
         y = ops.conv3x3(ops.groupnorm(h, B * T, *P["out_gn"], 1e-5, True), B * T, H, W, P["out_w"], bias=P["out_b"], out_f32=True)
-        return ops.rows_to_ncthw(y, B, self.out_channels, T, H, W).to(x.dtype)
+        out = ops.rows_to_ncthw(y, B, self.out_channels, T, H, W)
+        if comm:                                   # every rank needs the whole prediction for the (global-std) DDIM update
+            out = comm.gather_frames(out, T_all)
+        return out.to(x.dtype)
