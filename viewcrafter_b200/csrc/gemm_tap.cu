@@ -6,11 +6,19 @@
 //                                       the zero padding is TMA out-of-bounds fill
 //   * Conv3d (3,1,1), pad (1,0,0)     : 3 taps, A rows shifted by +-H*W rows of the [T*H*W, C] matrix (OOB rows = 0)
 // A may come from two tensors split along K (channel concat of skip connections without materialising it).
-// Epilogue (TMEM -> regs): + bias[z/bias_z_div][n], GEGLU (value*gelu(gate)), + residual, fp16 / fp32 store.
+// Epilogue: + bias[z/bias_z_div][n], GEGLU (value*gelu(gate)), + residual, fp16 / fp32 store.
 //
-// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2..5 = epilogue.
-// Two CTAs are co-resident per SM (<=113 KB smem, <=256 TMEM columns each) so one CTA's epilogue overlaps the
-// other's main loop.
+// PERSISTENT kernel, one CTA per SM, 320 threads:
+//   warp 0      TMA producer: walks this CTA's tiles and their (tap, k-block) iterations through a smem ring without
+//               draining between tiles, so the loads of tile i+1 are in flight while tile i is still being multiplied
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; TWO accumulators in TMEM (double buffer), so the
+//               main loop of tile i+1 overlaps the epilogue of tile i
+//   warps 2..9  epilogue (two warps per TMEM lane quadrant, interleaved 32-column chunks): TMEM -> registers ->
+//               (+bias / GEGLU) -> fp32 staging tile in smem -> re-read so that 4 lanes cover 64 contiguous bytes of one
+//               output row (full 32-byte sectors for the residual load and the store) -> + residual -> store
+// Tiles are ordered n-fastest so CTAs that run concurrently share A tiles in L2.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -19,6 +27,9 @@ namespace vc {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int MAX_TAPS = 9;
+static constexpr int EPI_WARPS = 8;
+static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+static constexpr int SROW = 36;     // staging row pitch in floats (32 + 4 pad: conflict-free 128-bit access)
 
 struct GemmParams {
   CUtensorMap tmap_a;
@@ -32,6 +43,7 @@ struct GemmParams {
   int tap_dx[MAX_TAPS];
   int tap_dy[MAX_TAPS];
   int n_tiles;
+  int total_tiles;
   __half* out;
   float* out_f32;
   int ldo;
@@ -47,33 +59,47 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (112 * 1024) / STAGE_BYTES >= 4 ? 4 : (112 * 1024) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int STAGING_BYTES = EPI_WARPS * 32 * SROW * 4;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STAGING_BYTES;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
+  static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 2) gemm_tap_kernel(const __grid_constant__ GemmParams p) {
+struct TileCoord {
+  int x0, y0, z, n_tile;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  const int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  const int ty = m % p.tiles_y;
+  t.z = m / p.tiles_y;
+  t.x0 = tx * p.bx;
+  t.y0 = ty * p.by;
+  return t;
+}
+
+template <int BN, bool STAGED>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int tile = blockIdx.x;
-  const int n_tile = tile % p.n_tiles;
-  int m_tile = tile / p.n_tiles;
-  const int tx = m_tile % p.tiles_x;
-  m_tile /= p.tiles_x;
-  const int ty = m_tile % p.tiles_y;
-  const int z = m_tile / p.tiles_y;
-  const int x0 = tx * p.bx, y0 = ty * p.by, n0 = n_tile * BN;
   const int kblocks = (p.K + BK - 1) / BK;
   const int iters = p.num_taps * kblocks;
 
@@ -84,7 +110,10 @@ __global__ void __launch_bounds__(192, 2) gemm_tap_kernel(const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], EPI_WARPS * 32);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -97,154 +126,225 @@ __global__ void __launch_bounds__(192, 2) gemm_tap_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      int it = 0;
-      for (int tap = 0; tap < p.num_taps; ++tap) {
-        const int cx = x0 + p.tap_dx[tap], cy = y0 + p.tap_dy[tap];
-        const int brow = tap * p.N + n0;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % STAGES;
-          if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          const int k = kb * BK;
-          if (k < p.K1)
-            tma_load_4d(sa, &p.tmap_a, &full_bar[s], k, cx, cy, z);
-          else
-            tma_load_4d(sa, &p.tmap_a2, &full_bar[s], k - p.K1, cx, cy, z);
-          tma_load_2d(sb, &p.tmap_b, &full_bar[s], k, brow);
+      long long it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(p, tile);
+        const int n0 = tc.n_tile * BN;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
+          const int brow = tap * p.N + n0;
+          for (int kb = 0; kb < kblocks; ++kb, ++it) {
+            const int s = (int)(it % STAGES);
+            if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
+            uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+            const int k = kb * BK;
+            if (k < p.K1)
+              tma_load_4d(sa, &p.tmap_a, &full_bar[s], k, cx, cy, tc.z);
+            else
+              tma_load_4d(sa, &p.tmap_a2, &full_bar[s], k - p.K1, cx, cy, tc.z);
+            tma_load_2d(sb, &p.tmap_b, &full_bar[s], k, brow);
+          }
         }
       }
     }
   } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&full_bar[s], (it / STAGES) & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + Cfg::A_BYTES;
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = umma_desc_sw128(sa + k * 32);
-          const uint64_t db = umma_desc_sw128(sb + k * 32);
-          umma_ss(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+      long long it = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        if (lt >= 2) {                               // the epilogue must have drained this accumulator
+          mbar_wait(&tmem_empty_bar[acc], (uint32_t)((lt >> 1) - 1) & 1);
+          tc_fence_after();
         }
-        umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+        const uint32_t tacc = tmem_base + acc * BN;
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = (int)(it % STAGES);
+          mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * 32);
+            const uint64_t db = umma_desc_sw128(sb + k * 32);
+            umma_ss(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&tmem_full_bar[acc]);   // accumulator complete
       }
-      umma_commit(tmem_full_bar);     // accumulator complete
     }
   } else {
-    // ---------------- epilogue ----------------
-    // TMEM -> registers (one accumulator row per thread, 32 columns at a time) -> (+bias / GEGLU) -> fp32 staging tile in
-    // the now idle pipeline smem -> re-read so that 4 lanes cover 64 contiguous bytes of one output row (full 32-byte
-    // sectors for the residual load and the store) -> + residual -> fp16 / fp32 store.
+    // ------------------------------ epilogue ------------------------------
+    const int ew = warp - 2;                      // 0..7
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-    constexpr int SROW = 36;                      // staging row pitch in floats (32 + 4 pad: conflict-free 128-bit access)
-    float* stage = reinterpret_cast<float*>(smem) + q * 32 * SROW;
-    const float* bias = p.bias ? p.bias + (long long)(p.bias_z_div > 0 ? z / p.bias_z_div : 0) * p.N : nullptr;
+    const int half = ew >> 2;                     // which of the two warps of this quadrant
+    float* stage = staging + ew * 32 * SROW;
     const int rsub = lane >> 2, piece = lane & 3;
-
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     constexpr int HALF = BN / 2;
     const int nchunks = p.geglu ? HALF / 32 : BN / 32;
     const int n_out = p.geglu ? p.N / 2 : p.N;
-    const int ocol0 = p.geglu ? n_tile * HALF : n0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const TileCoord tc = tile_coord(p, tile);
+      const int acc = lt & 1;
+      const int n0 = tc.n_tile * BN;
+      const int ocol0 = p.geglu ? tc.n_tile * HALF : n0;
+      const float* bias = p.bias ? p.bias + (long long)(p.bias_z_div > 0 ? tc.z / p.bias_z_div : 0) * p.N : nullptr;
+      mbar_wait(&tmem_full_bar[acc], (uint32_t)(lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 
 #pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
-      float f[32];
-      __syncwarp();
-      if (!p.geglu) {
-        uint32_t v[32];
-        tmem_ld32(trow + c * 32, v);
-        tc_wait_ld();
-        const int nb = n0 + c * 32;
-        if (nb >= p.N) break;                      // warp-uniform
+      for (int c = half; c < nchunks; c += 2) {
+        float f[32];
+        __syncwarp();
+        if (!p.geglu) {
+          uint32_t v[32];
+          tmem_ld32(trow + c * 32, v);
+          tc_wait_ld();
+          const int nb = n0 + c * 32;
+          if (nb >= p.N) break;                      // warp-uniform
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (bias) {
-          if (nb + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) f[j] += __ldg(bias + nb + j);
-          }
-        }
-      } else {
-        // GEGLU: tile columns [0,BN/2) are values, [BN/2,BN) the matching gates (weights were interleaved per tile).
-        uint32_t a[32], g[32];
-        tmem_ld32(trow + c * 32, a);
-        tmem_ld32(trow + HALF + c * 32, g);
-        tc_wait_ld();
-        const int nv = n0 + c * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float va = __uint_as_float(a[j]), vg = __uint_as_float(g[j]);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (bias) {
-            va += __ldg(bias + nv + j);
-            vg += __ldg(bias + nv + HALF + j);
-          }
-          f[j] = va * gelu_erf_fast(vg);
-        }
-      }
-      float4* srow = reinterpret_cast<float4*>(stage + lane * SROW);
+            if (nb + 32 <= p.N) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) srow[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-      __syncwarp();
-      const int col = ocol0 + c * 32 + piece * 8;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
+                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+              }
+            } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = 8 * i + rsub;
-        const int R = q * 32 + rr;
-        const int x = x0 + (R % p.bx), y = y0 + (R / p.bx);
-        if (x >= p.X || y >= p.Y || col >= n_out) continue;
-        const long long orow = ((long long)z * p.Y + y) * p.X + x;
-        const float4 lo = *reinterpret_cast<const float4*>(stage + rr * SROW + piece * 8);
-        const float4 hi = *reinterpret_cast<const float4*>(stage + rr * SROW + piece * 8 + 4);
-        float o[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        if (col + 8 <= n_out && (p.ldo & 7) == 0) {
-          if (p.res) {
-            const uint4 u = *reinterpret_cast<const uint4*>(p.res + orow * p.ldr + col);   // plain load: res may alias out
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 t = __half22float2(h[e]);
-              o[2 * e] += t.x; o[2 * e + 1] += t.y;
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) f[j] += __ldg(bias + nb + j);
             }
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + col);
-            op[0] = make_float4(o[0], o[1], o[2], o[3]);
-            op[1] = make_float4(o[4], o[5], o[6], o[7]);
-          } else {
-            uint4 u;
-            u.x = pack_half2(o[0], o[1]); u.y = pack_half2(o[2], o[3]);
-            u.z = pack_half2(o[4], o[5]); u.w = pack_half2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(p.out + orow * p.ldo + col) = u;
           }
         } else {
-          // ragged N tail / unaligned pitch (e.g. the 320->4 output conv): predicated scalar path
+          // GEGLU: tile columns [0,BN/2) are values, [BN/2,BN) the matching gates (weights were interleaved per tile).
+          uint32_t a[32], g[32];
+          tmem_ld32(trow + c * 32, a);
+          tmem_ld32(trow + HALF + c * 32, g);
+          tc_wait_ld();
+          const int nv = n0 + c * 32;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            if (col + e < n_out) {
-              float t = o[e];
-              if (p.res) t += __half2float(p.res[orow * p.ldr + col + e]);
-              if (p.out_f32) p.out_f32[orow * p.ldo + col + e] = t;
-              else p.out[orow * p.ldo + col + e] = __float2half_rn(t);
+          for (int j = 0; j < 32; ++j) {
+            float va = __uint_as_float(a[j]), vg = __uint_as_float(g[j]);
+            if (bias) {
+              va += __ldg(bias + nv + j);
+              vg += __ldg(bias + nv + HALF + j);
+            }
+            f[j] = va * gelu_erf_fast(vg);
+          }
+        }
+        if constexpr (!STAGED) {
+          // direct epilogue: this thread owns accumulator row R; 64 contiguous bytes (two full sectors) per chunk
+          const int R = q * 32 + lane;
+          const int x = tc.x0 + (R % p.bx), y = tc.y0 + (R / p.bx);
+          const int col0 = ocol0 + c * 32;
+          if (x < p.X && y < p.Y && col0 < n_out) {
+            const long long orow = ((long long)tc.z * p.Y + y) * p.X + x;
+            if (col0 + 32 <= n_out && (p.ldo & 7) == 0) {
+              if (p.res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.res + orow * p.ldr + col0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 u = rp[j];                       // plain load: res may alias out
+                  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 t = __half22float2(h[e]);
+                    f[j * 8 + 2 * e] += t.x; f[j * 8 + 2 * e + 1] += t.y;
+                  }
+                }
+              }
+              if (p.out_f32) {
+                float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + col0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              } else {
+                uint4* op = reinterpret_cast<uint4*>(p.out + orow * p.ldo + col0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 u;
+                  u.x = pack_half2(f[8 * j], f[8 * j + 1]); u.y = pack_half2(f[8 * j + 2], f[8 * j + 3]);
+                  u.z = pack_half2(f[8 * j + 4], f[8 * j + 5]); u.w = pack_half2(f[8 * j + 6], f[8 * j + 7]);
+                  op[j] = u;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                if (col0 + e < n_out) {
+                  float t = f[e];
+                  if (p.res) t += __half2float(p.res[orow * p.ldr + col0 + e]);
+                  if (p.out_f32) p.out_f32[orow * p.ldo + col0 + e] = t;
+                  else p.out[orow * p.ldo + col0 + e] = __float2half_rn(t);
+                }
+              }
+            }
+          }
+          continue;
+        }
+        float4* srow = reinterpret_cast<float4*>(stage + lane * SROW);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) srow[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        __syncwarp();
+        const int col = ocol0 + c * 32 + piece * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = 8 * i + rsub;
+          const int R = q * 32 + rr;
+          const int x = tc.x0 + (R % p.bx), y = tc.y0 + (R / p.bx);
+          if (x >= p.X || y >= p.Y || col >= n_out) continue;
+          const long long orow = ((long long)tc.z * p.Y + y) * p.X + x;
+          const float4 lo = *reinterpret_cast<const float4*>(stage + rr * SROW + piece * 8);
+          const float4 hi = *reinterpret_cast<const float4*>(stage + rr * SROW + piece * 8 + 4);
+          float o[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          if (col + 8 <= n_out && (p.ldo & 7) == 0) {
+            if (p.res) {
+              const uint4 u = *reinterpret_cast<const uint4*>(p.res + orow * p.ldr + col);   // plain load: res may alias out
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = __half22float2(h[e]);
+                o[2 * e] += t.x; o[2 * e + 1] += t.y;
+              }
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + col);
+              op[0] = make_float4(o[0], o[1], o[2], o[3]);
+              op[1] = make_float4(o[4], o[5], o[6], o[7]);
+            } else {
+              uint4 u;
+              u.x = pack_half2(o[0], o[1]); u.y = pack_half2(o[2], o[3]);
+              u.z = pack_half2(o[4], o[5]); u.w = pack_half2(o[6], o[7]);
+              *reinterpret_cast<uint4*>(p.out + orow * p.ldo + col) = u;
+            }
+          } else {
+            // ragged N tail / unaligned pitch (e.g. the 320->4 output conv): predicated scalar path
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (col + e < n_out) {
+                float t = o[e];
+                if (p.res) t += __half2float(p.res[orow * p.ldr + col + e]);
+                if (p.out_f32) p.out_f32[orow * p.ldo + col + e] = t;
+                else p.out[orow * p.ldo + col + e] = __float2half_rn(t);
+              }
             }
           }
         }
       }
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
 
@@ -256,17 +356,32 @@ __global__ void __launch_bounds__(192, 2) gemm_tap_kernel(const __grid_constant_
   }
 }
 
-template <int BN>
-static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+static int epilogue_mode() {
+  static int mode = -1;                     // tuning switch: VC_GEMM_EPI=staged|direct
+  if (mode < 0) {
+    const char* e = getenv("VC_GEMM_EPI");
+    mode = (e && e[0] == 's') ? 1 : 0;
+  }
+  return mode;
+}
+
+template <int BN, bool STAGED>
+static int launch_gemm_v(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    VC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  gemm_tap_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  gemm_tap_kernel<BN, STAGED><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;
+}
+
+template <int BN>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  return epilogue_mode() ? launch_gemm_v<BN, true>(p, stream) : launch_gemm_v<BN, false>(p, stream);
 }
 
 static int pick_bn(int N, int geglu) {
@@ -334,15 +449,16 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   p.bias = d.bias; p.bias_z_div = d.bias_z_div;
   p.res = d.res; p.ldr = d.ldr;
   p.geglu = d.geglu;
-  const long long grid = (long long)p.tiles_x * p.tiles_y * p.Z * p.n_tiles;
-  VC_REQUIRE(grid > 0 && grid < (1ll << 31), "gemm_tap: grid %lld out of range", grid);
+  const long long total = (long long)p.tiles_x * p.tiles_y * p.Z * p.n_tiles;
+  VC_REQUIRE(total > 0 && total < (1ll << 31), "gemm_tap: tile count %lld out of range", total);
+  p.total_tiles = (int)total;
   switch (BN) {
-    case 32: return launch_gemm<32>(p, (int)grid, stream);
-    case 64: return launch_gemm<64>(p, (int)grid, stream);
-    case 96: return launch_gemm<96>(p, (int)grid, stream);
-    case 128: return launch_gemm<128>(p, (int)grid, stream);
-    case 160: return launch_gemm<160>(p, (int)grid, stream);
-    case 256: return launch_gemm<256>(p, (int)grid, stream);
+    case 32: return launch_gemm<32>(p, stream);
+    case 64: return launch_gemm<64>(p, stream);
+    case 96: return launch_gemm<96>(p, stream);
+    case 128: return launch_gemm<128>(p, stream);
+    case 160: return launch_gemm<160>(p, stream);
+    case 256: return launch_gemm<256>(p, stream);
   }
   set_error("gemm_tap: no kernel for BN=%d", BN);
   return VC_ERR_UNSUPPORTED;

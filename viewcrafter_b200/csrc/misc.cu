@@ -1,124 +1,10 @@
-// Small / HBM-bound kernels of the denoise step: temporal self-attention over T<=32 frames,
+// Small / HBM-bound kernels of the denoise step:
 // nearest-2x upsample, stride-2 im2col, layout conversions, the timestep/fps embedding MLP pieces
 // and the fused DDIM update.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vc {
-
-// ------------------------------------------------------------------------------------------------
-// Temporal self-attention (attention.py:81-126 with N = T frames, batch = spatial sites):
-// one warp per (site, head); lane t owns query frame t.  q/k/v rows live at row (t*sites + site).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) temporal_attn_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
-                                                            const __half* __restrict__ v, int ld, __half* __restrict__ out, int ldo,
-                                                            int T, long long sites, int heads, float scale) {
-  __shared__ __align__(16) __half ks[4][32][64];
-  __shared__ __align__(16) __half vs[4][32][64];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long pairs = sites * heads;
-  for (long long pair = (long long)blockIdx.x * 4 + w; pair < pairs; pair += (long long)gridDim.x * 4) {
-    const long long site = pair / heads;
-    const int head = (int)(pair % heads);
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int j = (lane >> 3) + 4 * i;
-      if (j < T) {
-        const long long off = ((long long)j * sites + site) * ld + head * 64 + (lane & 7) * 8;
-        *reinterpret_cast<uint4*>(&ks[w][j][(lane & 7) * 8]) = *reinterpret_cast<const uint4*>(k + off);
-        *reinterpret_cast<uint4*>(&vs[w][j][(lane & 7) * 8]) = *reinterpret_cast<const uint4*>(v + off);
-      }
-    }
-    __syncwarp();
-    if (lane < T) {
-      float qf[64];
-      const __half* qp = q + ((long long)lane * sites + site) * ld + head * 64;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 u = *reinterpret_cast<const uint4*>(qp + i * 8);
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 t = __half22float2(h[e]);
-          qf[i * 8 + 2 * e] = t.x * scale;
-          qf[i * 8 + 2 * e + 1] = t.y * scale;
-        }
-      }
-      float sc[32];
-      float m = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float s = -INFINITY;
-        if (j < T) {
-          s = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint4 u = *reinterpret_cast<const uint4*>(&ks[w][j][i * 8]);
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 t = __half22float2(h[e]);
-              s += qf[i * 8 + 2 * e] * t.x + qf[i * 8 + 2 * e + 1] * t.y;
-            }
-          }
-        }
-        sc[j] = s;
-        m = fmaxf(m, s);
-      }
-      float l = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float p = (j < T) ? __expf(sc[j] - m) : 0.f;
-        sc[j] = p;
-        l += p;
-      }
-      const float inv = 1.f / l;
-      float o[64];
-#pragma unroll
-      for (int d = 0; d < 64; ++d) o[d] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < T) {
-          const float p = sc[j] * inv;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint4 u = *reinterpret_cast<const uint4*>(&vs[w][j][i * 8]);
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 t = __half22float2(h[e]);
-              o[i * 8 + 2 * e] += p * t.x;
-              o[i * 8 + 2 * e + 1] += p * t.y;
-            }
-          }
-        }
-      }
-      __half* op = out + ((long long)lane * sites + site) * ldo + head * 64;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint4 u;
-        u.x = pack_half2(o[i * 8 + 0], o[i * 8 + 1]); u.y = pack_half2(o[i * 8 + 2], o[i * 8 + 3]);
-        u.z = pack_half2(o[i * 8 + 4], o[i * 8 + 5]); u.w = pack_half2(o[i * 8 + 6], o[i * 8 + 7]);
-        *reinterpret_cast<uint4*>(op + i * 8) = u;
-      }
-    }
-  }
-}
-
-int temporal_attn(const __half* q, const __half* k, const __half* v, int ld, __half* out, int ldo, int T, long long sites,
-                  int heads, float scale, cudaStream_t stream) {
-  VC_REQUIRE(q && k && v && out, "temporal_attn: null pointer");
-  VC_REQUIRE(T >= 1 && T <= 32, "temporal_attn: T=%d unsupported (1..32)", T);
-  VC_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "temporal_attn: pitches must be multiples of 8");
-  const long long pairs = sites * heads;
-  long long blocks = (pairs + 3) / 4;
-  const long long cap = (long long)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  temporal_attn_kernel<<<(unsigned)blocks, 128, 0, stream>>>(q, k, v, ld, out, ldo, T, sites, heads, scale);
-  VC_CHECK_CUDA(cudaGetLastError());
-  return VC_OK;
-}
 
 // ------------------------------------------------------------------------------------------------
 // nearest 2x upsample (F.interpolate scale 2, openaimodel3d.py:101-104 / ae_modules.py:123), NHWC, 16-byte vectors
