@@ -1,0 +1,29 @@
+"""Short target for `ncu --set full`: a few launches of the dominant kernels at their headline shapes."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from viewcrafter_b200 import ops
+T, H, W, C = 25, 72, 128, 320
+M = T * H * W
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+x = (torch.randn(M, C, device="cuda") * 0.5).half()
+if which in ("gemm", "all"):
+    w9 = (torch.randn(9 * C, C, device="cuda") * 0.02).half()
+    b = torch.zeros(C, device="cuda")
+    for _ in range(3):
+        ops.conv3x3(x, T, H, W, w9, bias=b, res=x)
+if which in ("attn", "all"):
+    qkv = (torch.randn(M, 3 * C, device="cuda") * 0.5).half()
+    for _ in range(3):
+        ops.flash_attn(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], T, H * W, H * W, 5)
+if which in ("norm", "all"):
+    g, be = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    for _ in range(3):
+        ops.groupnorm(x, T, g, be, 1e-5, True)
+        ops.layernorm(x, g, be)
+if which in ("tattn", "all"):
+    qkv = (torch.randn(M, 3 * C, device="cuda") * 0.5).half()
+    for _ in range(3):
+        ops.temporal_attn(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], T, H * W, 5)
+torch.cuda.synchronize()
+print("done")

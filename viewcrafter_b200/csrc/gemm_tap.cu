@@ -8,17 +8,16 @@
 // A may come from two tensors split along K (channel concat of skip connections without materialising it).
 // Epilogue: + bias[z/bias_z_div][n], GEGLU (value*gelu(gate)), + residual, fp16 / fp32 store.
 //
-// PERSISTENT kernel, one CTA per SM, 320 threads:
-//   warp 0      TMA producer: walks this CTA's tiles and their (tap, k-block) iterations through a smem ring without
-//               draining between tiles, so the loads of tile i+1 are in flight while tile i is still being multiplied
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; TWO accumulators in TMEM (double buffer), so the
-//               main loop of tile i+1 overlaps the epilogue of tile i
-//   warps 2..9  epilogue (two warps per TMEM lane quadrant, interleaved 32-column chunks): TMEM -> registers ->
-//               (+bias / GEGLU) -> fp32 staging tile in smem -> re-read so that 4 lanes cover 64 contiguous bytes of one
-//               output row (full 32-byte sectors for the residual load and the store) -> + residual -> store
+// PERSISTENT kernel, one CTA per SM, 576 threads:
+//   warp 0       TMA producer: walks this CTA's tiles and their (tap, k-block) iterations through a smem ring without
+//                draining between tiles, so the loads of tile i+1 are in flight while tile i is still being multiplied
+//   warp 1       TMEM allocator + single-thread tcgen05.mma issuer; TWO accumulators in TMEM (double buffer), so the
+//                main loop of tile i+1 overlaps the epilogue of tile i
+//   warps 2..17  epilogue: four warps per TMEM lane quadrant take interleaved 32-column chunks; each thread owns one
+//                accumulator row: TMEM -> registers -> (+bias / GEGLU / +residual) -> 256-bit global stores (every
+//                store / residual load covers whole 32-byte sectors).  Measured on B200: this beats an smem-staged
+//                "coalesced" epilogue on every shape (profiles/README.md).
 // Tiles are ordered n-fastest so CTAs that run concurrently share A tiles in L2.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.h"
 
@@ -27,9 +26,9 @@ namespace vc {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int MAX_TAPS = 9;
-static constexpr int EPI_WARPS = 8;
+static constexpr int EPI_WARPS = 16;
+static constexpr int EPI_PER_QUAD = EPI_WARPS / 4;
 static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
-static constexpr int SROW = 36;     // staging row pitch in floats (32 + 4 pad: conflict-free 128-bit access)
 
 struct GemmParams {
   CUtensorMap tmap_a;
@@ -52,6 +51,7 @@ struct GemmParams {
   const __half* res;
   int ldr;
   int geglu;
+  int vec_ok;            // rows are 32-byte aligned: the 256-bit epilogue path may be used
 };
 
 template <int BN>
@@ -59,13 +59,12 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = EPI_WARPS * 32 * SROW * 4;
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - STAGING_BYTES;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
-  static_assert(STAGES >= 3, "pipeline too shallow");
+  static_assert(STAGES >= 4, "pipeline too shallow");
 };
 
 struct TileCoord {
@@ -85,14 +84,43 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile) {
   return t;
 }
 
-template <int BN, bool STAGED>
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one instruction moves a full 32-byte sector per thread
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* ptr, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(ptr)
+               : "memory");
+}
+
+// exact-erf GELU (attention.py:415-422 uses F.gelu), erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): 2 MUFU + ~12 FMA/ALU
+__device__ __forceinline__ float gelu_epilogue(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, copysignf(erf_abs, z), hx);
+}
+
+template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
@@ -183,14 +211,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
     }
   } else {
     // ------------------------------ epilogue ------------------------------
-    const int ew = warp - 2;                      // 0..7
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;                     // which of the two warps of this quadrant
-    float* stage = staging + ew * 32 * SROW;
-    const int rsub = lane >> 2, piece = lane & 3;
+    const int sub = (warp - 2) >> 2;              // which of the EPI_PER_QUAD warps of this quadrant
     constexpr int HALF = BN / 2;
     const int nchunks = p.geglu ? HALF / 32 : BN / 32;
     const int n_out = p.geglu ? p.N / 2 : p.N;
+    const int R = q * 32 + lane;                  // accumulator row owned by this thread
+    const int rx = R % p.bx, ry = R / p.bx;
+    const bool vec_ok = p.vec_ok != 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const TileCoord tc = tile_coord(p, tile);
@@ -198,12 +226,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
       const int n0 = tc.n_tile * BN;
       const int ocol0 = p.geglu ? tc.n_tile * HALF : n0;
       const float* bias = p.bias ? p.bias + (long long)(p.bias_z_div > 0 ? tc.z / p.bias_z_div : 0) * p.N : nullptr;
+      const int x = tc.x0 + rx, y = tc.y0 + ry;
+      const bool row_ok = x < p.X && y < p.Y;
+      const long long orow = ((long long)tc.z * p.Y + y) * p.X + x;
       mbar_wait(&tmem_full_bar[acc], (uint32_t)(lt >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 
 #pragma unroll 1
-      for (int c = half; c < nchunks; c += 2) {
+      for (int c = sub; c < nchunks; c += EPI_PER_QUAD) {
         float f[32];
         __syncwarp();
         if (!p.geglu) {
@@ -235,109 +266,62 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
           tc_wait_ld();
           const int nv = n0 + c * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float va = __uint_as_float(a[j]), vg = __uint_as_float(g[j]);
+          for (int j = 0; j < 32; j += 4) {
+            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
             if (bias) {
-              va += __ldg(bias + nv + j);
-              vg += __ldg(bias + nv + HALF + j);
+              ba = __ldg(reinterpret_cast<const float4*>(bias + nv + j));
+              bg = __ldg(reinterpret_cast<const float4*>(bias + nv + HALF + j));
             }
-            f[j] = va * gelu_erf_fast(vg);
+            f[j] = (__uint_as_float(a[j]) + ba.x) * gelu_epilogue(__uint_as_float(g[j]) + bg.x);
+            f[j + 1] = (__uint_as_float(a[j + 1]) + ba.y) * gelu_epilogue(__uint_as_float(g[j + 1]) + bg.y);
+            f[j + 2] = (__uint_as_float(a[j + 2]) + ba.z) * gelu_epilogue(__uint_as_float(g[j + 2]) + bg.z);
+            f[j + 3] = (__uint_as_float(a[j + 3]) + ba.w) * gelu_epilogue(__uint_as_float(g[j + 3]) + bg.w);
           }
         }
-        if constexpr (!STAGED) {
-          // direct epilogue: this thread owns accumulator row R; 64 contiguous bytes (two full sectors) per chunk
-          const int R = q * 32 + lane;
-          const int x = tc.x0 + (R % p.bx), y = tc.y0 + (R / p.bx);
-          const int col0 = ocol0 + c * 32;
-          if (x < p.X && y < p.Y && col0 < n_out) {
-            const long long orow = ((long long)tc.z * p.Y + y) * p.X + x;
-            if (col0 + 32 <= n_out && (p.ldo & 7) == 0) {
-              if (p.res) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.res + orow * p.ldr + col0);
+        const int col0 = ocol0 + c * 32;
+        if (!row_ok || col0 >= n_out) continue;
+        if (col0 + 32 <= n_out && vec_ok) {
+          if (p.res) {
+            const __half* rp = p.res + orow * p.ldr + col0;      // plain loads: res may alias out (in-place residual)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 u = rp[j];                       // plain load: res may alias out
-                  const __half2* h = reinterpret_cast<const __half2*>(&u);
+            for (int j = 0; j < 2; ++j) {
+              uint32_t u[8];
+              ld_global_256(rp + j * 16, u);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 t = __half22float2(h[e]);
-                    f[j * 8 + 2 * e] += t.x; f[j * 8 + 2 * e + 1] += t.y;
-                  }
-                }
-              }
-              if (p.out_f32) {
-                float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + col0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-              } else {
-                uint4* op = reinterpret_cast<uint4*>(p.out + orow * p.ldo + col0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uint4 u;
-                  u.x = pack_half2(f[8 * j], f[8 * j + 1]); u.y = pack_half2(f[8 * j + 2], f[8 * j + 3]);
-                  u.z = pack_half2(f[8 * j + 4], f[8 * j + 5]); u.w = pack_half2(f[8 * j + 6], f[8 * j + 7]);
-                  op[j] = u;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) {
-                if (col0 + e < n_out) {
-                  float t = f[e];
-                  if (p.res) t += __half2float(p.res[orow * p.ldr + col0 + e]);
-                  if (p.out_f32) p.out_f32[orow * p.ldo + col0 + e] = t;
-                  else p.out[orow * p.ldo + col0 + e] = __float2half_rn(t);
-                }
+              for (int e = 0; e < 8; ++e) {
+                const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&u[e]));
+                f[j * 16 + 2 * e] += t.x; f[j * 16 + 2 * e + 1] += t.y;
               }
             }
           }
-          continue;
-        }
-        float4* srow = reinterpret_cast<float4*>(stage + lane * SROW);
+          if (p.out_f32) {
+            float* op = p.out_f32 + orow * p.ldo + col0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) srow[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        __syncwarp();
-        const int col = ocol0 + c * 32 + piece * 8;
+            for (int j = 0; j < 4; ++j) {
+              uint32_t u[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = 8 * i + rsub;
-          const int R = q * 32 + rr;
-          const int x = tc.x0 + (R % p.bx), y = tc.y0 + (R / p.bx);
-          if (x >= p.X || y >= p.Y || col >= n_out) continue;
-          const long long orow = ((long long)tc.z * p.Y + y) * p.X + x;
-          const float4 lo = *reinterpret_cast<const float4*>(stage + rr * SROW + piece * 8);
-          const float4 hi = *reinterpret_cast<const float4*>(stage + rr * SROW + piece * 8 + 4);
-          float o[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-          if (col + 8 <= n_out && (p.ldo & 7) == 0) {
-            if (p.res) {
-              const uint4 u = *reinterpret_cast<const uint4*>(p.res + orow * p.ldr + col);   // plain load: res may alias out
-              const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 t = __half22float2(h[e]);
-                o[2 * e] += t.x; o[2 * e + 1] += t.y;
-              }
-            }
-            if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + col);
-              op[0] = make_float4(o[0], o[1], o[2], o[3]);
-              op[1] = make_float4(o[4], o[5], o[6], o[7]);
-            } else {
-              uint4 u;
-              u.x = pack_half2(o[0], o[1]); u.y = pack_half2(o[2], o[3]);
-              u.z = pack_half2(o[4], o[5]); u.w = pack_half2(o[6], o[7]);
-              *reinterpret_cast<uint4*>(p.out + orow * p.ldo + col) = u;
+              for (int e = 0; e < 8; ++e) u[e] = __float_as_uint(f[j * 8 + e]);
+              st_global_256(op + j * 8, u);
             }
           } else {
-            // ragged N tail / unaligned pitch (e.g. the 320->4 output conv): predicated scalar path
+            __half* op = p.out + orow * p.ldo + col0;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if (col + e < n_out) {
-                float t = o[e];
-                if (p.res) t += __half2float(p.res[orow * p.ldr + col + e]);
-                if (p.out_f32) p.out_f32[orow * p.ldo + col + e] = t;
-                else p.out[orow * p.ldo + col + e] = __float2half_rn(t);
-              }
+            for (int j = 0; j < 2; ++j) {
+              uint32_t u[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) u[e] = pack_half2(f[j * 16 + 2 * e], f[j * 16 + 2 * e + 1]);
+              st_global_256(op + j * 16, u);
+            }
+          }
+        } else {
+          // ragged N tail / unaligned pitch (e.g. the 320->4 output conv): predicated scalar path
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (col0 + e < n_out) {
+              float t = f[e];
+              if (p.res) t += __half2float(p.res[orow * p.ldr + col0 + e]);
+              if (p.out_f32) p.out_f32[orow * p.ldo + col0 + e] = t;
+              else p.out[orow * p.ldo + col0 + e] = __float2half_rn(t);
             }
           }
         }
@@ -356,32 +340,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
   }
 }
 
-static int epilogue_mode() {
-  static int mode = -1;                     // tuning switch: VC_GEMM_EPI=staged|direct
-  if (mode < 0) {
-    const char* e = getenv("VC_GEMM_EPI");
-    mode = (e && e[0] == 's') ? 1 : 0;
-  }
-  return mode;
-}
-
-template <int BN, bool STAGED>
-static int launch_gemm_v(const GemmParams& p, cudaStream_t stream) {
+template <int BN>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    VC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    VC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  gemm_tap_kernel<BN, STAGED><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  gemm_tap_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;
-}
-
-template <int BN>
-static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  return epilogue_mode() ? launch_gemm_v<BN, true>(p, stream) : launch_gemm_v<BN, false>(p, stream);
 }
 
 static int pick_bn(int N, int geglu) {
@@ -404,13 +374,14 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   VC_REQUIRE(d.bx * d.by == BM && d.bx >= 1, "gemm_tap: box %dx%d must cover 128 rows", d.bx, d.by);
   VC_REQUIRE(d.by == 1 || d.bx == d.X, "gemm_tap: multi-row boxes need bx == X (X=%d bx=%d)", d.X, d.bx);
   VC_REQUIRE(d.K % 8 == 0 && d.lda % 8 == 0, "gemm_tap: K and lda must be multiples of 8 (TMA 16-byte strides)");
-  VC_REQUIRE(d.out_f32 || d.N < 32 || d.ldo % 8 == 0, "gemm_tap: ldo must be a multiple of 8");
   VC_REQUIRE(d.K1 == d.K || (d.a2 && d.K1 % BK == 0 && d.K1 < d.K), "gemm_tap: bad K split K1=%d K=%d", d.K1, d.K);
   VC_REQUIRE(!d.geglu || (d.N % 128 == 0 && !d.res && !d.out_f32), "gemm_tap: GEGLU needs N %% 128 == 0");
   if ((reinterpret_cast<uintptr_t>(d.a) & 15) || (reinterpret_cast<uintptr_t>(d.w) & 15)) {
     set_error("gemm_tap: operands must be 16-byte aligned");
     return VC_ERR_ARG;
   }
+  const void* optr = d.out_f32 ? (const void*)d.out_f32 : (const void*)d.out;
+  const int esz = d.out_f32 ? 4 : 2;
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -449,6 +420,11 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   p.bias = d.bias; p.bias_z_div = d.bias_z_div;
   p.res = d.res; p.ldr = d.ldr;
   p.geglu = d.geglu;
+  // 256-bit epilogue accesses need 32-byte aligned rows (true for every activation on the U-Net / VAE path); anything
+  // else (odd pitches, the 4- and 3-channel output convs) takes the predicated scalar path inside the kernel
+  const bool o_al = ((reinterpret_cast<uintptr_t>(optr) & 31) == 0) && ((long long)d.ldo * esz) % 32 == 0;
+  const bool r_al = !d.res || (((reinterpret_cast<uintptr_t>(d.res) & 31) == 0) && ((long long)d.ldr * 2) % 32 == 0);
+  p.vec_ok = (o_al && r_al) ? 1 : 0;
   const long long total = (long long)p.tiles_x * p.tiles_y * p.Z * p.n_tiles;
   VC_REQUIRE(total > 0 && total < (1ll << 31), "gemm_tap: tile count %lld out of range", total);
   p.total_tiles = (int)total;
