@@ -14,8 +14,6 @@
 // Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2..5 = softmax /
 // correction / epilogue (TMEM lane quadrant = warp % 4).
 // TMEM columns: [0,128) S fp32 | [128,192) P fp16x2 | [192,256) O fp32.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.h"
 
@@ -42,18 +40,6 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-__device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
-  uint32_t y;
-  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
-  return y;
-}
-
-template <bool F16X2>
 __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -187,53 +173,29 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
       const float neg_m = -m;
       float psum = 0.f;
       // probabilities, packed in place: s0[0..15] <- s0, s0[16..31] <- s1, s2[0..15] <- s2, s2[16..31] <- s3
-      if constexpr (F16X2) {
-        // MUFU is the bottleneck of d=64 attention on Blackwell: ex2.approx.f16x2 produces TWO probabilities per MUFU
-        // op, already in the fp16 format the P operand needs.  Row sums: half2 partial sums over 16 values, then fp32.
-        auto run = [&](uint32_t (&src)[32], uint32_t* dst) {
 #pragma unroll
-          for (int blk = 0; blk < 2; ++blk) {
-            uint32_t hs = 0u;                                   // half2 (0, 0)
+      for (int e = 0; e < 32; e += 2) {
+        const float a0 = ex2f(fmaf(__uint_as_float(s0[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s0[e + 1]), sl2, neg_m));
+        psum += a0 + a1;
+        s0[e / 2] = pack_half2(a0, a1);
+      }
 #pragma unroll
-            for (int e = blk * 16; e < blk * 16 + 16; e += 2) {
-              const uint32_t x2 = pack_half2(fmaf(__uint_as_float(src[e]), sl2, neg_m), fmaf(__uint_as_float(src[e + 1]), sl2, neg_m));
-              const uint32_t p2 = ex2_h2(x2);
-              hs = hadd2_u32(hs, p2);
-              dst[e / 2] = p2;
-            }
-            const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&hs));
-            psum += f2.x + f2.y;
-          }
-        };
-        run(s0, s0);
-        run(s1, s0 + 16);
-        run(s2, s2);
-        run(s3, s2 + 16);
-      } else {
+      for (int e = 0; e < 32; e += 2) {
+        const float a0 = ex2f(fmaf(__uint_as_float(s1[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s1[e + 1]), sl2, neg_m));
+        psum += a0 + a1;
+        s0[16 + e / 2] = pack_half2(a0, a1);
+      }
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float a0 = ex2f(fmaf(__uint_as_float(s0[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s0[e + 1]), sl2, neg_m));
-          psum += a0 + a1;
-          s0[e / 2] = pack_half2(a0, a1);
-        }
+      for (int e = 0; e < 32; e += 2) {
+        const float a0 = ex2f(fmaf(__uint_as_float(s2[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s2[e + 1]), sl2, neg_m));
+        psum += a0 + a1;
+        s2[e / 2] = pack_half2(a0, a1);
+      }
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float a0 = ex2f(fmaf(__uint_as_float(s1[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s1[e + 1]), sl2, neg_m));
-          psum += a0 + a1;
-          s0[16 + e / 2] = pack_half2(a0, a1);
-        }
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float a0 = ex2f(fmaf(__uint_as_float(s2[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s2[e + 1]), sl2, neg_m));
-          psum += a0 + a1;
-          s2[e / 2] = pack_half2(a0, a1);
-        }
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float a0 = ex2f(fmaf(__uint_as_float(s3[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s3[e + 1]), sl2, neg_m));
-          psum += a0 + a1;
-          s2[16 + e / 2] = pack_half2(a0, a1);
-        }
+      for (int e = 0; e < 32; e += 2) {
+        const float a0 = ex2f(fmaf(__uint_as_float(s3[e]), sl2, neg_m)), a1 = ex2f(fmaf(__uint_as_float(s3[e + 1]), sl2, neg_m));
+        psum += a0 + a1;
+        s2[16 + e / 2] = pack_half2(a0, a1);
       }
       l += psum;
       if (j > 0) {
@@ -326,18 +288,13 @@ int flash_attn_d64(const AttnDesc& d, cudaStream_t stream) {
   p.out = d.out; p.ldo = d.ldo; p.Nq = d.Nq; p.Nk = d.Nk; p.kv_shared = shared;
   p.scale_log2 = d.scale * 1.4426950408889634f;
   p.accumulate = d.accumulate;
-  static int mode = -1;                      // tuning switch: VC_ATTN_EXP=f32 selects one fp32 exp2 per MUFU op
-  if (mode < 0) {
-    const char* e = getenv("VC_ATTN_EXP");
-    mode = (e && e[0] == 'f' && e[1] == '3') ? 0 : 1;
-    VC_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    VC_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+  static bool configured = false;
+  if (!configured) {
+    VC_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    configured = true;
   }
   dim3 grid((d.Nq + ATT_BM - 1) / ATT_BM, d.heads, d.B);
-  if (mode)
-    flash_attn_d64_kernel<true><<<grid, 192, ATT_SMEM, stream>>>(p);
-  else
-    flash_attn_d64_kernel<false><<<grid, 192, ATT_SMEM, stream>>>(p);
+  flash_attn_d64_kernel<<<grid, 192, ATT_SMEM, stream>>>(p);
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;
 }
