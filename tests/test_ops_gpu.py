@@ -289,6 +289,42 @@ def test_linear_strided_weight_view(ops):
     close(out, ref, 2e-2, rtol=2e-3, what="strided w")
 
 
+def test_gemm_cta_pair_path(ops):
+    """Shapes large enough to be routed to the tcgen05 cta_group::2 kernel (>= 148 tile pairs): odd m-tile counts
+    (last pair half empty), ragged M, bias + residual, GEGLU, K-split concat, 3x3 conv taps and temporal taps."""
+    M = 128 * 301 + 37
+    x, w = rnd(M, 320, seed=80), rnd(320, 320, seed=81, scale=320 ** -0.5)
+    b, r = rnd(320, seed=82, dtype=torch.float32), rnd(M, 320, seed=83)
+    close(ops.linear(x, w, bias=b, res=r), x.float() @ w.float().t() + b + r.float(), 4e-3, what="pair linear 160")
+    w2 = rnd(1024, 320, seed=84, scale=320 ** -0.5)
+    close(ops.linear(x, w2), x.float() @ w2.float().t(), 2e-3, what="pair linear 256")
+    wg = rnd(2560, 320, seed=85, scale=320 ** -0.5)
+    bg = rnd(2560, seed=86, dtype=torch.float32, scale=0.1)
+    hh = x.float() @ wg.float().t() + bg
+    wp, bp = ops.pack_geglu(wg, bg)
+    close(ops.linear(x, wp, bias=bp, geglu=True), hh[:, :1280] * F.gelu(hh[:, 1280:]), 4e-3, what="pair geglu")
+    a2 = rnd(M, 128, seed=87)
+    w3 = rnd(384, 448, seed=88, scale=448 ** -0.5)
+    close(ops.linear(x, w3, x2=a2), torch.cat([x, a2], 1).float() @ w3.float().t(), 2e-3, what="pair concat-K")
+    frames, H, W, Ci, Co = 5, 72, 128, 64, 256
+    xi = rnd(frames, Ci, H, W, seed=89)
+    wc = rnd(Co, Ci, 3, 3, seed=90, scale=(9 * Ci) ** -0.5)
+    bc = rnd(Co, seed=91, dtype=torch.float32)
+    ref = _nhwc_rows(F.conv2d(xi.float(), wc.float(), bc, padding=1))
+    close(ops.conv3x3(_nhwc_rows(xi), frames, H, W, ops.pack_conv3x3(wc), bias=bc), ref, 3e-3, what="pair conv3x3")
+    frames, H, W, Ci, Co = 41, 18, 32, 64, 128                     # 5 tiles per frame (last one ragged), odd tile count
+    xi = rnd(frames, Ci, H, W, seed=92)
+    wc = rnd(Co, Ci, 3, 3, seed=93, scale=(9 * Ci) ** -0.5)
+    ref = _nhwc_rows(F.conv2d(xi.float(), wc.float(), None, padding=1))
+    close(ops.conv3x3(_nhwc_rows(xi), frames, H, W, ops.pack_conv3x3(wc)), ref, 3e-3, what="pair conv3x3 ragged")
+    B, T, HW, C = 1, 5, 9216, 128
+    x5 = rnd(B, C, T, HW, 1, seed=94)
+    wt = rnd(C, C, 3, 1, 1, seed=95, scale=(3 * C) ** -0.5)
+    ref5 = F.conv3d(x5.float(), wt.float(), None, padding=(1, 0, 0))
+    rows = lambda t5: t5.permute(0, 2, 3, 4, 1).reshape(B * T * HW, C).contiguous()
+    close(ops.conv_temporal(rows(x5), B, T, HW, ops.pack_conv_temporal(wt)), rows(ref5), 3e-3, what="pair conv_temporal")
+
+
 def test_softmax_rows(ops):
     x = rnd(200, 1000, seed=71, dtype=torch.float32, scale=20.0)
     close(ops.softmax_rows(x, 0.044), torch.softmax(x * 0.044, -1), 1e-4, rtol=2e-3, what="softmax_rows")

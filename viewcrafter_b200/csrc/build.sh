@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr ${VC_NVCC_EXTRA:-}"
 OUT=../libvc_b200.so
-SRCS="host.cu capi.cu gemm_tap.cu attention.cu temporal_attn.cu norm.cu misc.cu"
+SRCS="host.cu capi.cu gemm_tap.cu gemm_tap2.cu attention.cu temporal_attn.cu norm.cu misc.cu"
 mkdir -p build
 pids=()
 for f in $SRCS; do

@@ -6,53 +6,22 @@
 //                                       the zero padding is TMA out-of-bounds fill
 //   * Conv3d (3,1,1), pad (1,0,0)     : 3 taps, A rows shifted by +-H*W rows of the [T*H*W, C] matrix (OOB rows = 0)
 // A may come from two tensors split along K (channel concat of skip connections without materialising it).
-// Epilogue: + bias[z/bias_z_div][n], GEGLU (value*gelu(gate)), + residual, fp16 / fp32 store.
+// Epilogue: + bias[z/bias_z_div][n], GEGLU (value*gelu(gate)), + residual, fp16 / fp32 store (gemm_common.cuh).
 //
-// PERSISTENT kernel, one CTA per SM, 576 threads:
+// This file: the host entry point and the ONE-CTA-per-tile persistent kernel (576 threads):
 //   warp 0       TMA producer: walks this CTA's tiles and their (tap, k-block) iterations through a smem ring without
 //                draining between tiles, so the loads of tile i+1 are in flight while tile i is still being multiplied
 //   warp 1       TMEM allocator + single-thread tcgen05.mma issuer; TWO accumulators in TMEM (double buffer), so the
 //                main loop of tile i+1 overlaps the epilogue of tile i
-//   warps 2..17  epilogue: four warps per TMEM lane quadrant take interleaved 32-column chunks; each thread owns one
-//                accumulator row: TMEM -> registers -> (+bias / GEGLU / +residual) -> 256-bit global stores (every
-//                store / residual load covers whole 32-byte sectors).  Measured on B200: this beats an smem-staged
-//                "coalesced" epilogue on every shape (profiles/README.md).
-// Tiles are ordered n-fastest so CTAs that run concurrently share A tiles in L2.
-#include "common.cuh"
+//   warps 2..17  epilogue (gemm_epilogue_tile)
+// Tiles are ordered n-fastest so CTAs that run concurrently share A tiles in L2.  Large problems are routed to the
+// CTA-pair kernel of gemm_tap2.cu (UMMA M=256), which halves the per-SM shared-memory traffic for B.
+#include <cstdlib>
+
+#include "gemm_common.cuh"
 #include "kernels.h"
 
 namespace vc {
-
-static constexpr int BM = 128;
-static constexpr int BK = 64;
-static constexpr int MAX_TAPS = 9;
-static constexpr int EPI_WARPS = 16;
-static constexpr int EPI_PER_QUAD = EPI_WARPS / 4;
-static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
-
-struct GemmParams {
-  CUtensorMap tmap_a;
-  CUtensorMap tmap_a2;
-  CUtensorMap tmap_b;
-  int tiles_x, tiles_y, Z;
-  int bx, by;
-  int X, Y;
-  int N, K, K1;          // K1 = channels served by tmap_a (K1 == K when single source)
-  int num_taps;
-  int tap_dx[MAX_TAPS];
-  int tap_dy[MAX_TAPS];
-  int n_tiles;
-  int total_tiles;
-  __half* out;
-  float* out_f32;
-  int ldo;
-  const float* bias;
-  int bias_z_div;
-  const __half* res;
-  int ldr;
-  int geglu;
-  int vec_ok;            // rows are 32-byte aligned: the 256-bit epilogue path may be used
-};
 
 template <int BN>
 struct GemmCfg {
@@ -66,53 +35,6 @@ struct GemmCfg {
   static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
   static_assert(STAGES >= 4, "pipeline too shallow");
 };
-
-struct TileCoord {
-  int x0, y0, z, n_tile;
-};
-
-__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int tile) {
-  TileCoord t;
-  t.n_tile = tile % p.n_tiles;
-  int m = tile / p.n_tiles;
-  const int tx = m % p.tiles_x;
-  m /= p.tiles_x;
-  const int ty = m % p.tiles_y;
-  t.z = m / p.tiles_y;
-  t.x0 = tx * p.bx;
-  t.y0 = ty * p.by;
-  return t;
-}
-
-// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one instruction moves a full 32-byte sector per thread
-__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
-               "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-__device__ __forceinline__ void ld_global_256(const void* ptr, uint32_t (&v)[8]) {
-  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "l"(ptr)
-               : "memory");
-}
-
-// exact-erf GELU (attention.py:415-422 uses F.gelu), erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): 2 MUFU + ~12 FMA/ALU
-__device__ __forceinline__ float gelu_epilogue(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float az = fabsf(z);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
-  const float erf_abs = fmaf(-poly * t, e, 1.0f);
-  const float hx = 0.5f * x;
-  return fmaf(hx, copysignf(erf_abs, z), hx);
-}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_constant__ GemmParams p) {
@@ -158,8 +80,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
     if (lane == 0) {
       long long it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord(p, tile);
-        const int n0 = tc.n_tile * BN;
+        const TileCoord tc = tile_coord_m(p, tile / p.n_tiles);
+        const int n0 = (tile % p.n_tiles) * BN;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
           const int brow = tap * p.N + n0;
@@ -211,122 +133,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
     }
   } else {
     // ------------------------------ epilogue ------------------------------
-    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int sub = (warp - 2) >> 2;              // which of the EPI_PER_QUAD warps of this quadrant
-    constexpr int HALF = BN / 2;
-    const int nchunks = p.geglu ? HALF / 32 : BN / 32;
-    const int n_out = p.geglu ? p.N / 2 : p.N;
-    const int R = q * 32 + lane;                  // accumulator row owned by this thread
-    const int rx = R % p.bx, ry = R / p.bx;
-    const bool vec_ok = p.vec_ok != 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-      const TileCoord tc = tile_coord(p, tile);
+      const TileCoord tc = tile_coord_m(p, tile / p.n_tiles);
       const int acc = lt & 1;
-      const int n0 = tc.n_tile * BN;
-      const int ocol0 = p.geglu ? tc.n_tile * HALF : n0;
-      const float* bias = p.bias ? p.bias + (long long)(p.bias_z_div > 0 ? tc.z / p.bias_z_div : 0) * p.N : nullptr;
-      const int x = tc.x0 + rx, y = tc.y0 + ry;
-      const bool row_ok = x < p.X && y < p.Y;
-      const long long orow = ((long long)tc.z * p.Y + y) * p.X + x;
       mbar_wait(&tmem_full_bar[acc], (uint32_t)(lt >> 1) & 1);
       tc_fence_after();
-      const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-
-#pragma unroll 1
-      for (int c = sub; c < nchunks; c += EPI_PER_QUAD) {
-        float f[32];
-        __syncwarp();
-        if (!p.geglu) {
-          uint32_t v[32];
-          tmem_ld32(trow + c * 32, v);
-          tc_wait_ld();
-          const int nb = n0 + c * 32;
-          if (nb >= p.N) break;                      // warp-uniform
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (bias) {
-            if (nb + 32 <= p.N) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
-                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) f[j] += __ldg(bias + nb + j);
-            }
-          }
-        } else {
-          // GEGLU: tile columns [0,BN/2) are values, [BN/2,BN) the matching gates (weights were interleaved per tile).
-          uint32_t a[32], g[32];
-          tmem_ld32(trow + c * 32, a);
-          tmem_ld32(trow + HALF + c * 32, g);
-          tc_wait_ld();
-          const int nv = n0 + c * 32;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-            if (bias) {
-              ba = __ldg(reinterpret_cast<const float4*>(bias + nv + j));
-              bg = __ldg(reinterpret_cast<const float4*>(bias + nv + HALF + j));
-            }
-            f[j] = (__uint_as_float(a[j]) + ba.x) * gelu_epilogue(__uint_as_float(g[j]) + bg.x);
-            f[j + 1] = (__uint_as_float(a[j + 1]) + ba.y) * gelu_epilogue(__uint_as_float(g[j + 1]) + bg.y);
-            f[j + 2] = (__uint_as_float(a[j + 2]) + ba.z) * gelu_epilogue(__uint_as_float(g[j + 2]) + bg.z);
-            f[j + 3] = (__uint_as_float(a[j + 3]) + ba.w) * gelu_epilogue(__uint_as_float(g[j + 3]) + bg.w);
-          }
-        }
-        const int col0 = ocol0 + c * 32;
-        if (!row_ok || col0 >= n_out) continue;
-        if (col0 + 32 <= n_out && vec_ok) {
-          if (p.res) {
-            const __half* rp = p.res + orow * p.ldr + col0;      // plain loads: res may alias out (in-place residual)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint32_t u[8];
-              ld_global_256(rp + j * 16, u);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&u[e]));
-                f[j * 16 + 2 * e] += t.x; f[j * 16 + 2 * e + 1] += t.y;
-              }
-            }
-          }
-          if (p.out_f32) {
-            float* op = p.out_f32 + orow * p.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t u[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) u[e] = __float_as_uint(f[j * 8 + e]);
-              st_global_256(op + j * 8, u);
-            }
-          } else {
-            __half* op = p.out + orow * p.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint32_t u[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) u[e] = pack_half2(f[j * 16 + 2 * e], f[j * 16 + 2 * e + 1]);
-              st_global_256(op + j * 16, u);
-            }
-          }
-        } else {
-          // ragged N tail / unaligned pitch (e.g. the 320->4 output conv): predicated scalar path
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (col0 + e < n_out) {
-              float t = f[e];
-              if (p.res) t += __half2float(p.res[orow * p.ldr + col0 + e]);
-              if (p.out_f32) p.out_f32[orow * p.ldo + col0 + e] = t;
-              else p.out[orow * p.ldo + col0 + e] = __float2half_rn(t);
-            }
-          }
-        }
-      }
-      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+      gemm_epilogue_tile<BN>(p, tc, tile % p.n_tiles, tmem_base + acc * BN, warp, lane);
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside): hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
     }
@@ -368,6 +182,16 @@ static int pick_bn(int N, int geglu) {
 
 int pick_bn_public(int N, int geglu) { return pick_bn(N, geglu); }
 
+// tuning switch: VC_GEMM_PAIR=0 forces the one-CTA kernel everywhere, =1 (default) uses CTA pairs for large problems
+static int pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("VC_GEMM_PAIR");
+    mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return mode;
+}
+
 int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   VC_REQUIRE(d.a && d.w && (d.out || d.out_f32), "gemm_tap: null pointer");
   VC_REQUIRE(d.num_taps >= 1 && d.num_taps <= MAX_TAPS, "gemm_tap: num_taps=%d out of range", d.num_taps);
@@ -385,6 +209,17 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  const int BN = pick_bn(d.N, d.geglu);
+  p.bx = d.bx; p.by = d.by; p.X = d.X; p.Y = d.Y; p.Z = d.Z;
+  p.tiles_x = (d.X + d.bx - 1) / d.bx;
+  p.tiles_y = (d.Y + d.by - 1) / d.by;
+  p.n_tiles = (d.N + BN - 1) / BN;
+  const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.Z;
+  // CTA pairs pay off once every SM pair has several 256-row tiles; N must be covered by whole BN tiles so that each
+  // CTA's half of the B tile (BN/2 rows) never straddles a tap boundary
+  const bool use_pair = pair_mode() && (BN == 128 || BN == 160 || BN == 256) && d.N % BN == 0 &&
+                        (m_tiles / 2) * p.n_tiles >= sm_count();
+
   // A: (K, X, Y, Z) with row pitch lda
   {
     uint64_t dims[4] = {(uint64_t)d.K1, (uint64_t)d.X, (uint64_t)d.Y, (uint64_t)d.Z};
@@ -401,21 +236,16 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
       p.tmap_a2 = p.tmap_a;
     }
   }
-  const int BN = pick_bn(d.N, d.geglu);
   {
     uint64_t dims[2] = {(uint64_t)d.K, (uint64_t)d.num_taps * d.N};
     uint64_t str[1] = {(uint64_t)(d.ldw > 0 ? d.ldw : d.K) * 2};
-    uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)(use_pair ? BN / 2 : BN)};
     int rc = encode_tmap_f16(&p.tmap_b, d.w, 2, dims, str, box);
     if (rc) return rc;
   }
-  p.bx = d.bx; p.by = d.by; p.X = d.X; p.Y = d.Y; p.Z = d.Z;
-  p.tiles_x = (d.X + d.bx - 1) / d.bx;
-  p.tiles_y = (d.Y + d.by - 1) / d.by;
   p.N = d.N; p.K = d.K; p.K1 = d.K1;
   p.num_taps = d.num_taps;
   for (int t = 0; t < d.num_taps; ++t) { p.tap_dx[t] = d.tap_dx[t]; p.tap_dy[t] = d.tap_dy[t]; }
-  p.n_tiles = (d.N + BN - 1) / BN;
   p.out = d.out; p.out_f32 = d.out_f32; p.ldo = d.ldo;
   p.bias = d.bias; p.bias_z_div = d.bias_z_div;
   p.res = d.res; p.ldr = d.ldr;
@@ -425,9 +255,10 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   const bool o_al = ((reinterpret_cast<uintptr_t>(optr) & 31) == 0) && ((long long)d.ldo * esz) % 32 == 0;
   const bool r_al = !d.res || (((reinterpret_cast<uintptr_t>(d.res) & 31) == 0) && ((long long)d.ldr * 2) % 32 == 0);
   p.vec_ok = (o_al && r_al) ? 1 : 0;
-  const long long total = (long long)p.tiles_x * p.tiles_y * p.Z * p.n_tiles;
+  const long long total = (use_pair ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;
   VC_REQUIRE(total > 0 && total < (1ll << 31), "gemm_tap: tile count %lld out of range", total);
   p.total_tiles = (int)total;
+  if (use_pair) return launch_gemm_pair(BN, p, stream);
   switch (BN) {
     case 32: return launch_gemm<32>(p, stream);
     case 64: return launch_gemm<64>(p, stream);
