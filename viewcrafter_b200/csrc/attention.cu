@@ -83,43 +83,51 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
 
+  // warps 0/1 run warp-uniform loops and ONE elected lane issues TMA / MMA (keeps operands in uniform registers)
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, ATT_TILE_BYTES);
       tma_load_4d(sQ, &p.tmap_q, q_full, 0, head, q0, b);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        if (j >= 2) mbar_wait(&kv_empty[s], ((j >> 1) - 1) & 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j & 1;
+      if (j >= 2) mbar_wait(&kv_empty[s], ((j >> 1) - 1) & 1);
+      if (elect_one()) {
         uint8_t* sk = sKV + s * 2 * ATT_TILE_BYTES;
         mbar_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
         tma_load_4d(sk, &p.tmap_k, &kv_full[s], 0, head, j * ATT_BN, bk);
         tma_load_4d(sk + ATT_TILE_BYTES, &p.tmap_v, &kv_full[s], 0, head, j * ATT_BN, bk);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);      // B = V is MN-major
-      const uint32_t aQ = smem_u32(sQ);
-      auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
-        tc_fence_after();
+    constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);      // B = V is MN-major
+    const uint32_t aQ = smem_u32(sQ);
+    auto issue_qk = [&](int j) {
+      const int s = j & 1;
+      mbar_wait(&kv_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t aK = smem_u32(sKV + s * 2 * ATT_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k)
           umma_ss(tS, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc_qk, k > 0 ? 1u : 0u);
         umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < ntiles; ++j) {
-        if (j + 1 < ntiles) {                       // next S as soon as this one has been copied out of TMEM
-          mbar_wait(s_free, j & 1);
-          issue_qk(j + 1);
-        }
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < ntiles; ++j) {
+      if (j + 1 < ntiles) {                       // next S as soon as this one has been copied out of TMEM
+        mbar_wait(s_free, j & 1);
+        issue_qk(j + 1);
+      }
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t aV = smem_u32(sKV + (j & 1) * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)
@@ -127,6 +135,7 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
         umma_commit(&kv_empty[j & 1]);
         umma_commit(o_done);
       }
+      __syncwarp();
     }
   } else {
     const int qd = warp & 3;

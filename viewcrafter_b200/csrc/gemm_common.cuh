@@ -34,6 +34,8 @@ struct GemmParams {
   int ldr;
   int geglu;
   int vec_ok;            // rows are 32-byte aligned: the 256-bit epilogue path may be used
+  int debug;             // profiling aid (VC_GEMM_DEBUG): 1 = skip the MMAs (feed rate only), 2 = skip TMA (MMA rate only),
+                         // 4 = skip the epilogue body; results are garbage in these modes
 };
 
 struct TileCoord {

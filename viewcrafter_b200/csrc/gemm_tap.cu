@@ -77,59 +77,77 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      long long it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord_m(p, tile / p.n_tiles);
-        const int n0 = (tile % p.n_tiles) * BN;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
-          const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
-          const int brow = tap * p.N + n0;
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
-            const int s = (int)(it % STAGES);
-            if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
+    // The whole warp runs the loop with warp-uniform control flow and ONE elected lane issues: the compiler can then
+    // keep barrier / descriptor operands in uniform registers (a divergent `if (lane == 0)` loop costs an ELECT/BRA.ANY
+    // serialisation loop around every UTMALDG -- measured).
+    long long it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord_m(p, tile / p.n_tiles);
+      const int n0 = (tile % p.n_tiles) * BN;
+      for (int tap = 0; tap < p.num_taps; ++tap) {
+        const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
+        const int brow = tap * p.N + n0;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = (int)(it % STAGES);
+          if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
+          if (elect_one()) {
             uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
-            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-            const int k = kb * BK;
-            if (k < p.K1)
-              tma_load_4d(sa, &p.tmap_a, &full_bar[s], k, cx, cy, tc.z);
-            else
-              tma_load_4d(sa, &p.tmap_a2, &full_bar[s], k - p.K1, cx, cy, tc.z);
-            tma_load_2d(sb, &p.tmap_b, &full_bar[s], k, brow);
+            if (p.debug & 2) {
+              mbar_arrive(&full_bar[s]);
+            } else {
+              mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+              const int k = kb * BK;
+              if (k < p.K1)
+                tma_load_4d(sa, &p.tmap_a, &full_bar[s], k, cx, cy, tc.z);
+              else
+                tma_load_4d(sa, &p.tmap_a2, &full_bar[s], k - p.K1, cx, cy, tc.z);
+              tma_load_2d(sb, &p.tmap_b, &full_bar[s], k, brow);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      long long it = 0;
-      int lt = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-        const int acc = lt & 1;
-        if (lt >= 2) {                               // the epilogue must have drained this accumulator
-          mbar_wait(&tmem_empty_bar[acc], (uint32_t)((lt >> 1) - 1) & 1);
-          tc_fence_after();
-        }
-        const uint32_t tacc = tmem_base + acc * BN;
-        for (int i = 0; i < iters; ++i, ++it) {
-          const int s = (int)(it % STAGES);
-          mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(sa + k * 32);
-            const uint64_t db = umma_desc_sw128(sb + k * 32);
-            umma_ss(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
-        }
-        umma_commit(&tmem_full_bar[acc]);   // accumulator complete
+    // warp-uniform loop, one elected lane issues (always the same lane: tcgen05.commit tracks the issuing thread's MMAs)
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    long long it = 0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      if (lt >= 2) {                               // the epilogue must have drained this accumulator
+        mbar_wait(&tmem_empty_bar[acc], (uint32_t)((lt >> 1) - 1) & 1);
+        tc_fence_after();
       }
+      const uint32_t tacc = tmem_base + acc * BN;
+      for (int i = 0; i < iters; ++i, ++it) {
+        const int s = (int)(it % STAGES);
+        mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          if (p.debug & 1) {
+            mbar_arrive(&empty_bar[s]);
+          } else {
+            const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = umma_desc_sw128(sa + k * 32);
+              const uint64_t db = umma_desc_sw128(sb + k * 32);
+              umma_ss(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        if (p.debug & 1) mbar_arrive(&tmem_full_bar[acc]);
+        else umma_commit(&tmem_full_bar[acc]);   // accumulator complete
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------ epilogue ------------------------------
@@ -139,7 +157,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
       const int acc = lt & 1;
       mbar_wait(&tmem_full_bar[acc], (uint32_t)(lt >> 1) & 1);
       tc_fence_after();
-      gemm_epilogue_tile<BN>(p, tc, tile % p.n_tiles, tmem_base + acc * BN, warp, lane);
+      if (!(p.debug & 4)) gemm_epilogue_tile<BN>(p, tc, tile % p.n_tiles, tmem_base + acc * BN, warp, lane);
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside): hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
@@ -255,6 +273,14 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   const bool o_al = ((reinterpret_cast<uintptr_t>(optr) & 31) == 0) && ((long long)d.ldo * esz) % 32 == 0;
   const bool r_al = !d.res || (((reinterpret_cast<uintptr_t>(d.res) & 31) == 0) && ((long long)d.ldr * 2) % 32 == 0);
   p.vec_ok = (o_al && r_al) ? 1 : 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("VC_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   const long long total = (use_pair ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;
   VC_REQUIRE(total > 0 && total < (1ll << 31), "gemm_tap: tile count %lld out of range", total);
   p.total_tiles = (int)total;

@@ -123,18 +123,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
-    if (lane == 0) {
-      long long it = 0;
-      for (int tile = cluster_id; tile < pair_tiles; tile += nclusters) {
-        const int n_tile = tile % p.n_tiles;
-        const TileCoord tc = tile_coord_m(p, (tile / p.n_tiles) * 2 + (int)rank);
-        const int n0 = n_tile * BN + (int)rank * (BN / 2);
-        for (int tap = 0; tap < p.num_taps; ++tap) {
-          const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
-          const int brow = tap * p.N + n0;
-          for (int kb = 0; kb < kblocks; ++kb, ++it) {
-            const int s = (int)(it % STAGES);
-            if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
+    // warp-uniform loop, one elected lane issues (keeps TMA operands in uniform registers)
+    long long it = 0;
+    for (int tile = cluster_id; tile < pair_tiles; tile += nclusters) {
+      const int n_tile = tile % p.n_tiles;
+      const TileCoord tc = tile_coord_m(p, (tile / p.n_tiles) * 2 + (int)rank);
+      const int n0 = n_tile * BN + (int)rank * (BN / 2);
+      for (int tap = 0; tap < p.num_taps; ++tap) {
+        const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
+        const int brow = tap * p.N + n0;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = (int)(it % STAGES);
+          if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
+          if (elect_one()) {
             uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
             if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);   // bytes of both CTAs land on the leader
@@ -145,12 +146,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
               tma2_load_4d(sa, &p.tmap_a2, &full_bar[s], k - p.K1, cx, cy, tc.z);
             tma2_load_2d(sb, &p.tmap_b, &full_bar[s], k, brow);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
       long long it = 0;
       int lt = 0;
@@ -165,14 +167,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
           const int s = (int)(it % STAGES);
           mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma2_ss(tacc, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (i > 0 || k > 0) ? 1u : 0u);
-          umma2_commit_mc(&empty_bar[s]);
+            for (int k = 0; k < BK / 16; ++k)
+              umma2_ss(tacc, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma2_commit_mc(&empty_bar[s]);
+          }
+          __syncwarp();
         }
-        umma2_commit_mc(&tmem_full_bar[acc]);
+        if (elect_one()) umma2_commit_mc(&tmem_full_bar[acc]);
+        __syncwarp();
       }
     }
   } else {
