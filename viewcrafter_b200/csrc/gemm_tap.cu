@@ -235,7 +235,10 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.Z;
   // CTA pairs pay off once every SM pair has several 256-row tiles; N must be covered by whole BN tiles so that each
   // CTA's half of the B tile (BN/2 rows) never straddles a tap boundary
-  const bool use_pair = pair_mode() && (BN == 128 || BN == 160 || BN == 256) && d.N % BN == 0 &&
+  // Measured on B200 (profiles/README.md): pairs win 10-15 % once the reduction is long (>= 10 k-blocks of 64), but lose
+  // on the short-K (K = 320 / 512) level-0 linears, which are epilogue / HBM bound and prefer 148 independent CTAs.
+  const int k_iters = d.num_taps * ((d.K + BK - 1) / BK);
+  const bool use_pair = pair_mode() && (BN == 128 || BN == 160 || BN == 256) && d.N % BN == 0 && k_iters >= 10 &&
                         (m_tiles / 2) * p.n_tiles >= sm_count();
 
   // A: (K, X, Y, Z) with row pitch lda
