@@ -22,9 +22,14 @@ namespace vc {
 
 template <int BN>
 struct Gemm2Cfg {
-  static constexpr int A_BYTES = BM * BK * 2;                  // this CTA's 128 rows
-  static constexpr int B_BYTES = (BN / 2) * BK * 2;            // this CTA's half of the B tile
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int A_BYTES = BM * BK * 2;                  // this CTA's 128 rows, one 64-wide K sub-block
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;            // this CTA's half of the B tile, one K sub-block
+  static constexpr int SUB_BYTES = A_BYTES + B_BYTES;
+  // The single MMA-issuing thread is the bottleneck of this kernel (measured: ~200 cycles of barrier wait / fence /
+  // commit per pipeline step against 320-512 cycles of tensor work), so every stage carries KSUB = 2 K sub-blocks:
+  // 8 MMAs per full-barrier wait and per tcgen05.commit instead of 4.
+  static constexpr int KSUB = 2;
+  static constexpr int STAGE_BYTES = KSUB * SUB_BYTES;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
@@ -132,19 +137,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
         const int brow = tap * p.N + n0;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        for (int kb = 0; kb < kblocks; kb += Cfg::KSUB, ++it) {
           const int s = (int)(it % STAGES);
+          const int nsub = min(Cfg::KSUB, kblocks - kb);
           if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
           if (elect_one()) {
-            uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-            uint8_t* sb = sa + Cfg::A_BYTES;
-            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);   // bytes of both CTAs land on the leader
-            const int k = kb * BK;
-            if (k < p.K1)
-              tma2_load_4d(sa, &p.tmap_a, &full_bar[s], k, cx, cy, tc.z);
-            else
-              tma2_load_4d(sa, &p.tmap_a2, &full_bar[s], k - p.K1, cx, cy, tc.z);
-            tma2_load_2d(sb, &p.tmap_b, &full_bar[s], k, brow);
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * nsub * Cfg::SUB_BYTES);   // bytes of both CTAs land on the leader
+            for (int u = 0; u < nsub; ++u) {
+              uint8_t* sa = smem + s * Cfg::STAGE_BYTES + u * Cfg::SUB_BYTES;
+              uint8_t* sb = sa + Cfg::A_BYTES;
+              const int k = (kb + u) * BK;
+              if (k < p.K1)
+                tma2_load_4d(sa, &p.tmap_a, &full_bar[s], k, cx, cy, tc.z);
+              else
+                tma2_load_4d(sa, &p.tmap_a2, &full_bar[s], k - p.K1, cx, cy, tc.z);
+              tma2_load_2d(sb, &p.tmap_b, &full_bar[s], k, brow);
+            }
           }
           __syncwarp();
         }
@@ -163,19 +171,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
           tc_fence_after();
         }
         const uint32_t tacc = tmem_base + acc * BN;
-        for (int i = 0; i < iters; ++i, ++it) {
-          const int s = (int)(it % STAGES);
-          mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-            const uint32_t sb = sa + Cfg::A_BYTES;
+        uint32_t first = 1;                          // the first MMA of a tile overwrites the accumulator
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          for (int kb = 0; kb < kblocks; kb += Cfg::KSUB, ++it) {
+            const int s = (int)(it % STAGES);
+            const int nsub = min(Cfg::KSUB, kblocks - kb);
+            mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              for (int u = 0; u < nsub; ++u) {
+                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES + u * Cfg::SUB_BYTES);
+                const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma2_ss(tacc, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (i > 0 || k > 0) ? 1u : 0u);
-            umma2_commit_mc(&empty_bar[s]);
+                for (int k = 0; k < BK / 16; ++k)
+                  umma2_ss(tacc, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (first && u == 0 && k == 0) ? 0u : 1u);
+              }
+              umma2_commit_mc(&empty_bar[s]);
+            }
+            first = 0;
+            __syncwarp();
           }
-          __syncwarp();
         }
         if (elect_one()) umma2_commit_mc(&tmem_full_bar[acc]);
         __syncwarp();

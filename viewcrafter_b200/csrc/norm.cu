@@ -12,7 +12,7 @@ namespace vc {
 
 static constexpr int GN_MAX_SPLITS = 512;
 
-size_t groupnorm_ws_bytes(int samples) { return (size_t)samples * GN_MAX_SPLITS * 64 * sizeof(float); }
+size_t groupnorm_ws_bytes(int samples) { return (size_t)samples * GN_MAX_SPLITS * 64 * sizeof(float) + (size_t)samples * sizeof(unsigned int); }
 
 struct GnGeom {
   int C, C1, C2, vecs, ppi, cg, splits;
@@ -27,7 +27,7 @@ __device__ __forceinline__ uint4 gn_load(const __half* x1, const __half* x2, con
   return *reinterpret_cast<const uint4*>(p);
 }
 
-__global__ void __launch_bounds__(1024) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+__device__ __forceinline__ void gn_stats_dev(const __half* __restrict__ x1, const __half* __restrict__ x2, const GnGeom& g,
                                                         float* __restrict__ partial) {
   extern __shared__ float red[];   // [2*C]
   const int tid = threadIdx.x;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const __half* __restrict
   }
 }
 
-__global__ void __launch_bounds__(1024) gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+__device__ __forceinline__ void gn_apply_dev(const __half* __restrict__ x1, const __half* __restrict__ x2, const GnGeom& g,
                                                         const float* __restrict__ partial, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
   __shared__ float mean_s[32], rstd_s[32];
@@ -137,6 +137,34 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const __half* __restrict
   }
 }
 
+__global__ void __launch_bounds__(1024) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+                                                        float* __restrict__ partial) {
+  gn_stats_dev(x1, x2, g, partial);
+}
+__global__ void __launch_bounds__(1024) gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+                                                        const float* __restrict__ partial, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
+  gn_apply_dev(x1, x2, g, partial, gamma, beta, eps, silu, out);
+}
+// Fused single launch: statistics pass, a grid-wide rendezvous of the CTAs of one sample (all CTAs are co-resident by
+// construction -- the host checks the occupancy), then the normalise pass, whose re-read of x is served by the 126 MB L2
+// for everything but the largest 5-D tensors: HBM traffic drops from 3 passes to ~2.
+__global__ void __launch_bounds__(1024) gn_fused_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+                                                        float* __restrict__ partial, unsigned int* __restrict__ counters,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                                        __half* __restrict__ out) {
+  gn_stats_dev(x1, x2, g, partial);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&counters[blockIdx.y], 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(&counters[blockIdx.y]) < (unsigned)g.splits) __nanosleep(40);
+    __threadfence();
+  }
+  __syncthreads();
+  gn_apply_dev(x1, x2, g, partial, gamma, beta, eps, silu, out);
+}
+
 static int gn_geometry(GnGeom& g, const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample) {
   const int C = C1 + (x2 ? C2 : 0);
   VC_REQUIRE(x1, "groupnorm: null pointer");
@@ -169,7 +197,20 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int sampl
   VC_REQUIRE(ws_bytes >= (size_t)samples * g.splits * 64 * sizeof(float), "groupnorm: workspace too small");
   const int threads = g.vecs * g.ppi;
   dim3 grid(g.splits, samples);
-  gn_stats_kernel<<<grid, threads, 2 * g.C * sizeof(float), stream>>>(x1, x2, g, partial_ws);
+  const size_t smem = 2 * g.C * sizeof(float);
+  // fused path: needs every CTA resident at once (spin rendezvous) and room for the per-sample counters after the partials
+  const size_t part_bytes = (size_t)samples * g.splits * 64 * sizeof(float);
+  int per_sm = 0;
+  VC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem));
+  const bool fused = (long long)per_sm * sm_count() >= (long long)g.splits * samples && ws_bytes >= part_bytes + samples * sizeof(unsigned int);
+  if (fused) {
+    unsigned int* counters = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(partial_ws) + part_bytes);
+    VC_CHECK_CUDA(cudaMemsetAsync(counters, 0, samples * sizeof(unsigned int), stream));
+    gn_fused_kernel<<<grid, threads, smem, stream>>>(x1, x2, g, partial_ws, counters, gamma, beta, eps, silu, out);
+    VC_CHECK_CUDA(cudaGetLastError());
+    return VC_OK;
+  }
+  gn_stats_kernel<<<grid, threads, smem, stream>>>(x1, x2, g, partial_ws);
   VC_CHECK_CUDA(cudaGetLastError());
   gn_apply_kernel<<<grid, threads, 0, stream>>>(x1, x2, g, partial_ws, gamma, beta, eps, silu, out);
   VC_CHECK_CUDA(cudaGetLastError());
