@@ -99,7 +99,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
   const int cluster_id = blockIdx.x >> 1;
   const int nclusters = gridDim.x >> 1;
   const int kblocks = (p.K + BK - 1) / BK;
-  const int iters = p.num_taps * kblocks;
   const int pair_tiles = p.total_tiles;             // (m-tile pairs) x n_tiles
 
   if (warp == 0 && lane == 0) {

@@ -202,7 +202,14 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int sampl
   const size_t part_bytes = (size_t)samples * g.splits * 64 * sizeof(float);
   int per_sm = 0;
   VC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem));
-  const bool fused = (long long)per_sm * sm_count() >= (long long)g.splits * samples && ws_bytes >= part_bytes + samples * sizeof(unsigned int);
+  const long long capacity = (long long)per_sm * sm_count();
+  if (capacity < (long long)g.splits * samples && capacity >= samples) {   // shrink the split so that every CTA is resident
+    g.splits = (int)(capacity / samples);
+    g.rows_per_split = (rows_per_sample + g.splits - 1) / g.splits;
+    g.stat_splits = g.splits;
+    grid = dim3(g.splits, samples);
+  }
+  const bool fused = capacity >= (long long)g.splits * samples && ws_bytes >= part_bytes + samples * sizeof(unsigned int);
   if (fused) {
     unsigned int* counters = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(partial_ws) + part_bytes);
     VC_CHECK_CUDA(cudaMemsetAsync(counters, 0, samples * sizeof(unsigned int), stream));
