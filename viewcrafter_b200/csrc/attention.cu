@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
     mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
     mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, 4);      // one arrival per softmax warp (512 serialised mbarrier arrivals per tile were measurable)
+    mbar_init(p_full, 4);
     mbar_init(o_done, 1);
     fence_barrier_init();
   }
@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
       tmem_ld32(tS + lane_off + 96, s3);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive(s_free);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
 
       float mx = -INFINITY;
       if (valid == ATT_BN) {
@@ -226,7 +227,8 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
       tmem_st32(tP + lane_off + 32, s2);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue
     mbar_wait(o_done, (ntiles - 1) & 1);

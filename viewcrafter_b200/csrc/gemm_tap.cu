@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], EPI_WARPS * 32);
+      mbar_init(&tmem_empty_bar[a], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
       if (!(p.debug & 4)) gemm_epilogue_tile<BN>(p, tc, tile % p.n_tiles, tmem_base + acc * BN, warp, lane);
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside): hand it back to the MMA warp
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // one arrival per warp
     }
   }
 

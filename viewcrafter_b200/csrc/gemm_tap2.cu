@@ -110,7 +110,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 2 * EPI_WARPS * 32);     // both CTAs' epilogue threads
+      mbar_init(&tmem_empty_bar[a], 2 * EPI_WARPS);          // one arrival per epilogue warp of both CTAs
     }
     fence_barrier_init();
   }
@@ -206,7 +206,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
       tc_fence_after();
       gemm_epilogue_tile<BN>(p, tc, n_tile, tmem_base + acc * BN, warp, lane);
       tc_fence_before();
-      mbar_arrive_remote(&tmem_empty_bar[acc], 0);          // the leader's barrier counts both epilogues
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);          // the leader's barrier counts both epilogues
     }
   }
 
