@@ -76,3 +76,57 @@ def test_frame_sharded_forward_matches_single_process(world, T, B, H):
     assert d_single < 0.02, d_single
     assert d_ref < 0.02, d_ref
     assert moved > 0
+
+
+def _cfg_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    import _pytest.monkeypatch as mpatch
+    from tests import fake_ops
+    from viewcrafter_b200 import parallel
+    from viewcrafter_b200.ddim import DDIMSampler
+    from viewcrafter_b200.diffusion import LatentDiffusion
+    mpx = mpatch.MonkeyPatch()
+    fake_ops.install(mpx)
+    model = LatentDiffusion(dict(UNET_PARAMS, model_channels=64), None, base_scale=0.3).eval()
+    unet = model.model.diffusion_model
+    unet.load_state_dict(synth.synth_state_dict(synth.module_shapes(unet), 7), strict=True)
+    g = torch.Generator().manual_seed(8)
+    shape = (1, 4, 4, 16, 16)
+    x, cc = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    c = {"c_crossattn": [torch.randn(1, 333, 1024, generator=g)], "c_concat": [cc]}
+    uc = {"c_crossattn": [torch.randn(1, 333, 1024, generator=g)], "c_concat": [cc]}
+    ts = torch.full((1,), 599, dtype=torch.long)
+
+    def step():
+        smp = DDIMSampler(model)
+        smp.make_schedule(5, "uniform_trailing", 1.0, verbose=False)
+        torch.manual_seed(9)
+        return smp.p_sample_ddim(x, c, ts, index=2, unconditional_guidance_scale=7.5, unconditional_conditioning=uc,
+                                 fs=torch.tensor([10]), guidance_rescale=0.7)[0]
+
+    ref = step()
+    parallel.shard_model(model, dist, rank, world)
+    out = step()
+    if rank == 0:
+        q.put(float((out - ref).abs().max()))
+    dist.barrier()
+    dist.destroy_process_group()
+    mpx.undo()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_cfg_split_times_frame_sharding_matches_single_process(world):
+    """world 2 = pure CFG split (cond on rank 0, uncond on rank 1); world 4 = CFG split x 2-way frame sharding."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cfg_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0, f"rank exited with {p.exitcode}"
+    d = q.get(timeout=10)
+    assert d < (1e-5 if world == 2 else 0.15), d       # world 2 runs the identical single-GPU forwards; CFG amplifies fp16 noise x16

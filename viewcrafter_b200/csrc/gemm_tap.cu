@@ -31,8 +31,11 @@ struct GemmCfg {
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
-  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
-  static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
+  // as many accumulators as fit the 512 TMEM columns (2..4): short-K tiles finish their main loop faster than the
+  // accumulator hand-off (commit -> epilogue wake-up -> drain -> arrive) can turn around, so two buffers are not enough
+  static constexpr int NACC = (512 / BN) > 4 ? 4 : (512 / BN);
+  static constexpr int TMEM_COLS = NACC * BN <= 32 ? 32 : NACC * BN <= 64 ? 64 : NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;
+  static_assert(NACC >= 2 && NACC * BN <= 512, "at least two accumulators must fit TMEM");
   static_assert(STAGES >= 4, "pipeline too shallow");
 };
 
@@ -44,9 +47,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [NACC]
+  uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::NACC;   // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::NACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < Cfg::NACC; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], EPI_WARPS);
     }
@@ -116,9 +119,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
     long long it = 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-      const int acc = lt & 1;
-      if (lt >= 2) {                               // the epilogue must have drained this accumulator
-        mbar_wait(&tmem_empty_bar[acc], (uint32_t)((lt >> 1) - 1) & 1);
+      const int acc = lt % Cfg::NACC;
+      if (lt >= Cfg::NACC) {                       // the epilogue must have drained this accumulator
+        mbar_wait(&tmem_empty_bar[acc], (uint32_t)((lt / Cfg::NACC) - 1) & 1);
         tc_fence_after();
       }
       const uint32_t tacc = tmem_base + acc * BN;
@@ -154,8 +157,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const TileCoord tc = tile_coord_m(p, tile / p.n_tiles);
-      const int acc = lt & 1;
-      mbar_wait(&tmem_full_bar[acc], (uint32_t)(lt >> 1) & 1);
+      const int acc = lt % Cfg::NACC;
+      mbar_wait(&tmem_full_bar[acc], (uint32_t)(lt / Cfg::NACC) & 1);
       tc_fence_after();
       if (!(p.debug & 4)) gemm_epilogue_tile<BN>(p, tc, tile % p.n_tiles, tmem_base + acc * BN, warp, lane);
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside): hand it back to the MMA warp
@@ -188,7 +191,11 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
 }
 
 static int pick_bn(int N, int geglu) {
-  if (geglu) return (N % 256 == 0) ? 256 : 128;
+  if (geglu) {
+    static int g = -1;                       // tuning switch VC_GEGLU_BN=128|256
+    if (g < 0) { const char* e = getenv("VC_GEGLU_BN"); g = e ? atoi(e) : 256; }
+    return (g == 256 && N % 256 == 0) ? 256 : 128;
+  }
   if (N <= 32) return 32;
   if (N <= 64) return 64;
   if (N % 256 == 0) return 256;

@@ -133,6 +133,10 @@ class DDIMSampler(object):
 
     def _apply_both(self, x, t, c, uc, kwargs):
         """cond + uncond as one B=2 forward when every conditioning entry can be stacked; else two calls (ddim.py:223-224)."""
+        cfg = getattr(self.model, "_cfg", None)
+        if cfg is not None:                                   # multi-GPU CFG split: this rank computes one branch only
+            mine = self.model.apply_model(x, t, c if cfg.branch == 0 else uc, **kwargs)
+            return cfg.exchange(mine.float().contiguous())
         if self.batch_cfg and isinstance(c, dict) and isinstance(uc, dict) and c.keys() == uc.keys():
             cat = {k: [torch.cat([a, u], 0) for a, u in zip(c[k], uc[k])] for k in c}
             kw = {k: (torch.cat([v, v], 0) if isinstance(v, torch.Tensor) and v.dim() >= 1 and v.shape[0] == x.shape[0] else v)
