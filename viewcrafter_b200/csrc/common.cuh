@@ -76,6 +76,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrival WITHOUT release semantics: for hand-offs whose payload lives in TMEM (ordered by tcgen05.fence::before/after
+// around the barrier).  The default .release form compiles to MEMBAR.ALL.CTA, which makes the arriving warp wait until
+// all of its earlier *global stores* have drained -- a ~1 us bubble per tile in a GEMM epilogue (seen in ncu: MEMBAR /
+// ERRBAR among the top stall PCs).
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)));
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

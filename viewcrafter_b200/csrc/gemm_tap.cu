@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // one arrival per warp
+      if (lane == 0) mbar_arrive_relaxed(&tmem_empty_bar[acc]);   // one arrival per warp; payload is TMEM: no release fence
     }
   }
 

@@ -78,7 +78,9 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar_local, uint32_t cta_rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar_local)), "r"(cta_rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  // relaxed: the payload (a drained TMEM accumulator) is ordered by tcgen05 fences; a release here would be a
+  // MEMBAR.ALL.GPU that waits for the warp's outstanding global stores
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote));
 }
 
 template <int BN>
