@@ -116,10 +116,14 @@ def flash_attn(q, k, v, B, Nq, Nk, heads, kv_shared=False, scale=0.125, out=None
     return _h(y)
 
 
-def temporal_attn(q, k, v, T, sites, heads, scale=0.125):
+def temporal_attn(q, k, v, T, sites, heads, scale=0.125, out=None):
     C = heads * 64
     tok = lambda t: t.reshape(T, sites, -1)[:, :, :C].permute(1, 0, 2)
-    return _h(_attn(tok(q), tok(k), tok(v), heads, scale).permute(1, 0, 2).reshape(T * sites, C))
+    r = _h(_attn(tok(q), tok(k), tok(v), heads, scale).permute(1, 0, 2).reshape(T * sites, C))
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
 
 
 def groupnorm(x, samples, gamma, beta, eps, silu, x2=None):

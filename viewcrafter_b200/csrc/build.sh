@@ -4,14 +4,15 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr ${VC_NVCC_EXTRA:-}"
-OUT=../libvc_b200.so
+OUT=${VC_OUT:-../libvc_b200.so}          # VC_OUT / VC_BUILD_DIR / VC_NVCC_EXTRA: side-by-side A/B builds (load with VC_B200_LIB)
+BUILD=${VC_BUILD_DIR:-build}
 SRCS="host.cu capi.cu gemm_tap.cu gemm_tap2.cu attention.cu temporal_attn.cu norm.cu misc.cu"
-mkdir -p build
+mkdir -p $BUILD
 pids=()
 for f in $SRCS; do
-  $NVCC $FLAGS -c $f -o build/${f%.cu}.o &
+  $NVCC $FLAGS -c $f -o $BUILD/${f%.cu}.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT build/*.o -lcudart
+$NVCC -shared -o $OUT $BUILD/*.o -lcudart
 echo "built $(realpath $OUT)"

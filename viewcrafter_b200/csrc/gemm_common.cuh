@@ -8,16 +8,46 @@ namespace vc {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int MAX_TAPS = 9;
-static constexpr int EPI_WARPS = 16;
+#ifndef VC_EPI_WARPS
+#define VC_EPI_WARPS 12
+#endif
+static constexpr int EPI_WARPS = VC_EPI_WARPS;   // multiple of 4 (EPI_WARPS / 4 warps per TMEM lane quadrant).  12 warps -> 14 per CTA -> 128 registers
+                                                 // per thread without spills; 16 warps cap at 96 and spilled the residual prefetch (measured slower)
 static constexpr int EPI_PER_QUAD = EPI_WARPS / 4;
 static constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+static constexpr int EPI_STAGE_BYTES = 32 * 32 * 2;              // one warp's staging tile for TMA stores: 32 rows x 32 fp16
+static constexpr int EPI_SMEM_BYTES = EPI_WARPS * EPI_STAGE_BYTES;
+
+// Division by a runtime constant as multiply-high + shift (valid for dividends < 2^31): the persistent kernels turn a
+// linear tile index into (n-tile, x, y, z) once per tile in EVERY thread, and a generic 32-bit division is ~20 SASS
+// instructions each.
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  if (d == 1) { f.mul = 0; f.shr = 0; return f; }
+  uint32_t lg = 0;
+  while ((1u << lg) < (uint32_t)d) ++lg;           // ceil(log2 d)
+  const uint32_t p = 31 + lg;
+  f.mul = (uint32_t)(((1ull << p) + (uint32_t)d - 1) / (uint32_t)d);
+  f.shr = p - 32;
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ int fast_div(const FastDiv& f, int n) { return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr); }
+#endif
 
 struct GemmParams {
   CUtensorMap tmap_a;
   CUtensorMap tmap_a2;
   CUtensorMap tmap_b;
+  CUtensorMap tmap_out;  // fp16 output as (N, X, Y, Z), box (32, min(bx,32), 32/min(bx,32), 1), 64B swizzle (out_tma only)
   int tiles_x, tiles_y, Z;
+  FastDiv div_tiles_x, div_tiles_y, div_n_tiles;
   int bx, by;
+  int bx_shift;          // bx is a power of two (bx * by == 128)
   int X, Y;
   int N, K, K1;          // K1 = channels served by tmap_a (K1 == K when single source)
   int num_taps;
@@ -33,6 +63,7 @@ struct GemmParams {
   const __half* res;
   int ldr;
   int geglu;
+  int out_tma;           // fp16 output written by TMA stores from per-warp staging tiles (full-line, LSU-free)
   int vec_ok;            // rows are 32-byte aligned: the 256-bit epilogue path may be used
   int debug;             // profiling aid (VC_GEMM_DEBUG): 1 = skip the MMAs (feed rate only), 2 = skip TMA (MMA rate only),
                          // 4 = skip the epilogue body; results are garbage in these modes
@@ -43,16 +74,18 @@ struct TileCoord {
 };
 
 // m-tile index -> tile origin; indices past the last m-tile give z >= Z (TMA zero-fills, the epilogue masks the rows)
+#ifdef __CUDACC__
 __device__ __forceinline__ TileCoord tile_coord_m(const GemmParams& p, int m) {
   TileCoord t;
-  const int tx = m % p.tiles_x;
-  m /= p.tiles_x;
-  const int ty = m % p.tiles_y;
-  t.z = m / p.tiles_y;
-  t.x0 = tx * p.bx;
+  const int q1 = fast_div(p.div_tiles_x, m);
+  const int tx = m - q1 * p.tiles_x;
+  t.z = fast_div(p.div_tiles_y, q1);
+  const int ty = q1 - t.z * p.tiles_y;
+  t.x0 = tx << p.bx_shift;
   t.y0 = ty * p.by;
   return t;
 }
+#endif
 
 #ifdef __CUDACC__
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one instruction moves a full 32-byte sector per thread
@@ -85,119 +118,263 @@ __device__ __forceinline__ float gelu_epilogue(float x) {
   return fmaf(hx, copysignf(erf_abs, z), hx);
 }
 
-// Epilogue of one 128 x BN accumulator (this CTA's TMEM, column base `tacc`), executed by the 16 epilogue warps
-// (warp index 2..17).  Four warps per TMEM lane quadrant take interleaved 32-column chunks; each thread owns one row:
-// TMEM -> registers -> (+bias / GEGLU / +residual) -> 256-bit global stores (whole 32-byte sectors).
-template <int BN>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const TileCoord& tc, int n_tile, uint32_t tacc, int warp,
-                                                   int lane) {
-  const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-  const int sub = (warp - 2) >> 2;              // which of the EPI_PER_QUAD warps of this quadrant
-  constexpr int HALF = BN / 2;
-  const int nchunks = p.geglu ? HALF / 32 : BN / 32;
-  const int n_out = p.geglu ? p.N / 2 : p.N;
-  const int R = q * 32 + lane;                  // accumulator row owned by this thread
-  const int x = tc.x0 + (R % p.bx), y = tc.y0 + (R / p.bx);
-  const bool row_ok = x < p.X && y < p.Y && tc.z < p.Z;
-  const long long orow = ((long long)tc.z * p.Y + y) * p.X + x;
-  const int n0 = n_tile * BN;
-  const int ocol0 = p.geglu ? n_tile * HALF : n0;
-  const float* bias = p.bias ? p.bias + (long long)(p.bias_z_div > 0 ? min(tc.z, p.Z - 1) / p.bias_z_div : 0) * p.N : nullptr;
-  const uint32_t trow = tacc + ((uint32_t)(q * 32) << 16);
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue: TMEM -> registers -> (+bias / GEGLU / +residual) -> 256-bit global stores (whole 32-byte sectors), executed
+// by the EPI_WARPS epilogue warps (warp index 2..) of both GEMM kernels.  EPI_PER_QUAD warps share each TMEM lane
+// quadrant and split the accumulator's 32-column chunks; each thread owns one row.
+//   * chunk ownership rotates with the CTA-local tile counter `lt`, so tiles whose chunk count is not a multiple of
+//     EPI_PER_QUAD load the warps evenly over consecutive tiles;
+//   * the residual is software-pipelined one chunk ahead ACROSS tiles: while a chunk is converted and stored, the
+//     residual of the warp's next chunk -- of this tile or of the CTA's next tile -- is already in flight, so its HBM
+//     latency overlaps the main loop instead of sitting on the epilogue's critical path (measured: short-K linears with a
+//     residual spent a quarter of all epilogue stall samples on that load).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int epi_first_chunk(int sub, int lt, int nch) {
+  // chunk g = lt * nch + c of the CTA's chunk stream belongs to warp slot g mod EPI_PER_QUAD
+  if ((EPI_PER_QUAD & (EPI_PER_QUAD - 1)) == 0) return (sub - lt * nch) & (EPI_PER_QUAD - 1);
+  const int m = (lt * nch) % EPI_PER_QUAD;
+  return (sub + EPI_PER_QUAD - m) % EPI_PER_QUAD;
+}
 
-#pragma unroll 1
-  for (int c = sub; c < nchunks; c += EPI_PER_QUAD) {
-    float f[32];
+struct EpiTile {
+  long long orow;        // output row index of this thread
+  const float* bias;     // bias row for this tile's z (or nullptr)
+  int n_tile;
+  int c_first;           // this warp's first chunk in the tile
+  int wx, wy, wz;        // (x, y, z) of the warp's first row: TMA store coordinates
+  bool row_ok;
+};
+
+// tile index -> this thread's view of it.  m-tile = (tile / n_tiles) * m_mul + m_add  (CTA pairs: m_mul 2, m_add rank)
+__device__ __forceinline__ EpiTile epi_tile(const GemmParams& p, int tile, int lt, int nch, int m_mul, int m_add, int warp, int lane) {
+  EpiTile t;
+  const int mq = fast_div(p.div_n_tiles, tile);
+  t.n_tile = tile - mq * p.n_tiles;
+  const TileCoord tc = tile_coord_m(p, mq * m_mul + m_add);
+  const int R = (warp & 3) * 32 + lane;          // accumulator row owned by this thread (TMEM lane)
+  const int R0 = (warp & 3) * 32;
+  t.wx = tc.x0 + (R0 & (p.bx - 1)); t.wy = tc.y0 + (R0 >> p.bx_shift); t.wz = tc.z;
+  const int x = tc.x0 + (R & (p.bx - 1)), y = tc.y0 + (R >> p.bx_shift);
+  t.row_ok = x < p.X && y < p.Y && tc.z < p.Z;
+  t.orow = ((long long)tc.z * p.Y + y) * p.X + x;
+  t.bias = p.bias ? p.bias + (long long)(p.bias_z_div > 0 ? min(tc.z, p.Z - 1) / p.bias_z_div : 0) * p.N : nullptr;
+  t.c_first = epi_first_chunk((warp - 2) >> 2, lt, nch);
+  return t;
+}
+
+// store 32 consecutive output columns of this thread's row (fp16 or fp32), vector path or predicated scalar path
+__device__ __forceinline__ void epi_store32(const GemmParams& p, const EpiTile& t, int col0, int n_out, float (&f)[32], bool res_scalar,
+                                            uint8_t* stage, int lane) {
+  if (p.out_tma) {
+    // Stage the warp's 32 x 32 fp16 tile in shared memory (64B-swizzled rows: conflict-free 16-byte stores) and let the TMA
+    // unit write it: rows outside (X, Y, Z) are clipped by the tensor map, the LSU sees no global store at all.  Row-per-
+    // thread 32-byte global stores touch 32 different 128-byte lines per instruction and capped the epilogue at ~3 TB/s.
+    if (lane == 0) tma_store_wait_read();          // the previous store has finished reading this warp's staging tile
     __syncwarp();
-    if (!p.geglu) {
-      uint32_t v[32];
-      tmem_ld32(trow + c * 32, v);
-      tc_wait_ld();
-      const int nb = n0 + c * 32;
-      if (nb >= p.N) break;                      // warp-uniform
+    const uint32_t sbase = smem_u32(stage) + lane * 64;
+    const int sw = (lane >> 1) & 3;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (bias) {
-        if (nb + 32 <= p.N) {
+    for (int h = 0; h < 4; ++h) {
+      const uint32_t u0 = pack_half2(f[h * 8 + 0], f[h * 8 + 1]), u1 = pack_half2(f[h * 8 + 2], f[h * 8 + 3]);
+      const uint32_t u2 = pack_half2(f[h * 8 + 4], f[h * 8 + 5]), u3 = pack_half2(f[h * 8 + 6], f[h * 8 + 7]);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + ((h ^ sw) << 4)), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(&p.tmap_out, stage, col0, t.wx, t.wy, t.wz);
+      tma_store_commit();
+    }
+    return;
+  }
+  if (!t.row_ok || col0 >= n_out) return;
+  if (col0 + 32 <= n_out && p.vec_ok) {
+    if (p.out_f32) {
+      float* op = p.out_f32 + t.orow * p.ldo + col0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
-            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-          }
-        } else {
+      for (int h = 0; h < 4; ++h) {
+        uint32_t u[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) f[j] += __ldg(bias + nb + j);
-        }
+        for (int e = 0; e < 8; ++e) u[e] = __float_as_uint(f[h * 8 + e]);
+        st_global_256(op + h * 8, u);
       }
     } else {
-      // GEGLU: tile columns [0,BN/2) are values, [BN/2,BN) the matching gates (weights were interleaved per tile).
-      uint32_t a[32], g[32];
-      tmem_ld32(trow + c * 32, a);
-      tmem_ld32(trow + HALF + c * 32, g);
-      tc_wait_ld();
-      const int nv = n0 + c * 32;
+      __half* op = p.out + t.orow * p.ldo + col0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-        if (bias) {
-          ba = __ldg(reinterpret_cast<const float4*>(bias + nv + j));
-          bg = __ldg(reinterpret_cast<const float4*>(bias + nv + HALF + j));
-        }
-        f[j] = (__uint_as_float(a[j]) + ba.x) * gelu_epilogue(__uint_as_float(g[j]) + bg.x);
-        f[j + 1] = (__uint_as_float(a[j + 1]) + ba.y) * gelu_epilogue(__uint_as_float(g[j + 1]) + bg.y);
-        f[j + 2] = (__uint_as_float(a[j + 2]) + ba.z) * gelu_epilogue(__uint_as_float(g[j + 2]) + bg.z);
-        f[j + 3] = (__uint_as_float(a[j + 3]) + ba.w) * gelu_epilogue(__uint_as_float(g[j + 3]) + bg.w);
+      for (int h = 0; h < 2; ++h) {
+        uint32_t u[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) u[e] = pack_half2(f[h * 16 + 2 * e], f[h * 16 + 2 * e + 1]);
+        st_global_256(op + h * 16, u);
       }
     }
-    const int col0 = ocol0 + c * 32;
-    if (!row_ok || col0 >= n_out) continue;
-    if (col0 + 32 <= n_out && p.vec_ok) {
-      if (p.res) {
-        const __half* rp = p.res + orow * p.ldr + col0;      // plain loads: res may alias out (in-place residual)
+  } else {
+    // ragged N tail / unaligned pitch (e.g. the 320->4 output conv): predicated scalar path
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint32_t u[8];
-          ld_global_256(rp + j * 16, u);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&u[e]));
-            f[j * 16 + 2 * e] += t.x; f[j * 16 + 2 * e + 1] += t.y;
-          }
-        }
-      }
-      if (p.out_f32) {
-        float* op = p.out_f32 + orow * p.ldo + col0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t u[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) u[e] = __float_as_uint(f[j * 8 + e]);
-          st_global_256(op + j * 8, u);
-        }
-      } else {
-        __half* op = p.out + orow * p.ldo + col0;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint32_t u[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) u[e] = pack_half2(f[j * 16 + 2 * e], f[j * 16 + 2 * e + 1]);
-          st_global_256(op + j * 16, u);
-        }
-      }
-    } else {
-      // ragged N tail / unaligned pitch (e.g. the 320->4 output conv): predicated scalar path
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        if (col0 + e < n_out) {
-          float t = f[e];
-          if (p.res) t += __half2float(p.res[orow * p.ldr + col0 + e]);
-          if (p.out_f32) p.out_f32[orow * p.ldo + col0 + e] = t;
-          else p.out[orow * p.ldo + col0 + e] = __float2half_rn(t);
-        }
+    for (int e = 0; e < 32; ++e) {
+      if (col0 + e < n_out) {
+        float v = f[e];
+        if (res_scalar) v += __half2float(p.res[t.orow * p.ldr + col0 + e]);
+        if (p.out_f32) p.out_f32[t.orow * p.ldo + col0 + e] = v;
+        else p.out[t.orow * p.ldo + col0 + e] = __float2half_rn(v);
       }
     }
   }
+}
+
+// is chunk c of tile t on the vectorised residual path?  (same predicate at prefetch and at use)
+template <int BN>
+__device__ __forceinline__ bool epi_res_vec(const GemmParams& p, const EpiTile& t, int c) {
+  return p.res != nullptr && p.vec_ok && t.row_ok && c < BN / 32 && t.n_tile * BN + c * 32 + 32 <= p.N;
+}
+template <int BN>
+__device__ __forceinline__ void epi_res_prefetch(const GemmParams& p, const EpiTile& t, int c, uint32_t (&rres)[16]) {
+  if (epi_res_vec<BN>(p, t, c)) {
+    const __half* rp = p.res + t.orow * p.ldr + t.n_tile * BN + c * 32;   // plain loads: res may alias out (in-place residual)
+    ld_global_256(rp, *reinterpret_cast<uint32_t(*)[8]>(&rres[0]));
+    ld_global_256(rp + 16, *reinterpret_cast<uint32_t(*)[8]>(&rres[8]));
+  }
+}
+
+// hand a drained accumulator back to the MMA warp (CTA pairs: to the leader CTA's barrier).  Relaxed: the payload is TMEM,
+// ordered by the tcgen05 fences; a release here would be a MEMBAR that waits for the warp's outstanding global stores.
+template <bool PAIR>
+__device__ __forceinline__ void epi_release_acc(uint64_t* bar) {
+  if (PAIR) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0u));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote));
+  } else {
+    mbar_arrive_relaxed(bar);
+  }
+}
+
+// The epilogue warps' whole persistent loop over this CTA's tiles tile0, tile0 + stride, ... < p.total_tiles.
+template <int BN, int NACC, bool PAIR>
+__device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, int tile0, int stride, int m_mul, int m_add, uint32_t tmem_base,
+                                                   uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint8_t* epi_smem, int warp,
+                                                   int lane) {
+  uint8_t* stage = epi_smem + (warp - 2) * EPI_STAGE_BYTES;
+  const uint32_t tquad = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  int acc = 0, lt = 0;
+  uint32_t aph = 0;
+  if (!p.geglu) {
+    constexpr int NCH = BN / 32;
+    constexpr int MAXC = (NCH + EPI_PER_QUAD - 1) / EPI_PER_QUAD;
+    if (tile0 >= p.total_tiles) return;
+    EpiTile cur = epi_tile(p, tile0, 0, NCH, m_mul, m_add, warp, lane);
+    uint32_t rres[16];
+    epi_res_prefetch<BN>(p, cur, cur.c_first, rres);
+    for (int tile = tile0; tile < p.total_tiles; tile += stride, ++lt) {
+      const bool has_next = tile + stride < p.total_tiles;
+      EpiTile nxt = cur;
+      if (has_next) nxt = epi_tile(p, tile + stride, lt + 1, NCH, m_mul, m_add, warp, lane);
+      const int n0 = cur.n_tile * BN;
+      // chunks of this warp in this tile: c_first + j * EPI_PER_QUAD while inside the tile and inside N
+      int nmy = 0;
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j) {
+        const int c = cur.c_first + j * EPI_PER_QUAD;
+        if (c < NCH && n0 + c * 32 < p.N) nmy = j + 1;
+      }
+      if (nmy == 0 && has_next) epi_res_prefetch<BN>(p, nxt, nxt.c_first, rres);
+
+      mbar_wait(&tmem_full_bar[acc], aph);          // accumulator complete
+      tc_fence_after();
+      if (!(p.debug & 4)) {
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+          if (j >= nmy) break;                       // warp-uniform
+          const int c = cur.c_first + j * EPI_PER_QUAD;
+          const int nb = n0 + c * 32;
+          float f[32];
+          {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(tquad + acc * BN + c * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+          }
+          if (cur.bias) {
+            if (nb + 32 <= p.N) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(cur.bias + nb + e));
+                f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (nb + e < p.N) f[e] += __ldg(cur.bias + nb + e);
+            }
+          }
+          const bool vec = epi_res_vec<BN>(p, cur, c);
+          if (vec) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float2 t2 = __half22float2(*reinterpret_cast<const __half2*>(&rres[e]));
+              f[2 * e] += t2.x; f[2 * e + 1] += t2.y;
+            }
+          }
+          // rres is free again: request the residual of this warp's next chunk before storing this one
+          if (j + 1 < nmy) epi_res_prefetch<BN>(p, cur, c + EPI_PER_QUAD, rres);
+          else if (has_next) epi_res_prefetch<BN>(p, nxt, nxt.c_first, rres);
+          epi_store32(p, cur, nb, p.N, f, p.res != nullptr && !vec, stage, lane);
+        }
+      }
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) epi_release_acc<PAIR>(&tmem_empty_bar[acc]);
+      if (++acc == NACC) { acc = 0; aph ^= 1; }
+      cur = nxt;
+    }
+  } else {
+    // GEGLU: tile columns [0,BN/2) are values, [BN/2,BN) the matching gates (weights were interleaved per tile);
+    // out[:, n_tile*BN/2 + c] = (value + bias_v) * gelu(gate + bias_g).  No residual (checked on the host).
+    constexpr int HALF = BN / 2;
+    constexpr int NCH = HALF / 32 > 0 ? HALF / 32 : 1;
+    constexpr int MAXC = (NCH + EPI_PER_QUAD - 1) / EPI_PER_QUAD;
+    for (int tile = tile0; tile < p.total_tiles; tile += stride, ++lt) {
+      const EpiTile cur = epi_tile(p, tile, lt, NCH, m_mul, m_add, warp, lane);
+      const int n0 = cur.n_tile * BN;
+      mbar_wait(&tmem_full_bar[acc], aph);
+      tc_fence_after();
+      if (!(p.debug & 4)) {
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+          const int c = cur.c_first + j * EPI_PER_QUAD;
+          if (c >= NCH) break;                       // warp-uniform
+          float f[32];
+          uint32_t a[32], g[32];
+          __syncwarp();
+          tmem_ld32(tquad + acc * BN + c * 32, a);
+          tmem_ld32(tquad + acc * BN + HALF + c * 32, g);
+          tc_wait_ld();
+          const int nv = n0 + c * 32;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+            if (cur.bias) {
+              ba = __ldg(reinterpret_cast<const float4*>(cur.bias + nv + e));
+              bg = __ldg(reinterpret_cast<const float4*>(cur.bias + nv + HALF + e));
+            }
+            f[e] = (__uint_as_float(a[e]) + ba.x) * gelu_epilogue(__uint_as_float(g[e]) + bg.x);
+            f[e + 1] = (__uint_as_float(a[e + 1]) + ba.y) * gelu_epilogue(__uint_as_float(g[e + 1]) + bg.y);
+            f[e + 2] = (__uint_as_float(a[e + 2]) + ba.z) * gelu_epilogue(__uint_as_float(g[e + 2]) + bg.z);
+            f[e + 3] = (__uint_as_float(a[e + 3]) + ba.w) * gelu_epilogue(__uint_as_float(g[e + 3]) + bg.w);
+          }
+          epi_store32(p, cur, cur.n_tile * HALF + c * 32, p.N / 2, f, false, stage, lane);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) epi_release_acc<PAIR>(&tmem_empty_bar[acc]);
+      if (++acc == NACC) { acc = 0; aph ^= 1; }
+    }
+  }
+  if (p.out_tma && lane == 0) tma_store_wait_all();   // bulk stores must be complete before the CTA exits
 }
 #endif  // __CUDACC__
 

@@ -8,12 +8,12 @@
 // A may come from two tensors split along K (channel concat of skip connections without materialising it).
 // Epilogue: + bias[z/bias_z_div][n], GEGLU (value*gelu(gate)), + residual, fp16 / fp32 store (gemm_common.cuh).
 //
-// This file: the host entry point and the ONE-CTA-per-tile persistent kernel (576 threads):
+// This file: the host entry point and the ONE-CTA-per-tile persistent kernel (64 + 32 * EPI_WARPS = 448 threads):
 //   warp 0       TMA producer: walks this CTA's tiles and their (tap, k-block) iterations through a smem ring without
 //                draining between tiles, so the loads of tile i+1 are in flight while tile i is still being multiplied
 //   warp 1       TMEM allocator + single-thread tcgen05.mma issuer; TWO accumulators in TMEM (double buffer), so the
 //                main loop of tile i+1 overlaps the epilogue of tile i
-//   warps 2..17  epilogue (gemm_epilogue_tile)
+//   warps 2..    epilogue (gemm_epilogue_loop, gemm_common.cuh)
 // Tiles are ordered n-fastest so CTAs that run concurrently share A tiles in L2.  Large problems are routed to the
 // CTA-pair kernel of gemm_tap2.cu (UMMA M=256), which halves the per-SM shared-memory traffic for B.
 #include <cstdlib>
@@ -28,9 +28,9 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - EPI_SMEM_BYTES /*store staging*/;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024 + 512;
   // as many accumulators as fit the 512 TMEM columns (2..4): short-K tiles finish their main loop faster than the
   // accumulator hand-off (commit -> epilogue wake-up -> drain -> arrive) can turn around, so two buffers are not enough
   static constexpr int NACC = (512 / BN) > 4 ? 4 : (512 / BN);
@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;          // per-warp staging tiles of the TMA-store epilogue
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_SMEM_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;     // [NACC]
   uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::NACC;   // [NACC]
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
+    if (p.out_tma) tma_prefetch_desc(&p.tmap_out);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -78,21 +80,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Ring / accumulator positions are carried as (index, phase bit) pairs and tile coordinates come from multiply-high
+  // divisions: the role loops below are single-warp instruction streams whose length bounds the tile rate of short-K
+  // problems (measured: with 64-bit `it % STAGES` arithmetic and generic divisions the empty skeleton -- no TMA, no MMA,
+  // no epilogue -- already cost 1.3 us per tile).
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     // The whole warp runs the loop with warp-uniform control flow and ONE elected lane issues: the compiler can then
     // keep barrier / descriptor operands in uniform registers (a divergent `if (lane == 0)` loop costs an ELECT/BRA.ANY
     // serialisation loop around every UTMALDG -- measured).
-    long long it = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord_m(p, tile / p.n_tiles);
-      const int n0 = (tile % p.n_tiles) * BN;
+      const int m_tile = fast_div(p.div_n_tiles, tile);
+      const TileCoord tc = tile_coord_m(p, m_tile);
+      const int n0 = (tile - m_tile * p.n_tiles) * BN;
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
         const int brow = tap * p.N + n0;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = (int)(it % STAGES);
-          if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);        // a fresh barrier passes the wait on the "previous" phase
           if (elect_one()) {
             uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
@@ -109,6 +116,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
             }
           }
           __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -116,56 +124,44 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
     // ------------------------------ MMA issuer ------------------------------
     // warp-uniform loop, one elected lane issues (always the same lane: tcgen05.commit tracks the issuing thread's MMAs)
     constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-    long long it = 0;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-      const int acc = lt % Cfg::NACC;
-      if (lt >= Cfg::NACC) {                       // the epilogue must have drained this accumulator
-        mbar_wait(&tmem_empty_bar[acc], (uint32_t)((lt / Cfg::NACC) - 1) & 1);
-        tc_fence_after();
-      }
+    // smem descriptors: only the 14-bit start-address field (bytes >> 4) changes between stages / k-slices and the ring
+    // lies below 256 KB, so the field never carries: descriptors are formed by integer adds on the low word
+    const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
+    const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo = (uint32_t)desc0;
+    int s = 0, acc = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], aph ^ 1);    // the epilogue must have drained this accumulator
+      tc_fence_after();
       const uint32_t tacc = tmem_base + acc * BN;
-      for (int i = 0; i < iters; ++i, ++it) {
-        const int s = (int)(it % STAGES);
-        mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
+      for (int i = 0; i < iters; ++i) {
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (elect_one()) {
           if (p.debug & 1) {
             mbar_arrive(&empty_bar[s]);
           } else {
-            const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-            const uint32_t sb = sa + Cfg::A_BYTES;
+            const uint32_t la = desc_lo + (uint32_t)(s * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t da = umma_desc_sw128(sa + k * 32);
-              const uint64_t db = umma_desc_sw128(sb + k * 32);
-              umma_ss(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ss(tacc, ((uint64_t)desc_hi << 32) | (la + 2 * k), ((uint64_t)desc_hi << 32) | (la + (Cfg::A_BYTES >> 4) + 2 * k), idesc,
+                      (i > 0 || k > 0) ? 1u : 0u);
             umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
           }
         }
         __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       if (elect_one()) {
         if (p.debug & 1) mbar_arrive(&tmem_full_bar[acc]);
         else umma_commit(&tmem_full_bar[acc]);   // accumulator complete
       }
       __syncwarp();
+      if (++acc == Cfg::NACC) { acc = 0; aph ^= 1; }
     }
   } else {
     // ------------------------------ epilogue ------------------------------
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-      const TileCoord tc = tile_coord_m(p, tile / p.n_tiles);
-      const int acc = lt % Cfg::NACC;
-      mbar_wait(&tmem_full_bar[acc], (uint32_t)(lt / Cfg::NACC) & 1);
-      tc_fence_after();
-      if (!(p.debug & 4)) gemm_epilogue_tile<BN>(p, tc, tile % p.n_tiles, tmem_base + acc * BN, warp, lane);
-      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld inside): hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(&tmem_empty_bar[acc]);   // one arrival per warp; payload is TMEM: no release fence
-    }
+    gemm_epilogue_loop<BN, Cfg::NACC, false>(p, blockIdx.x, gridDim.x, 1, 0, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane);
   }
 
   tc_fence_before();
@@ -240,6 +236,12 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   p.tiles_x = (d.X + d.bx - 1) / d.bx;
   p.tiles_y = (d.Y + d.by - 1) / d.by;
   p.n_tiles = (d.N + BN - 1) / BN;
+  p.div_tiles_x = make_fastdiv(p.tiles_x);
+  p.div_tiles_y = make_fastdiv(p.tiles_y);
+  p.div_n_tiles = make_fastdiv(p.n_tiles);
+  p.bx_shift = 0;
+  while ((1 << p.bx_shift) < d.bx) ++p.bx_shift;
+  VC_REQUIRE((1 << p.bx_shift) == d.bx, "gemm_tap: bx=%d must be a power of two", d.bx);
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.Z;
   // CTA pairs pay off once every SM pair has several 256-row tiles; N must be covered by whole BN tiles so that each
   // CTA's half of the B tile (BN/2 rows) never straddles a tap boundary
@@ -284,6 +286,21 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   const bool o_al = ((reinterpret_cast<uintptr_t>(optr) & 31) == 0) && ((long long)d.ldo * esz) % 32 == 0;
   const bool r_al = !d.res || (((reinterpret_cast<uintptr_t>(d.res) & 31) == 0) && ((long long)d.ldr * 2) % 32 == 0);
   p.vec_ok = (o_al && r_al) ? 1 : 0;
+  {
+    // TMA-store epilogue: fp16 output whose width is whole 32-column chunks and whose rows are 16-byte aligned
+    static int tma_store = -1;                 // tuning switch VC_GEMM_TMA_STORE=0 keeps the direct-store epilogue
+    if (tma_store < 0) { const char* e = getenv("VC_GEMM_TMA_STORE"); tma_store = (e && e[0] == '0') ? 0 : 1; }
+    const int n_out = d.geglu ? d.N / 2 : d.N;
+    p.out_tma = (tma_store && d.out && !d.out_f32 && n_out % 32 == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && d.ldo % 8 == 0) ? 1 : 0;
+    if (p.out_tma) {
+      const uint32_t bw = d.bx < 32 ? d.bx : 32;
+      uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)d.X, (uint64_t)d.Y, (uint64_t)d.Z};
+      uint64_t str[3] = {(uint64_t)d.ldo * 2, (uint64_t)d.ldo * 2 * d.X, (uint64_t)d.ldo * 2 * d.X * d.Y};
+      uint32_t box[4] = {32, bw, 32 / bw, 1};
+      int rc = encode_tmap_f16(&p.tmap_out, d.out, 4, dims, str, box, 64);
+      if (rc) return rc;
+    }
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {

@@ -6,7 +6,7 @@
 // 1.25 PFLOP/s on the big 3x3 convs).  In a CTA pair each SM stages its own 128 A rows but only HALF of the B tile; the
 // pair's tensor cores read the two halves from both SMs, so per-SM smem traffic for B halves.
 //
-// Structure (cluster of 2 CTAs on one TPC, persistent, 576 threads per CTA):
+// Structure (cluster of 2 CTAs on one TPC, persistent, 448 threads per CTA):
 //   both CTAs : warp0 = TMA producer for its own A rows + its half of B (TMA .cta_group::2: the complete_tx lands on
 //               the LEADER's full barrier), warps2..17 = epilogue for its own 128 accumulator rows (own TMEM)
 //   leader    : warp1 lane0 issues tcgen05.mma.cta_group::2 for the pair; tcgen05.commit multicasts to both CTAs'
@@ -30,9 +30,9 @@ struct Gemm2Cfg {
   // 8 MMAs per full-barrier wait and per tcgen05.commit instead of 4.
   static constexpr int KSUB = 2;
   static constexpr int STAGE_BYTES = KSUB * SUB_BYTES;
-  static constexpr int BUDGET = 227 * 1024 - 1024 - 512;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - EPI_SMEM_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024 + 512;
   static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   static_assert(BN % 32 == 0 && (BN / 2) % 8 == 0, "B half must be whole 8-row swizzle groups");
   static_assert(B_BYTES % 1024 == 0, "B half must keep 1024-byte alignment of the next stage");
@@ -75,21 +75,14 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
                "h"((uint16_t)3)
                : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar_local, uint32_t cta_rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar_local)), "r"(cta_rank));
-  // relaxed: the payload (a drained TMEM accumulator) is ordered by tcgen05 fences; a release here would be a
-  // MEMBAR.ALL.GPU that waits for the warp's outstanding global stores
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote));
-}
-
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gemm_tap2_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;          // per-warp staging tiles of the TMA-store epilogue
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_SMEM_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]  (only the leader's copy is waited on)
@@ -106,6 +99,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
+    if (p.out_tma) tma_prefetch_desc(&p.tmap_out);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -127,21 +121,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // ring / accumulator positions as (index, phase) pairs and multiply-high tile coordinates: see gemm_tap.cu
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
     // warp-uniform loop, one elected lane issues (keeps TMA operands in uniform registers)
-    long long it = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int tile = cluster_id; tile < pair_tiles; tile += nclusters) {
-      const int n_tile = tile % p.n_tiles;
-      const TileCoord tc = tile_coord_m(p, (tile / p.n_tiles) * 2 + (int)rank);
+      const int m_pair = fast_div(p.div_n_tiles, tile);
+      const int n_tile = tile - m_pair * p.n_tiles;
+      const TileCoord tc = tile_coord_m(p, m_pair * 2 + (int)rank);
       const int n0 = n_tile * BN + (int)rank * (BN / 2);
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
         const int brow = tap * p.N + n0;
-        for (int kb = 0; kb < kblocks; kb += Cfg::KSUB, ++it) {
-          const int s = (int)(it % STAGES);
+        for (int kb = 0; kb < kblocks; kb += Cfg::KSUB) {
           const int nsub = min(Cfg::KSUB, kblocks - kb);
-          if (it >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((it / STAGES) - 1) & 1);
+          mbar_wait(&empty_bar[s], ph ^ 1);
           if (elect_one()) {
             if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * nsub * Cfg::SUB_BYTES);   // bytes of both CTAs land on the leader
             for (int u = 0; u < nsub; ++u) {
@@ -156,6 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
             }
           }
           __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -163,54 +160,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
     if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
-      long long it = 0;
-      int lt = 0;
-      for (int tile = cluster_id; tile < pair_tiles; tile += nclusters, ++lt) {
-        const int acc = lt & 1;
-        if (lt >= 2) {
-          mbar_wait(&tmem_empty_bar[acc], (uint32_t)((lt >> 1) - 1) & 1);
-          tc_fence_after();
-        }
+      const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
+      const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo = (uint32_t)desc0;   // start-address field never carries
+      int s = 0, acc = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = cluster_id; tile < pair_tiles; tile += nclusters) {
+        mbar_wait(&tmem_empty_bar[acc], aph ^ 1);
+        tc_fence_after();
         const uint32_t tacc = tmem_base + acc * BN;
         uint32_t first = 1;                          // the first MMA of a tile overwrites the accumulator
         for (int tap = 0; tap < p.num_taps; ++tap) {
-          for (int kb = 0; kb < kblocks; kb += Cfg::KSUB, ++it) {
-            const int s = (int)(it % STAGES);
+          for (int kb = 0; kb < kblocks; kb += Cfg::KSUB) {
             const int nsub = min(Cfg::KSUB, kblocks - kb);
-            mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1);
+            mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             if (elect_one()) {
               for (int u = 0; u < nsub; ++u) {
-                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES + u * Cfg::SUB_BYTES);
-                const uint32_t sb = sa + Cfg::A_BYTES;
+                const uint32_t la = desc_lo + (uint32_t)((s * Cfg::STAGE_BYTES + u * Cfg::SUB_BYTES) >> 4);
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)
-                  umma2_ss(tacc, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc, (first && u == 0 && k == 0) ? 0u : 1u);
+                  umma2_ss(tacc, ((uint64_t)desc_hi << 32) | (la + 2 * k), ((uint64_t)desc_hi << 32) | (la + (Cfg::A_BYTES >> 4) + 2 * k),
+                           idesc, (first && u == 0 && k == 0) ? 0u : 1u);
               }
               umma2_commit_mc(&empty_bar[s]);
             }
             first = 0;
             __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
         }
         if (elect_one()) umma2_commit_mc(&tmem_full_bar[acc]);
         __syncwarp();
+        acc ^= 1;
+        if (acc == 0) aph ^= 1;
       }
     }
   } else {
     // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
-    int lt = 0;
-    for (int tile = cluster_id; tile < pair_tiles; tile += nclusters, ++lt) {
-      const int n_tile = tile % p.n_tiles;
-      const TileCoord tc = tile_coord_m(p, (tile / p.n_tiles) * 2 + (int)rank);
-      const int acc = lt & 1;
-      mbar_wait(&tmem_full_bar[acc], (uint32_t)(lt >> 1) & 1);
-      tc_fence_after();
-      gemm_epilogue_tile<BN>(p, tc, n_tile, tmem_base + acc * BN, warp, lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);          // the leader's barrier counts both epilogues
-    }
+    // the leader's tmem_empty barrier counts the epilogue warps of both CTAs
+    gemm_epilogue_loop<BN, 2, true>(p, cluster_id, nclusters, 2, (int)rank, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane);
   }
 
   tc_fence_before();

@@ -200,9 +200,11 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, Nq: in
 
 
 def temporal_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, T: int, sites: int, heads: int,
-                  scale: float = 0.125) -> torch.Tensor:
+                  scale: float = 0.125, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk16(q, "tattn.q")
-    out = torch.empty((T * sites, heads * 64), device=q.device, dtype=torch.float16)
+    if out is None:
+        out = torch.empty((T * sites, heads * 64), device=q.device, dtype=torch.float16)
+    assert out.shape == (T * sites, heads * 64) and out.dtype == torch.float16 and out.stride(1) == 1
     assert q.stride(0) == k.stride(0) == v.stride(0)
     check(_lib.load().vc_temporal_attn(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), out.data_ptr(), out.stride(0),
                                        T, sites, heads, scale, _stream()), "vc_temporal_attn")

@@ -377,7 +377,7 @@ class UNetModel(nn.Module):
                 a = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=torch.float16)
                 for b in range(B):
                     rows = slice(b * Tg * HWl, (b + 1) * Tg * HWl)
-                    a[rows] = ops.temporal_attn(qkv[rows, :C], qkv[rows, C:2 * C], qkv[rows, 2 * C:], Tg, HWl, heads)
+                    ops.temporal_attn(qkv[rows, :C], qkv[rows, C:2 * C], qkv[rows, 2 * C:], Tg, HWl, heads, out=a[rows])
                 x = ops.linear(a, Q[ow], bias=Q[ob], res=x)
             g = ops.linear(ops.layernorm(x, *Q["ln3"]), Q["ff1_w"], bias=Q["ff1_b"], geglu=True)
             x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x)
