@@ -230,7 +230,11 @@ def main():
     metric = "DDIM denoise-steps/sec @ %sx%df" % (wl["px"], wl["T"])
     config = {"workload": "%s: latent 1x4x%dx%dx%d, CFG 7.5 (2 U-Net forwards/step), guidance_rescale 0.7, eta 1.0, 50-step uniform_trailing schedule"
                           % (args.workload, wl["T"], wl["H"], wl["W"]),
-              "l2": "working set per forward (tens of GB of activations, 2.9 GB weights) exceeds the 126 MB L2; no flush needed"}
+              "l2": "working set per forward (tens of GB of activations, 2.9 GB weights) exceeds the 126 MB L2; no flush needed",
+              "cfg": ("N=1: cond+uncond as one B=2 forward; the context-free prefix (input_blocks.0, init_attn, input_blocks.1 up to "
+                      "attn1; 6.9 of 165.5 TFLOP) is computed once for both branches and the cross-attention K/V of the step-invariant "
+                      "context are projected once per context tensor -- same outputs as two full forwards (SURVEY.md App. C.1/C.2); "
+                      "N>=2 even: one CFG branch per half of the ranks")}
 
     if args.impl == "reference":
         if rank != 0:

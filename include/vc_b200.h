@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VC_B200_ABI_VERSION 1
+#define VC_B200_ABI_VERSION 2
 
 int vc_abi_version(void);
 const char* vc_last_error(void);
@@ -51,6 +51,11 @@ typedef struct vc_gemm_desc {
   const float* bias; int32_t bias_z_div;   /* bias row = z / bias_z_div (0: single row)                  */
   const void* res; int32_t ldr;      /* optional fp16 residual added in the epilogue                     */
   int32_t geglu;                     /* 1: x*gelu(gate) epilogue, weights pre-interleaved per N tile     */
+  /* LayerNorm folded into the epilogue (BasicTransformerBlock norm1/2/3 -> to_q/k/v, ff.net[0]; attention.py:283-292):
+   * A holds the RAW rows, w is pre-scaled by the LayerNorm weight, bias holds (W.beta + linear bias);
+   * out[r,n] = rstd[r] * (acc[r,n] - mean[r] * ln_colsum[n]) + bias[n].  NULL = plain GEMM.  num_taps must be 1. */
+  const float* ln_stats;             /* [rows][2] fp32 (mean, rstd) from vc_layernorm_stats                */
+  const float* ln_colsum;            /* [N] fp32: sum_k w[n,k] of the fp16 weights                         */
 } vc_gemm_desc;
 int vc_gemm_tap(const vc_gemm_desc* d, void* stream);
 /* N-tile width the kernel will use for (N, geglu): needed to interleave GEGLU weights on the host */
@@ -94,6 +99,9 @@ int vc_groupnorm_stats(const void* x1, int32_t C1, const void* x2, int32_t C2, i
 int vc_groupnorm_apply(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t samples, int64_t rows_per_sample,
                        const float* stats, int64_t stat_rows, const float* gamma, const float* beta, float eps, int32_t silu, void* out,
                        void* stream);
+/* statistics half of nn.LayerNorm: stats[row] = (mean, 1/sqrt(var + eps)) in fp32; the normalisation is applied by the
+ * consuming vc_gemm_tap (ln_stats / ln_colsum), so the normalised activation is never written to memory */
+int vc_layernorm_stats(const void* x, int64_t rows, int32_t C, float eps, float* stats, void* stream);
 /* nn.LayerNorm over the last dim (attention.py:233-235), fp16 in/out, fp32 statistics */
 int vc_layernorm(const void* x, int64_t rows, int32_t C, const float* gamma, const float* beta, float eps, void* out,
                  void* stream);

@@ -38,13 +38,45 @@ def pack_geglu(w, b):
     return w[idx].to(torch.float16).contiguous(), b[idx].float().contiguous()
 
 
+def fold_layernorm(w, gamma, beta, bias=None):
+    w32 = w.reshape(w.shape[0], -1).float()
+    w16 = (w32 * gamma.float()[None, :]).to(torch.float16).contiguous()
+    b2 = w32 @ beta.float()
+    if bias is not None:
+        b2 = b2 + bias.float()
+    return w16, w16.float().sum(1).contiguous(), b2.contiguous()
+
+
+def pack_geglu_ln(w, b, gamma, beta):
+    w16, cs, b2 = fold_layernorm(w, gamma, beta, b)
+    inner = w.shape[0] // 2
+    bn = _geglu_tile(2 * inner)
+    half = bn // 2
+    idx = []
+    for t in range(2 * inner // bn):
+        idx.extend(range(t * half, (t + 1) * half))
+        idx.extend(range(inner + t * half, inner + (t + 1) * half))
+    idx = torch.tensor(idx)
+    return w16[idx].contiguous(), b2[idx].contiguous(), cs[idx].contiguous()
+
+
+def layernorm_stats(x, eps=1e-5):
+    xf = x.float()
+    mean = xf.mean(1)
+    rstd = torch.rsqrt(xf.var(1, unbiased=False) + eps)
+    return torch.stack([mean, rstd], 1).contiguous()
+
+
 def _h(t):
     return t.to(torch.float16)
 
 
-def linear(x, w, bias=None, res=None, geglu=False, out=None, out_f32=False, x2=None):
+def linear(x, w, bias=None, res=None, geglu=False, out=None, out_f32=False, x2=None, ln=None):
     a = x.float() if x2 is None else torch.cat([x.float(), x2.float()], 1)
     y = a @ w.float().t()
+    if ln is not None:
+        stats, colsum = ln
+        y = stats[:, 1:2] * (y - stats[:, 0:1] * colsum[None, :])
     if bias is not None:
         y = y + bias
     if geglu:

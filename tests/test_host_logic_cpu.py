@@ -115,3 +115,33 @@ def test_latent_diffusion_builds_inside_cuda_device_context_guard():
     with torch.device("meta"):
         b = schedule.model_buffers(base_scale=0.3)
     assert b["alphas_cumprod"].device.type == "cpu" and b["alphas_cumprod"].shape[0] == 1000
+
+
+def test_shared_cfg_prefix_and_kv_cache(cpu_ops):
+    """the context-free prefix computed once and the cached cross-attention K/V give the results of the
+    plain B=2 forward; the K/V cache follows the context tensor (new tensor or in-place write -> recomputed)."""
+    from viewcrafter_b200.unet import UNetModel
+    m = UNetModel(**dict(UNET_PARAMS, model_channels=64)).eval()
+    m.load_state_dict(synth.synth_state_dict(synth.module_shapes(m), seed=51), strict=True)
+    g = torch.Generator().manual_seed(52)
+    x1 = torch.randn(1, 8, 3, 8, 8, generator=g)
+    x = torch.cat([x1, x1], 0)
+    t, fs = torch.tensor([499, 499]), torch.tensor([10, 10])
+    ctx = torch.randn(2, 333, 1024, generator=g)
+    plain = m(x, t, context=ctx, fs=fs)
+    shared = m(x, t, context=ctx, fs=fs, cfg_shared_prefix=True)
+    # not bit-equal: the fp16 roundings of a B=1 and a B=2 GEMM differ (summation order), the same noise as B=2 vs B=1 runs
+    d = (plain - shared).abs()
+    assert float(d.max()) < 0.02 and float(d.mean()) < 3e-3, (float(d.max()), float(d.mean()))
+    assert float((plain[0] - plain[1]).abs().mean()) > 5 * float(d.mean())      # the two branches do differ (different context)
+    # K/V cache: same tensor object -> hit; in-place change or a new tensor -> recomputed
+    n_cached = len(m._kv_cache)
+    assert n_cached > 3 and m._kv_cache["ref"] is ctx
+    ctx2 = ctx.clone()
+    ctx2[1] = ctx[0]
+    out2 = m(x, t, context=ctx2, fs=fs)
+    assert m._kv_cache["ref"] is ctx2
+    assert float((out2[0] - out2[1]).abs().max()) < 0.02              # identical branches now
+    ctx2[1] = ctx[1]                                                  # in-place write bumps the version counter
+    out3 = m(x, t, context=ctx2, fs=fs)
+    assert float((out3 - plain).abs().max()) < 0.02

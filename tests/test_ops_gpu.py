@@ -231,6 +231,41 @@ def test_layernorm(ops, rows, C):
     close(ops.layernorm(x, g, b), F.layer_norm(x.float(), (C,), g, b, 1e-5), 3e-3, what="layernorm")
 
 
+@pytest.mark.parametrize("rows,C", [(300, 320), (1000, 1280)])
+def test_layernorm_stats(ops, rows, C):
+    x = rnd(rows, C, seed=157, scale=2.0) + 1.0
+    st = ops.layernorm_stats(x)
+    xf = x.float()
+    close(st[:, 0], xf.mean(1), 1e-5, what="ln mean")
+    close(st[:, 1], torch.rsqrt(xf.var(1, unbiased=False) + 1e-5), 1e-5, what="ln rstd")
+
+
+@pytest.mark.parametrize("M,C,N", [(300, 320, 960), (9216, 320, 320), (700, 640, 1920), (1000, 1280, 3840)])
+def test_linear_folded_layernorm(ops, M, C, N):
+    """LayerNorm folded into the consumer GEMM (raw rows in, epilogue applies mean / rstd) vs LayerNorm -> Linear in fp32."""
+    x = rnd(M, C, seed=158, scale=1.5) + 0.7                  # non-zero row means: the mean * colsum term matters
+    g, b = rnd(C, seed=159, dtype=torch.float32) + 1.0, rnd(C, seed=160, dtype=torch.float32, scale=0.3)
+    w = rnd(N, C, seed=161, dtype=torch.float32, scale=C ** -0.5)
+    bias = rnd(N, seed=162, dtype=torch.float32, scale=0.2)
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5) @ w.t() + bias
+    w16, cs, b2 = ops.fold_layernorm(w, g, b, bias)
+    out = ops.linear(x, w16, bias=b2, ln=(ops.layernorm_stats(x), cs))
+    close(out, ref, 6e-3, what="folded LN linear")
+
+
+@pytest.mark.parametrize("M,C", [(300, 320), (2304, 640)])
+def test_geglu_folded_layernorm(ops, M, C):
+    x = rnd(M, C, seed=163, scale=1.5) - 0.4
+    g, b = rnd(C, seed=164, dtype=torch.float32) + 1.0, rnd(C, seed=165, dtype=torch.float32, scale=0.3)
+    w = rnd(8 * C, C, seed=166, dtype=torch.float32, scale=C ** -0.5)
+    bias = rnd(8 * C, seed=167, dtype=torch.float32, scale=0.1)
+    h = F.layer_norm(x.float(), (C,), g, b, 1e-5) @ w.t() + bias
+    val, gate = h.chunk(2, dim=-1)
+    wp, bp, cs = ops.pack_geglu_ln(w, bias, g, b)
+    out = ops.linear(x, wp, bias=bp, geglu=True, ln=(ops.layernorm_stats(x), cs))
+    close(out, val * F.gelu(gate), 8e-3, what="folded LN geglu")
+
+
 # ---------------------------------------------------------------------------------------------- boundary / embedding / ddim
 def test_layout_roundtrip(ops):
     B, C, T, H, W = 2, 4, 3, 5, 8

@@ -74,6 +74,33 @@ def test_unet_batch2_and_default_fs_vs_oracle():
     assert float(err.max()) <= MAX_ERR and float(err.mean()) <= MEAN_ERR
 
 
+def test_shared_cfg_prefix_vs_oracle():
+    """cond/uncond batch with the context-free prefix computed once (cfg_shared_prefix) and the cached
+    cross-attention K/V (App. C.1): same outputs as two independent oracle forwards, also on the second (cache-hit) call."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import lvdm_oracle as O
+    from oracle import synth
+    from viewcrafter_b200.unet import UNetModel
+    kw = dict(UNET_KW); kw.update(model_channels=64)
+    shapes = synth.module_shapes(UNetModel(**kw))
+    m, sd = _build(dict(model_channels=64), shapes, seed=11)
+    g = torch.Generator().manual_seed(12)
+    x1 = torch.randn(1, 8, 5, 8, 8, generator=g)
+    x = torch.cat([x1, x1], 0)
+    ctx = torch.randn(2, 333, 1024, generator=g)
+    t, fs = torch.tensor([499, 499]), torch.tensor([10, 10])
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, ctx, fs)
+    xc, tc, cc, fc = x.cuda(), t.cuda(), ctx.cuda(), fs.cuda()
+    for call in range(2):
+        y = m(xc, tc, context=cc, fs=fc, cfg_shared_prefix=True)
+        err = (y.cpu() - ref).abs()
+        print(f"shared prefix call {call}: max err {float(err.max()):.4g} mean err {float(err.mean()):.4g}")
+        assert float(err.max()) <= MAX_ERR and float(err.mean()) <= MEAN_ERR
+    assert m._kv_cache["ref"] is cc and len(m._kv_cache) > 3
+
+
 def test_unet_full_width_block_stack_vs_oracle():
     """Real channel widths (model_channels=320: 5/10/20 heads, N tiles of 160/256, K split 1280+640...) at a tiny
     spatial size so the fp32 CPU oracle finishes in seconds."""

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VC_B200_LIB") or os.path.join(_HERE, "libvc_b200.so")   # override: A/B builds of the kernels
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class VcError(RuntimeError):
@@ -24,7 +24,7 @@ class GemmDesc(C.Structure):
                 ("tap_dx", C.c_int32 * 9), ("tap_dy", C.c_int32 * 9),
                 ("out", C.c_void_p), ("out_f32", C.c_void_p), ("ldo", C.c_int32),
                 ("bias", C.c_void_p), ("bias_z_div", C.c_int32), ("res", C.c_void_p), ("ldr", C.c_int32),
-                ("geglu", C.c_int32)]
+                ("geglu", C.c_int32), ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p)]
 
 
 class AttnDesc(C.Structure):
@@ -56,6 +56,7 @@ SIGNATURES = {
     "vc_groupnorm_nhwc": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp, _vp, _f32, _i32, _vp, _vp, _sz, _vp]),
     "vc_groupnorm_stats": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp, _vp, _sz, _vp]),
     "vc_groupnorm_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _f32, _i32, _vp, _vp]),
+    "vc_layernorm_stats": (C.c_int, [_vp, _i64, _i32, _f32, _vp, _vp]),
     "vc_layernorm": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp]),
     "vc_softmax_rows_f32": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp]),
     "vc_upsample2x_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

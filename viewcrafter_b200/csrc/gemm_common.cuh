@@ -63,6 +63,8 @@ struct GemmParams {
   const __half* res;
   int ldr;
   int geglu;
+  const float* ln_stats;   // folded LayerNorm: per-row (mean, rstd); nullptr = plain
+  const float* ln_colsum;  // folded LayerNorm: per-column sum of the (gamma-scaled) weights
   int out_tma;           // fp16 output written by TMA stores from per-warp staging tiles (full-line, LSU-free)
   int vec_ok;            // rows are 32-byte aligned: the 256-bit epilogue path may be used
   int debug;             // profiling aid (VC_GEMM_DEBUG): 1 = skip the MMAs (feed rate only), 2 = skip TMA (MMA rate only),
@@ -278,6 +280,8 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, int tile
         if (c < NCH && n0 + c * 32 < p.N) nmy = j + 1;
       }
       if (nmy == 0 && has_next) epi_res_prefetch<BN>(p, nxt, nxt.c_first, rres);
+      float2 ln = make_float2(0.f, 1.f);
+      if (p.ln_stats && cur.row_ok) ln = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + cur.orow);
 
       mbar_wait(&tmem_full_bar[acc], aph);          // accumulator complete
       tc_fence_after();
@@ -295,6 +299,15 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, int tile
             tc_wait_ld();
 #pragma unroll
             for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+          }
+          if (p.ln_stats) {                          // folded LayerNorm (host guarantees N % 32 == 0)
+            const float nm = -ln.x;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + nb + e));
+              f[e] = fmaf(nm, cs.x, f[e]) * ln.y; f[e + 1] = fmaf(nm, cs.y, f[e + 1]) * ln.y;
+              f[e + 2] = fmaf(nm, cs.z, f[e + 2]) * ln.y; f[e + 3] = fmaf(nm, cs.w, f[e + 3]) * ln.y;
+            }
           }
           if (cur.bias) {
             if (nb + 32 <= p.N) {
@@ -339,6 +352,9 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, int tile
     for (int tile = tile0; tile < p.total_tiles; tile += stride, ++lt) {
       const EpiTile cur = epi_tile(p, tile, lt, NCH, m_mul, m_add, warp, lane);
       const int n0 = cur.n_tile * BN;
+      float2 ln = make_float2(0.f, 1.f);
+      if (p.ln_stats && cur.row_ok) ln = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + cur.orow);
+      const float nm = -ln.x;
       mbar_wait(&tmem_full_bar[acc], aph);
       tc_fence_after();
       if (!(p.debug & 4)) {
@@ -353,6 +369,21 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, int tile
           tmem_ld32(tquad + acc * BN + HALF + c * 32, g);
           tc_wait_ld();
           const int nv = n0 + c * 32;
+          if (p.ln_stats) {                          // folded LayerNorm on both the value and the gate columns
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 ca = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + nv + e));
+              const float4 cg = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + nv + HALF + e));
+              a[e] = __float_as_uint(fmaf(nm, ca.x, __uint_as_float(a[e])) * ln.y);
+              a[e + 1] = __float_as_uint(fmaf(nm, ca.y, __uint_as_float(a[e + 1])) * ln.y);
+              a[e + 2] = __float_as_uint(fmaf(nm, ca.z, __uint_as_float(a[e + 2])) * ln.y);
+              a[e + 3] = __float_as_uint(fmaf(nm, ca.w, __uint_as_float(a[e + 3])) * ln.y);
+              g[e] = __float_as_uint(fmaf(nm, cg.x, __uint_as_float(g[e])) * ln.y);
+              g[e + 1] = __float_as_uint(fmaf(nm, cg.y, __uint_as_float(g[e + 1])) * ln.y);
+              g[e + 2] = __float_as_uint(fmaf(nm, cg.z, __uint_as_float(g[e + 2])) * ln.y);
+              g[e + 3] = __float_as_uint(fmaf(nm, cg.w, __uint_as_float(g[e + 3])) * ln.y);
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;

@@ -281,6 +281,12 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   p.bias = d.bias; p.bias_z_div = d.bias_z_div;
   p.res = d.res; p.ldr = d.ldr;
   p.geglu = d.geglu;
+  VC_REQUIRE((d.ln_stats == nullptr) == (d.ln_colsum == nullptr), "gemm_tap: ln_stats and ln_colsum go together");
+  VC_REQUIRE(!d.ln_stats || (d.num_taps == 1 && d.N % 32 == 0 && d.Y == 1 && d.Z == 1 && !d.a2),
+             "gemm_tap: folded LayerNorm needs a plain [M,K] x [N,K] GEMM with N %% 32 == 0");
+  VC_REQUIRE(!d.ln_stats || ((reinterpret_cast<uintptr_t>(d.ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(d.ln_colsum) & 15) == 0),
+             "gemm_tap: ln_stats / ln_colsum misaligned");
+  p.ln_stats = d.ln_stats; p.ln_colsum = d.ln_colsum;
   // 256-bit epilogue accesses need 32-byte aligned rows (true for every activation on the U-Net / VAE path); anything
   // else (odd pitches, the 4- and 3-channel output convs) takes the predicated scalar path inside the kernel
   const bool o_al = ((reinterpret_cast<uintptr_t>(optr) & 31) == 0) && ((long long)d.ldo * esz) % 32 == 0;

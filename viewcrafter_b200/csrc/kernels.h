@@ -22,6 +22,11 @@ struct GemmDesc {
   const float* bias = nullptr; int bias_z_div = 0;
   const __half* res = nullptr; int ldr = 0;
   int geglu = 0;
+  // LayerNorm folded into the epilogue: the GEMM runs on the RAW rows x with weights pre-scaled by the LayerNorm gamma,
+  //   out[r,n] = rstd[r] * (acc[r,n] - mean[r] * ln_colsum[n]) + bias[n]      (bias holds W.beta + linear bias)
+  // ln_stats: [rows][2] fp32 (mean, rstd) from layernorm_stats; ln_colsum[n] = sum_k w[n,k] (of the fp16 weights). 1 tap only.
+  const float* ln_stats = nullptr;
+  const float* ln_colsum = nullptr;
 };
 int gemm_tap(const GemmDesc& d, cudaStream_t stream);
 
@@ -50,6 +55,7 @@ int groupnorm_apply(const __half* x1, int C1, const __half* x2, int C2, int samp
                     const float* stats, long long stat_rows, const float* gamma, const float* beta, float eps, int silu, __half* out,
                     cudaStream_t stream);
 
+int layernorm_stats(const __half* x, long long rows, int C, float eps, float* stats, cudaStream_t stream);
 int layernorm_rows(const __half* x, long long rows, int C, const float* gamma, const float* beta, float eps, __half* out,
                    cudaStream_t stream);
 

@@ -21,10 +21,37 @@ struct GnGeom {
   long long stat_rows;    // rows the statistics cover (== rows, or the global row count when sharded across GPUs)
 };
 
-__device__ __forceinline__ uint4 gn_load(const __half* x1, const __half* x2, const GnGeom& g, long long sample, long long row, int c) {
-  const long long r = sample * g.rows + row;
-  const __half* p = (c < g.C1) ? (x1 + r * g.C1 + c) : (x2 + r * g.C2 + (c - g.C1));
-  return *reinterpret_cast<const uint4*>(p);
+// Per-thread view of the rows a CTA owns: thread (pl, v) handles channel vector v (8 channels) of rows r0 + pl + k * ppi.
+// Pointers are formed once and advanced by a constant stride: the loops below are pure streaming and were instruction-
+// issue bound when every load recomputed a 64-bit (row * C + c) address and re-decided which of the two sources to read.
+struct GnThread {
+  const __half* src;      // first element this thread reads
+  long long sstride;      // elements between this thread's consecutive rows in the source
+  long long n;            // rows this thread handles
+  long long orow0;        // first output row (sample-relative)
+};
+__device__ __forceinline__ GnThread gn_thread(const __half* x1, const __half* x2, const GnGeom& g, int split, int sample, int v, int pl) {
+  GnThread t;
+  const long long r0 = (long long)split * g.rows_per_split;
+  const long long r1 = min(g.rows, r0 + g.rows_per_split);
+  const long long first = r0 + pl;
+  t.n = first < r1 ? (r1 - first + g.ppi - 1) / g.ppi : 0;
+  t.orow0 = first;
+  const int c = v * 8;
+  const long long r = (long long)sample * g.rows + first;
+  if (c < g.C1) { t.src = x1 + r * g.C1 + c; t.sstride = (long long)g.ppi * g.C1; }
+  else { t.src = x2 + r * g.C2 + (c - g.C1); t.sstride = (long long)g.ppi * g.C2; }
+  return t;
+}
+
+__device__ __forceinline__ void gn_acc8(const uint4& u, float (&s)[8], float (&ss)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(h[e]);
+    s[2 * e] += f.x; ss[2 * e] = fmaf(f.x, f.x, ss[2 * e]);
+    s[2 * e + 1] += f.y; ss[2 * e + 1] = fmaf(f.y, f.y, ss[2 * e + 1]);
+  }
 }
 
 __device__ __forceinline__ void gn_stats_dev(const __half* __restrict__ x1, const __half* __restrict__ x2, const GnGeom& g,
@@ -38,27 +65,18 @@ __device__ __forceinline__ void gn_stats_dev(const __half* __restrict__ x1, cons
   float s[8], ss[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
-  const long long r0 = (long long)split * g.rows_per_split;
-  const long long r1 = min(g.rows, r0 + g.rows_per_split);
-  // 4 independent 16-byte loads in flight per thread (the kernel is pure streaming: latency must be covered by MLP)
-  for (long long r = r0 + pl; r < r1; r += 4ll * g.ppi) {
-    uint4 u[4];
+  const GnThread t = gn_thread(x1, x2, g, split, sample, v, pl);
+  const __half* p = t.src;
+  long long k = 0;
+  // 8 independent 16-byte loads in flight per thread (pure streaming: latency is covered by memory-level parallelism)
+  for (; k + 8 <= t.n; k += 8, p += 8 * t.sstride) {
+    uint4 u[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long ri = r + (long long)i * g.ppi;
-      u[i] = ri < r1 ? gn_load(x1, x2, g, sample, ri, v * 8) : make_uint4(0, 0, 0, 0);
-    }
+    for (int i = 0; i < 8; ++i) u[i] = *reinterpret_cast<const uint4*>(p + i * t.sstride);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __half2* h = reinterpret_cast<const __half2*>(&u[i]);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h[e]);
-        s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
-        s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
-      }
-    }
+    for (int i = 0; i < 8; ++i) gn_acc8(u[i], s, ss);
   }
+  for (; k < t.n; ++k, p += t.sstride) gn_acc8(*reinterpret_cast<const uint4*>(p), s, ss);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     atomicAdd(&red[v * 8 + e], s[e]);
@@ -71,6 +89,25 @@ __device__ __forceinline__ void gn_stats_dev(const __half* __restrict__ x1, cons
     for (int c = grp * g.cg; c < (grp + 1) * g.cg; ++c) acc += red[which * g.C + c];
     partial[((long long)sample * g.splits + split) * 64 + tid] = acc;
   }
+}
+
+__device__ __forceinline__ uint4 gn_norm8(const uint4& u, const float (&sc)[8], const float (&sh)[8], int silu) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+  float f[8];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t2 = __half22float2(h[e]);
+    f[2 * e] = fmaf(t2.x, sc[2 * e], sh[2 * e]);
+    f[2 * e + 1] = fmaf(t2.y, sc[2 * e + 1], sh[2 * e + 1]);
+  }
+  if (silu) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+  }
+  uint4 o;
+  o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
+  o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
+  return o;
 }
 
 __device__ __forceinline__ void gn_apply_dev(const __half* __restrict__ x1, const __half* __restrict__ x2, const GnGeom& g,
@@ -104,52 +141,34 @@ __device__ __forceinline__ void gn_apply_dev(const __half* __restrict__ x1, cons
     sc[e] = a;
     sh[e] = beta[c] - mean_s[grp] * a;
   }
-  const long long r0 = (long long)blockIdx.x * g.rows_per_split;
-  const long long r1 = min(g.rows, r0 + g.rows_per_split);
-  for (long long r = r0 + pl; r < r1; r += 4ll * g.ppi) {
+  const GnThread t = gn_thread(x1, x2, g, blockIdx.x, sample, v, pl);
+  const __half* p = t.src;
+  __half* o = out + ((long long)sample * g.rows + t.orow0) * g.C + v * 8;
+  const long long ostride = (long long)g.ppi * g.C;
+  long long k = 0;
+  for (; k + 4 <= t.n; k += 4, p += 4 * t.sstride, o += 4 * ostride) {
     uint4 u[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long ri = r + (long long)i * g.ppi;
-      if (ri < r1) u[i] = gn_load(x1, x2, g, sample, ri, v * 8);
-    }
+    for (int i = 0; i < 4; ++i) u[i] = *reinterpret_cast<const uint4*>(p + i * t.sstride);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long ri = r + (long long)i * g.ppi;
-      if (ri >= r1) break;
-      const __half2* h = reinterpret_cast<const __half2*>(&u[i]);
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 t = __half22float2(h[e]);
-        f[2 * e] = t.x; f[2 * e + 1] = t.y;
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float y = f[e] * sc[e] + sh[e];
-        f[e] = silu ? silu_f(y) : y;
-      }
-      uint4 o;
-      o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
-      o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(out + ((long long)sample * g.rows + ri) * g.C + v * 8) = o;
-    }
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(o + i * ostride) = gn_norm8(u[i], sc, sh, silu);
   }
+  for (; k < t.n; ++k, p += t.sstride, o += ostride) *reinterpret_cast<uint4*>(o) = gn_norm8(*reinterpret_cast<const uint4*>(p), sc, sh, silu);
 }
 
-__global__ void __launch_bounds__(1024) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
-                                                        float* __restrict__ partial) {
+__global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+                                                       float* __restrict__ partial) {
   gn_stats_dev(x1, x2, g, partial);
 }
-__global__ void __launch_bounds__(1024) gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
-                                                        const float* __restrict__ partial, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
+__global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+                                                       const float* __restrict__ partial, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
   gn_apply_dev(x1, x2, g, partial, gamma, beta, eps, silu, out);
 }
 // Fused single launch: statistics pass, a grid-wide rendezvous of the CTAs of one sample (all CTAs are co-resident by
 // construction -- the host checks the occupancy), then the normalise pass, whose re-read of x is served by the 126 MB L2
 // for everything but the largest 5-D tensors: HBM traffic drops from 3 passes to ~2.
-__global__ void __launch_bounds__(1024) gn_fused_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+__global__ void __launch_bounds__(512) gn_fused_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
                                                         float* __restrict__ partial, unsigned int* __restrict__ counters,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                                         __half* __restrict__ out) {
@@ -168,7 +187,7 @@ __global__ void __launch_bounds__(1024) gn_fused_kernel(const __half* __restrict
 static int gn_geometry(GnGeom& g, const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample) {
   const int C = C1 + (x2 ? C2 : 0);
   VC_REQUIRE(x1, "groupnorm: null pointer");
-  VC_REQUIRE(C % 32 == 0 && C1 % 8 == 0 && (!x2 || C2 % 8 == 0) && C <= 8192, "groupnorm: unsupported channels C1=%d C2=%d", C1, C2);
+  VC_REQUIRE(C % 32 == 0 && C1 % 8 == 0 && (!x2 || C2 % 8 == 0) && C <= 4096, "groupnorm: unsupported channels C1=%d C2=%d", C1, C2);
   VC_REQUIRE(samples >= 1 && rows_per_sample >= 1, "groupnorm: empty input");
   g.C = C; g.C1 = C1; g.C2 = x2 ? C2 : 0;
   g.vecs = C / 8;
@@ -354,6 +373,77 @@ int layernorm_rows(const __half* x, long long rows, int C, const float* gamma, c
     layernorm_kernel<5><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, gamma, beta, eps, out);
   else
     layernorm_kernel<8><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, gamma, beta, eps, out);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// Statistics half of LayerNorm: stats[row] = (mean, rstd).  The normalisation itself is folded into the consuming GEMM's
+// epilogue (GemmDesc::ln_stats), which turns LayerNorm from a read + write pass into this read-only pass.
+// One warp per group of 4 rows, every lane keeps 4 independent 16-byte loads in flight; sums are taken about a per-row
+// pivot (the row's first element) so the one-pass variance does not cancel when |mean| >> std.  ~40 registers: 48+ warps
+// per SM (the register-resident two-pass kernel above runs at 16 warps per SM and ~2.6 TB/s as a pure reader).
+__global__ void __launch_bounds__(256) ln_stats_kernel(const __half* __restrict__ x, long long rows, int C, float eps,
+                                                       float2* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int vecs = C >> 3;
+  const float invC = 1.f / (float)C;
+  for (long long row0 = gw * 4; row0 < rows; row0 += nwarps * 4) {
+    float piv[4], s[4], q[4];
+    const __half* rp[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const long long row = min(row0 + rr, rows - 1);            // clamp: tail rows recompute the last row (not stored)
+      rp[rr] = x + row * C;
+      piv[rr] = __half2float(__ldg(rp[rr]));
+      s[rr] = q[rr] = 0.f;
+    }
+    for (int v = lane; v < vecs; v += 32) {
+      uint4 u[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) u[rr] = *reinterpret_cast<const uint4*>(rp[rr] + v * 8);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[rr]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          const float a = f.x - piv[rr], b = f.y - piv[rr];
+          s[rr] += a + b;
+          q[rr] = fmaf(a, a, fmaf(b, b, q[rr]));
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s[rr] += __shfl_xor_sync(0xffffffffu, s[rr], o);
+        q[rr] += __shfl_xor_sync(0xffffffffu, q[rr], o);
+      }
+    }
+    if (lane < 4 && row0 + lane < rows) {
+      float sm = s[0], qm = q[0], pm = piv[0];
+#pragma unroll
+      for (int rr = 1; rr < 4; ++rr)
+        if (lane == rr) { sm = s[rr]; qm = q[rr]; pm = piv[rr]; }
+      const float d = sm * invC;
+      const float var = fmaxf(qm * invC - d * d, 0.f);
+      stats[row0 + lane] = make_float2(pm + d, rsqrtf(var + eps));
+    }
+  }
+}
+
+int layernorm_stats(const __half* x, long long rows, int C, float eps, float* stats, cudaStream_t stream) {
+  VC_REQUIRE(x && stats, "layernorm_stats: null pointer");
+  VC_REQUIRE(C % 8 == 0 && C <= 8192 && rows > 0, "layernorm_stats: unsupported C=%d rows=%lld", C, rows);
+  VC_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 7) == 0, "layernorm_stats: stats must be 8-byte aligned");
+  const int wpb = 8;
+  long long blocks = (rows + 4 * wpb - 1) / (4 * wpb);
+  const long long cap = (long long)sm_count() * 8;              // 8 x 256 threads = 64 warps per SM
+  if (blocks > cap) blocks = cap;
+  ln_stats_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, eps, reinterpret_cast<float2*>(stats));
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -131,6 +131,23 @@ class DDIMSampler(object):
                 intermediates['pred_x0'].append(pred_x0)
         return img, intermediates
 
+    def _stacked_conditioning(self, c, uc):
+        """cond|uncond conditioning stacked along the batch axis, built once per (c, uc) pair and reused for every step:
+        the sampler passes the same dicts for all steps (ddim.py:150-160), and handing the U-Net the SAME context tensor
+        each step lets it keep the cross-attention K/V projections.  Also reports whether the
+        c_concat entries of the two branches are the same tensors (utils/diffusion_utils.py:152-153)."""
+        ents = [(a, u) for k in c for a, u in zip(c[k], uc[k])]
+        sig = [(a, a._version, u, u._version) for a, u in ents]
+        cached = getattr(self, "_cat_cache", None)
+        if cached is not None and len(cached[0]) == len(sig) and all(
+                a is a0 and va == va0 and u is u0 and vu == vu0 for (a, va, u, vu), (a0, va0, u0, vu0) in zip(sig, cached[0])):
+            return cached[1], cached[2]
+        cat = {k: [torch.cat([a, u], 0) for a, u in zip(c[k], uc[k])] for k in c}
+        same = all((a is u) or (a.shape == u.shape and bool(torch.equal(a, u))) for a, u in zip(c.get("c_concat", []), uc.get("c_concat", []))) \
+            if "c_concat" in c else False
+        self._cat_cache = (sig, cat, same)
+        return cat, same
+
     def _apply_both(self, x, t, c, uc, kwargs):
         """cond + uncond as one B=2 forward when every conditioning entry can be stacked; else two calls (ddim.py:223-224)."""
         cfg = getattr(self.model, "_cfg", None)
@@ -138,9 +155,13 @@ class DDIMSampler(object):
             mine = self.model.apply_model(x, t, c if cfg.branch == 0 else uc, **kwargs)
             return cfg.exchange(mine.float().contiguous())
         if self.batch_cfg and isinstance(c, dict) and isinstance(uc, dict) and c.keys() == uc.keys():
-            cat = {k: [torch.cat([a, u], 0) for a, u in zip(c[k], uc[k])] for k in c}
+            cat, same_concat = self._stacked_conditioning(c, uc)
             kw = {k: (torch.cat([v, v], 0) if isinstance(v, torch.Tensor) and v.dim() >= 1 and v.shape[0] == x.shape[0] else v)
                   for k, v in kwargs.items()}
+            if same_concat and x.shape[0] == 1:
+                # both branches see the same x, t, fs and c_concat: let the U-Net compute the context-free prefix once
+                # (ignored by models that do not know the hint)
+                kw["cfg_shared_prefix"] = True
             out = self.model.apply_model(torch.cat([x, x], 0), torch.cat([t, t], 0), cat, **kw)
             n = x.shape[0]
             return out[:n].contiguous(), out[n:].contiguous()

@@ -26,7 +26,8 @@ class DiffusionWrapper(nn.Module):
         if self.conditioning_key != "hybrid":
             raise NotImplementedError("only the 'hybrid' conditioning of ViewCrafter is implemented")
         xc = torch.cat([x] + c_concat, dim=1)
-        cc = torch.cat(c_crossattn, 1)
+        # a single entry is passed through as the SAME tensor object: the U-Net keys its cross-attention K/V cache on it
+        cc = c_crossattn[0] if len(c_crossattn) == 1 else torch.cat(c_crossattn, 1)
         return self.diffusion_model(xc, t, context=cc, **kwargs)
 
 

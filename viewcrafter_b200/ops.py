@@ -57,17 +57,42 @@ def pack_linear(w: torch.Tensor) -> torch.Tensor:
     return w.reshape(w.shape[0], w.shape[1]).to(torch.float16).contiguous()
 
 
-def pack_geglu(w: torch.Tensor, b: torch.Tensor):
-    """GEGLU proj [2*inner, C]: interleave value/gate rows per N tile so the epilogue sees both (attention.py:415-422)."""
-    inner = w.shape[0] // 2
-    bn = _lib.load().vc_gemm_tile_n(2 * inner, 1)
+def _geglu_index(n2: int, device) -> torch.Tensor:
+    inner = n2 // 2
+    bn = _lib.load().vc_gemm_tile_n(n2, 1)
     half = bn // 2
     idx = []
-    for t in range(2 * inner // bn):
+    for t in range(n2 // bn):
         idx.extend(range(t * half, (t + 1) * half))
         idx.extend(range(inner + t * half, inner + (t + 1) * half))
-    idx = torch.tensor(idx, device=w.device)
+    return torch.tensor(idx, device=device)
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor):
+    """GEGLU proj [2*inner, C]: interleave value/gate rows per N tile so the epilogue sees both (attention.py:415-422)."""
+    idx = _geglu_index(w.shape[0], w.device)
     return w[idx].to(torch.float16).contiguous(), b[idx].float().contiguous()
+
+
+def fold_layernorm(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    """Fold ``LayerNorm(gamma, beta)`` into the linear layer that consumes it (attention.py:283-292: norm1/2/3 feed to_q/k/v
+    and the GEGLU projection and nothing else):  W (gamma*xhat + beta) + b  =  rstd * (W' x - mean * colsum(W')) + (W beta + b)
+    with W' = W * gamma.  Returns (W' fp16 [N,K], colsum fp32 [N] of the ROUNDED W', bias' fp32 [N]); pair with
+    ``linear(x_raw, W', bias=bias', ln=(layernorm_stats(x_raw), colsum))``."""
+    w32 = w.reshape(w.shape[0], -1).float()
+    w16 = (w32 * gamma.float()[None, :]).to(torch.float16).contiguous()
+    colsum = w16.float().sum(1).contiguous()
+    b2 = w32 @ beta.float()
+    if bias is not None:
+        b2 = b2 + bias.float()
+    return w16, colsum, b2.contiguous()
+
+
+def pack_geglu_ln(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """pack_geglu of a projection with the preceding LayerNorm folded in -> (w16, bias, colsum), rows interleaved per N tile."""
+    w16, cs, b2 = fold_layernorm(w, gamma, beta, b)
+    idx = _geglu_index(w.shape[0], w.device)
+    return w16[idx].contiguous(), b2[idx].contiguous(), cs[idx].contiguous()
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -79,8 +104,9 @@ def _gemm(desc: GemmDesc):
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
            geglu: bool = False, out: Optional[torch.Tensor] = None, out_f32: bool = False,
-           x2: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = [x|x2] @ w.T (+bias) (GEGLU) (+res).  x: [M,K1] fp16 (row pitch = x.stride(0)), w: [N,K] fp16."""
+           x2: Optional[torch.Tensor] = None, ln=None) -> torch.Tensor:
+    """y = [x|x2] @ w.T (+bias) (GEGLU) (+res).  x: [M,K1] fp16 (row pitch = x.stride(0)), w: [N,K] fp16.
+    ln = (stats [M,2] fp32 from layernorm_stats(x), colsum [N] fp32): LayerNorm folded into the epilogue (fold_layernorm)."""
     _chk16(x, "linear.x"); _chk16(w, "linear.w")
     M, K1 = x.shape
     N, K = w.shape
@@ -106,6 +132,11 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if res is not None:
         d.res, d.ldr = res.data_ptr(), res.stride(0)
     d.geglu = int(geglu)
+    if ln is not None:
+        stats, colsum = ln
+        assert stats.shape == (M, 2) and stats.dtype == torch.float32 and stats.is_contiguous()
+        assert colsum.shape == (N,) and colsum.dtype == torch.float32 and colsum.is_contiguous()
+        d.ln_stats, d.ln_colsum = stats.data_ptr(), colsum.data_ptr()
     _gemm(d)
     return out
 
@@ -271,6 +302,15 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     check(_lib.load().vc_layernorm(x.data_ptr(), x.shape[0], x.shape[1], gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(),
                                    _stream()), "vc_layernorm")
     return out
+
+
+def layernorm_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """[M,2] fp32 (mean, rstd) per row: the statistics half of LayerNorm (the consumer GEMM applies them, see fold_layernorm)."""
+    _chk16(x, "layernorm_stats.x")
+    assert x.is_contiguous()
+    stats = torch.empty((x.shape[0], 2), device=x.device, dtype=torch.float32)
+    check(_lib.load().vc_layernorm_stats(x.data_ptr(), x.shape[0], x.shape[1], eps, stats.data_ptr(), _stream()), "vc_layernorm_stats")
+    return stats
 
 
 def softmax_rows(x: torch.Tensor, scale: float) -> torch.Tensor:

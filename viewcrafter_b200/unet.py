@@ -15,6 +15,7 @@ libvc_b200.so on channels-last fp16 activations (``rows = (b t) h w``, columns =
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -27,6 +28,16 @@ def _zero(m: nn.Module) -> nn.Module:
     for p in m.parameters():
         nn.init.zeros_(p)
     return m
+
+
+_LN_FOLD = os.environ.get("VC_LN_FOLD", "1") != "0"   # fold norm1/2/3 into their consumer GEMMs (A/B switch, read at import)
+
+
+def _ln_linear(Q: dict, x: torch.Tensor, name: str, ln: str, **kw) -> torch.Tensor:
+    """LayerNorm -> Linear of a transformer block: folded (statistics pass + GEMM epilogue) or as two passes."""
+    if Q[name + "_cs"] is not None:
+        return ops.linear(x, Q[name], bias=Q[name + "_b"], ln=(ops.layernorm_stats(x), Q[name + "_cs"]), **kw)
+    return ops.linear(ops.layernorm(x, *Q[ln]), Q[name], bias=Q[name + "_b"], **kw)
 
 
 def _unsupported(flag: str):
@@ -203,6 +214,7 @@ class UNetModel(nn.Module):
         self.out = nn.Sequential(nn.GroupNorm(32, ch), nn.SiLU(), _zero(nn.Conv2d(mc, out_channels, 3, padding=1)))
 
         self._packed = None
+        self._kv_cache = {}         # cross-attention K/V projections of the current context (see _kv_projector)
         self._comm = None           # set by viewcrafter_b200.parallel.shard_model for frame-sharded multi-GPU execution
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
@@ -211,9 +223,11 @@ class UNetModel(nn.Module):
     # ------------------------------------------------------------------------------------------
     def invalidate_packed(self):
         self._packed = None
+        self._kv_cache = {}
 
     def _apply(self, fn, *a, **k):
         self._packed = None
+        self._kv_cache = {}
         return super()._apply(fn, *a, **k)
 
     @staticmethod
@@ -248,20 +262,32 @@ class UNetModel(nn.Module):
         blocks = []
         for b in m.transformer_blocks:
             Q = {}
-            for i, ln in enumerate((b.norm1, b.norm2, b.norm3), 1):
-                Q[f"ln{i}"] = (f(ln.weight), f(ln.bias))
+            # norm1/2/3 feed exactly one linear each (attention.py:283-292): fold them into it -- the GEMM reads the raw
+            # residual stream and its epilogue applies (mean, rstd); LayerNorm shrinks to a read-only statistics pass.
+            # VC_LN_FOLD=0 keeps the separate LayerNorm pass (A/B switch).
+            n1, n2, n3 = ((ln.weight.detach(), ln.bias.detach()) for ln in (b.norm1, b.norm2, b.norm3))
             a1, a2 = b.attn1, b.attn2
-            Q["qkv1"] = torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0).detach().to(torch.float16).contiguous()
+            cat = lambda *ws: torch.cat(ws, 0).detach()
+            if _LN_FOLD:
+                fold = ops.fold_layernorm
+            else:
+                fold = lambda w, g, bta: (ops.pack_linear(w), None, None)
+                Q["ln1"], Q["ln2"], Q["ln3"] = ((f(g), f(bta)) for g, bta in (n1, n2, n3))
+            Q["qkv1"], Q["qkv1_cs"], Q["qkv1_b"] = fold(cat(a1.to_q.weight, a1.to_k.weight, a1.to_v.weight), *n1)
             Q["o1_w"], Q["o1_b"] = ops.pack_linear(a1.to_out[0].weight.detach()), f(a1.to_out[0].bias)
             if m.kind == "T":
-                Q["qkv2"] = torch.cat([a2.to_q.weight, a2.to_k.weight, a2.to_v.weight], 0).detach().to(torch.float16).contiguous()
+                Q["qkv2"], Q["qkv2_cs"], Q["qkv2_b"] = fold(cat(a2.to_q.weight, a2.to_k.weight, a2.to_v.weight), *n2)
             else:
-                Q["q2"] = ops.pack_linear(a2.to_q.weight.detach())
+                Q["q2"], Q["q2_cs"], Q["q2_b"] = fold(a2.to_q.weight.detach(), *n2)
                 Q["kv_txt"] = torch.cat([a2.to_k.weight, a2.to_v.weight], 0).detach().to(torch.float16).contiguous()
                 if hasattr(a2, "to_k_ip"):
                     Q["kv_img"] = torch.cat([a2.to_k_ip.weight, a2.to_v_ip.weight], 0).detach().to(torch.float16).contiguous()
             Q["o2_w"], Q["o2_b"] = ops.pack_linear(a2.to_out[0].weight.detach()), f(a2.to_out[0].bias)
-            Q["ff1_w"], Q["ff1_b"] = ops.pack_geglu(b.ff.net[0].proj.weight.detach(), b.ff.net[0].proj.bias.detach())
+            if _LN_FOLD:
+                Q["ff1"], Q["ff1_b"], Q["ff1_cs"] = ops.pack_geglu_ln(b.ff.net[0].proj.weight.detach(), b.ff.net[0].proj.bias.detach(), *n3)
+            else:
+                Q["ff1"], Q["ff1_b"] = ops.pack_geglu(b.ff.net[0].proj.weight.detach(), b.ff.net[0].proj.bias.detach())
+                Q["ff1_cs"] = None
             Q["ff2_w"], Q["ff2_b"] = ops.pack_linear(b.ff.net[2].weight.detach()), f(b.ff.net[2].bias)
             blocks.append(Q)
         P["blocks"] = blocks
@@ -339,28 +365,35 @@ class UNetModel(nn.Module):
         return ops.groupnorm_apply(x, B, st, stat_rows, gamma, beta, eps, silu)
 
     @staticmethod
-    def _spatial_tf(P, h, ctx, B, T, H, W):
-        BT, HW, heads = B * T, H * W, P["heads"]
+    def _spatial_tf(P, h, ctx, B, T, H, W, expand=False):
+        """expand=True (shared CFG prefix): `h` holds ONE batch element that is identical for the B=2
+        conditional / unconditional branches; everything up to and including attn1 of the first block does not see the
+        context, so it runs once and is duplicated right before the first cross-attention."""
+        Bc = 1 if expand else B
+        BT, HW, heads = Bc * T, H * W, P["heads"]
         C = heads * 64
         x = ops.linear(ops.groupnorm(h, BT, *P["gn"], 1e-6, False), P["in_w"], bias=P["in_b"])
         for Q in P["blocks"]:
-            qkv = ops.linear(ops.layernorm(x, *Q["ln1"]), Q["qkv1"])
+            qkv = _ln_linear(Q, x, "qkv1", "ln1")
             a = ops.flash_attn(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], BT, HW, HW, heads)
             x = ops.linear(a, Q["o1_w"], bias=Q["o1_b"], res=x)
-            q = ops.linear(ops.layernorm(x, *Q["ln2"]), Q["q2"])
+            if expand:
+                x, h = torch.cat([x, x], 0), torch.cat([h, h], 0)
+                expand, Bc, BT = False, B, B * T
+            q = _ln_linear(Q, x, "q2", "ln2")
             a = torch.empty_like(q)
-            for b in range(B):
+            for b in range(Bc):
                 rows = slice(b * T * HW, (b + 1) * T * HW)
-                kv = ops.linear(ctx["text"][b], Q["kv_txt"])                            # [77, 2C]
+                kv = ctx["kv"](Q, "kv_txt", ctx["text"][b], b)                            # [77, 2C]
                 ops.flash_attn(q[rows], kv[:, :C], kv[:, C:], T, HW, kv.shape[0], heads, kv_shared=True, out=a[rows])
                 if "kv_img" in Q and ctx["img"] is not None:
-                    ki = ops.linear(ctx["img"][b], Q["kv_img"])                         # [256, 2C] or [T*16, 2C]
+                    ki = ctx["kv"](Q, "kv_img", ctx["img"][b], b)                         # [256, 2C] or [T*16, 2C]
                     if ctx["img_per_frame"]:
                         ops.flash_attn(q[rows], ki[:, :C], ki[:, C:], T, HW, ki.shape[0] // T, heads, out=a[rows], accumulate=True)
                     else:
                         ops.flash_attn(q[rows], ki[:, :C], ki[:, C:], T, HW, ki.shape[0], heads, kv_shared=True, out=a[rows], accumulate=True)
             x = ops.linear(a, Q["o2_w"], bias=Q["o2_b"], res=x)
-            g = ops.linear(ops.layernorm(x, *Q["ln3"]), Q["ff1_w"], bias=Q["ff1_b"], geglu=True)
+            g = _ln_linear(Q, x, "ff1", "ln3", geglu=True)
             x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x)
         return ops.linear(x, P["out_w"], bias=P["out_b"], res=h)
 
@@ -373,13 +406,13 @@ class UNetModel(nn.Module):
         x = ops.linear(UNetModel._gn5d(t_in, B, *P["gn"], 1e-6, False, comm, Tg * HW), P["in_w"], bias=P["in_b"])
         for Q in P["blocks"]:
             for ln, wqkv, ow, ob in (("ln1", "qkv1", "o1_w", "o1_b"), ("ln2", "qkv2", "o2_w", "o2_b")):
-                qkv = ops.linear(ops.layernorm(x, *Q[ln]), Q[wqkv])
+                qkv = _ln_linear(Q, x, wqkv, ln)
                 a = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=torch.float16)
                 for b in range(B):
                     rows = slice(b * Tg * HWl, (b + 1) * Tg * HWl)
                     ops.temporal_attn(qkv[rows, :C], qkv[rows, C:2 * C], qkv[rows, 2 * C:], Tg, HWl, heads, out=a[rows])
                 x = ops.linear(a, Q[ow], bias=Q[ob], res=x)
-            g = ops.linear(ops.layernorm(x, *Q["ln3"]), Q["ff1_w"], bias=Q["ff1_b"], geglu=True)
+            g = _ln_linear(Q, x, "ff1", "ln3", geglu=True)
             x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x)
         out = ops.linear(x, P["out_w"], bias=P["out_b"], res=t_in)
         return comm.to_frames(out, B, HW) if comm else out
@@ -404,6 +437,23 @@ class UNetModel(nn.Module):
                 h = ops.conv3x3(h, B * T, H, W, P["w"], bias=P["b"])
         return h, H, W
 
+    def _kv_projector(self, context: torch.Tensor, img_range):
+        """to_k / to_v (and to_k_ip / to_v_ip) of the cross-attentions see only the context, which a sampling run feeds
+        unchanged for all its steps: project once per (context tensor, version) and reuse.  The cache
+        holds one context (a few MB of fp16) and is dropped as soon as a different tensor arrives."""
+        cache = self._kv_cache
+        # keyed on the tensor OBJECT (kept alive by the cache, so its storage cannot be recycled under the key) + its version
+        # counter (bumped by any in-place write)
+        if cache.get("ref") is not context or cache.get("ver") != context._version or cache.get("rng") != img_range:
+            self._kv_cache = cache = {"ref": context, "ver": context._version, "rng": img_range}
+
+        def project(Q, name, tokens, b):
+            k = (id(Q), name, b)
+            if k not in cache:
+                cache[k] = ops.linear(tokens, Q[name])
+            return cache[k]
+        return project
+
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x, timesteps, context=None, features_adapter=None, fs=None, **kwargs):
@@ -420,6 +470,10 @@ class UNetModel(nn.Module):
         B, Cin, T, H, W = x.shape
         dev = x.device
         x32 = x.float().contiguous()
+        # cfg_shared_prefix: the caller (DDIMSampler._apply_both) asserts that batch rows 0 and 1 carry the same x, t, fs
+        # and c_concat and differ only in the cross-attention context
+        kinds = [Pm["kind"] for Pm in P["input"][1]] if len(P["input"]) > 1 else []
+        shared = bool(kwargs.get("cfg_shared_prefix")) and B == 2 and comm is None and kinds[:2] == ["R", "S"]
         # --- embeddings (fp32) : time_embed(t) + fps_embedding(fs), one row per batch element (frame-invariant) ---
         ts = timesteps.to(device=dev, dtype=torch.int64).contiguous()
         tw = P["time"]
@@ -436,7 +490,7 @@ class UNetModel(nn.Module):
         per_frame = (L == 77 + T_all * 16)
         img_lo, img_hi = (77 + 16 * f0, 77 + 16 * f1) if (comm and per_frame) else (77, L)
         ctx = dict(text=[ctx16[b, :77] for b in range(B)], img=[ctx16[b, img_lo:img_hi] for b in range(B)] if L > 77 else None,
-                   img_per_frame=per_frame)
+                   img_per_frame=per_frame, kv=self._kv_projector(context, (img_lo, img_hi)))
         # --- input latent -> rows [(b t) h w, Cin padded to 8] ---
         cin_pad = max(8, (Cin + 7) // 8 * 8)
         h = torch.zeros((B * T * H * W, cin_pad), device=dev, dtype=torch.float16) if cin_pad != Cin else \
@@ -444,7 +498,31 @@ class UNetModel(nn.Module):
         ops.ncthw_to_rows(x32, h, 0)
 
         hs = []
+        first = 0
+        if shared:
+            # both CFG branches see the same x, t, fs and c_concat, so everything before the first
+            # cross-attention (input_blocks.0, init_attn, input_blocks.1.0 and input_blocks.1.1 up to attn1) is computed once
+            # on one batch element and duplicated; the results are those of the plain B=2 forward.
+            emb1 = emb[:1].contiguous()
+            h = h[:T * H * W]
+            h, H, W = self._run_stage(P["input"][0], h, None, emb1, ctx, 1, T, H, W)
+            if self.addition_attention:
+                h, H, W = self._run_stage(P["init_attn"], h, None, emb1, ctx, 1, T, H, W)
+            hs.append(torch.cat([h, h], 0))
+            Bc = 1
+            for Pm in P["input"][1]:
+                if Bc == 1 and Pm["kind"] == "R":
+                    h = self._res(Pm, h, None, emb1, 1, T, H, W, None)
+                elif Bc == 1 and Pm["kind"] == "S":
+                    h = self._spatial_tf(Pm, h, ctx, B, T, H, W, expand=True)
+                    Bc = B
+                else:
+                    h, H, W = self._run_stage([Pm], h, None, emb, ctx, B, T, H, W)
+            hs.append(h)
+            first = 2
         for i, stage in enumerate(P["input"]):
+            if i < first:
+                continue
             h, H, W = self._run_stage(stage, h, None, emb, ctx, B, T, H, W)
             if i == 0 and self.addition_attention:
                 h, H, W = self._run_stage(P["init_attn"], h, None, emb, ctx, B, T, H, W)
