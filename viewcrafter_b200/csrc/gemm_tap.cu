@@ -245,10 +245,12 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.Z;
   // CTA pairs pay off once every SM pair has several 256-row tiles; N must be covered by whole BN tiles so that each
   // CTA's half of the B tile (BN/2 rows) never straddles a tap boundary
-  // Measured on B200 (profiles/README.md): pairs win 10-15 % once the reduction is long (>= 10 k-blocks of 64), but lose
-  // on the short-K (K = 320 / 512) level-0 linears, which are epilogue / HBM bound and prefer 148 independent CTAs.
+  // Measured on B200 (profiles/README.md): pairs win 10-15 % on long reductions; since the role loops were slimmed down they
+  // also win 4-13 % on the short-K (K = 320 / 512, 5-8 k-blocks) level-0 linears (they lost there before).
   const int k_iters = d.num_taps * ((d.K + BK - 1) / BK);
-  const bool use_pair = pair_mode() && (BN == 128 || BN == 160 || BN == 256) && d.N % BN == 0 && k_iters >= 10 &&
+  static int pair_min_k = -1;                  // tuning switch VC_GEMM_PAIR_MINK: shortest reduction (in 64-wide k-blocks) routed to CTA pairs
+  if (pair_min_k < 0) { const char* e = getenv("VC_GEMM_PAIR_MINK"); pair_min_k = e ? atoi(e) : 5; }
+  const bool use_pair = pair_mode() && (BN == 128 || BN == 160 || BN == 256) && d.N % BN == 0 && k_iters >= pair_min_k &&
                         (m_tiles / 2) * p.n_tiles >= sm_count();
 
   // A: (K, X, Y, Z) with row pitch lda

@@ -33,7 +33,8 @@ struct Gemm2Cfg {
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - EPI_SMEM_BYTES;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024 + 512;
-  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  static constexpr int NACC = (512 / BN) > 4 ? 4 : (512 / BN);   // TMEM accumulators: as many as fit the 512 columns (short-K tiles outrun two)
+  static constexpr int TMEM_COLS = NACC * BN <= 32 ? 32 : NACC * BN <= 64 ? 64 : NACC * BN <= 128 ? 128 : NACC * BN <= 256 ? 256 : 512;
   static_assert(BN % 32 == 0 && (BN / 2) % 8 == 0, "B half must be whole 8-row swizzle groups");
   static_assert(B_BYTES % 1024 == 0, "B half must keep 1024-byte alignment of the next stage");
 };
@@ -84,9 +85,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;          // per-warp staging tiles of the TMA-store epilogue
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + EPI_SMEM_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]  (only the leader's copy is waited on)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [NACC]
+  uint64_t* tmem_empty_bar = tmem_full_bar + Cfg::NACC;   // [NACC]  (only the leader's copy is waited on)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + Cfg::NACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,7 +105,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < Cfg::NACC; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 2 * EPI_WARPS);          // one arrival per epilogue warp of both CTAs
     }
@@ -191,14 +192,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
         }
         if (elect_one()) umma2_commit_mc(&tmem_full_bar[acc]);
         __syncwarp();
-        acc ^= 1;
-        if (acc == 0) aph ^= 1;
+        if (++acc == Cfg::NACC) { acc = 0; aph ^= 1; }
       }
     }
   } else {
     // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
     // the leader's tmem_empty barrier counts the epilogue warps of both CTAs
-    gemm_epilogue_loop<BN, 2, true>(p, cluster_id, nclusters, 2, (int)rank, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane);
+    gemm_epilogue_loop<BN, Cfg::NACC, true>(p, cluster_id, nclusters, 2, (int)rank, tmem_base, tmem_full_bar, tmem_empty_bar, epi_smem, warp, lane);
   }
 
   tc_fence_before();
