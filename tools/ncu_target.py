@@ -20,7 +20,16 @@ if which in ("norm", "all"):
     g, be = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
     for _ in range(3):
         ops.groupnorm(x, T, g, be, 1e-5, True)
-        ops.layernorm(x, g, be)
+        ops.layernorm_stats(x)
+if which in ("lin", "all"):
+    # level-0 transformer linears with the LayerNorm folded into the epilogue: qkv (320->960) and GEGLU (320->2560)
+    g32, b32 = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    wq, csq, bq = ops.fold_layernorm(torch.randn(3 * C, C, device="cuda") * 0.05, g32, b32)
+    wg, bg, csg = ops.pack_geglu_ln(torch.randn(8 * C, C, device="cuda") * 0.05, torch.zeros(8 * C, device="cuda"), g32, b32)
+    st = ops.layernorm_stats(x)
+    for _ in range(3):
+        ops.linear(x, wq, bias=bq, ln=(st, csq))
+        ops.linear(x, wg, bias=bg, geglu=True, ln=(st, csg))
 if which in ("tattn", "all"):
     qkv = (torch.randn(M, 3 * C, device="cuda") * 0.5).half()
     for _ in range(3):

@@ -214,7 +214,8 @@ class UNetModel(nn.Module):
         self.out = nn.Sequential(nn.GroupNorm(32, ch), nn.SiLU(), _zero(nn.Conv2d(mc, out_channels, 3, padding=1)))
 
         self._packed = None
-        self._kv_cache = {}         # cross-attention K/V projections of the current context (see _kv_projector)
+        self._kv_caches = []        # cross-attention K/V projections of the last two contexts (see _kv_projector)
+        self._kv_cache = {}
         self._comm = None           # set by viewcrafter_b200.parallel.shard_model for frame-sharded multi-GPU execution
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
@@ -223,11 +224,11 @@ class UNetModel(nn.Module):
     # ------------------------------------------------------------------------------------------
     def invalidate_packed(self):
         self._packed = None
-        self._kv_cache = {}
+        self._kv_caches, self._kv_cache = [], {}
 
     def _apply(self, fn, *a, **k):
         self._packed = None
-        self._kv_cache = {}
+        self._kv_caches, self._kv_cache = [], {}
         return super()._apply(fn, *a, **k)
 
     @staticmethod
@@ -440,12 +441,20 @@ class UNetModel(nn.Module):
     def _kv_projector(self, context: torch.Tensor, img_range):
         """to_k / to_v (and to_k_ip / to_v_ip) of the cross-attentions see only the context, which a sampling run feeds
         unchanged for all its steps: project once per (context tensor, version) and reuse.  The cache
-        holds one context (a few MB of fp16) and is dropped as soon as a different tensor arrives."""
-        cache = self._kv_cache
+        holds the last two contexts (a few MB of fp16 each)."""
         # keyed on the tensor OBJECT (kept alive by the cache, so its storage cannot be recycled under the key) + its version
-        # counter (bumped by any in-place write)
-        if cache.get("ref") is not context or cache.get("ver") != context._version or cache.get("rng") != img_range:
-            self._kv_cache = cache = {"ref": context, "ver": context._version, "rng": img_range}
+        # counter (bumped by any in-place write).  Two entries: an unbatched sampler alternates cond / uncond contexts.
+        cache = None
+        for cnd in self._kv_caches:
+            if cnd["ref"] is context and cnd["ver"] == context._version and cnd["rng"] == img_range:
+                cache = cnd
+                break
+        if cache is None:
+            cache = {"ref": context, "ver": context._version, "rng": img_range}
+            self._kv_caches = [cache] + [cnd for cnd in self._kv_caches if cnd["ref"] is not context][:1]
+        else:
+            self._kv_caches = [cache] + [cnd for cnd in self._kv_caches if cnd is not cache][:1]
+        self._kv_cache = cache                     # most recent entry (introspection / tests)
 
         def project(Q, name, tokens, b):
             k = (id(Q), name, b)
