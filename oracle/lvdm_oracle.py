@@ -350,6 +350,49 @@ def vae_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
     return F.conv2d(h, sd[d + ".conv_out.weight"], sd[d + ".conv_out.bias"], padding=1)
 
 
+def vae_encode_moments(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """AutoencoderKL.encode up to the moments (autoencoder.py:97-100) -> Encoder.forward (ae_modules.py:430-463);
+    Downsample = zero-pad right/bottom by one, then 3x3 stride-2 conv without padding (ae_modules.py:102-106).
+    sd keys are relative to the autoencoder ("encoder.*", "quant_conv.*").  Returns [N, 2*embed_dim, h, w]."""
+    e = "encoder"
+    h = F.conv2d(x, sd[e + ".conv_in.weight"], sd[e + ".conv_in.bias"], padding=1)
+    lvl = 0
+    while f"{e}.down.{lvl}.block.0.norm1.weight" in sd:
+        b = 0
+        while f"{e}.down.{lvl}.block.{b}.norm1.weight" in sd:
+            h = vae_resnet_block(sd, f"{e}.down.{lvl}.block.{b}", h)
+            if f"{e}.down.{lvl}.attn.{b}.norm.weight" in sd:
+                h = vae_attn_block(sd, f"{e}.down.{lvl}.attn.{b}", h)
+            b += 1
+        if f"{e}.down.{lvl}.downsample.conv.weight" in sd:
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
+            h = F.conv2d(h, sd[f"{e}.down.{lvl}.downsample.conv.weight"], sd[f"{e}.down.{lvl}.downsample.conv.bias"], stride=2)
+        lvl += 1
+    h = vae_resnet_block(sd, e + ".mid.block_1", h)
+    h = vae_attn_block(sd, e + ".mid.attn_1", h)
+    h = vae_resnet_block(sd, e + ".mid.block_2", h)
+    h = _swish(_gn(h, sd, e + ".norm_out", 1e-6))
+    h = F.conv2d(h, sd[e + ".conv_out.weight"], sd[e + ".conv_out.bias"], padding=1)
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+def posterior_sample(moments: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """DiagonalGaussianDistribution.__init__ + sample (distributions.py:24-40): logvar clamped to [-30, 20]."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    return mean + torch.exp(0.5 * logvar) * noise
+
+
+def encode_first_stage(sd: SD, x5: torch.Tensor, noises: List[torch.Tensor], scale_factor: float = 0.18215) -> torch.Tensor:
+    """LatentDiffusion.encode_first_stage with perframe_ae + get_first_stage_encoding (ddpm3d.py:611-644): one posterior
+    sample per frame (noises[i] is the randn the i-th frame's DiagonalGaussianDistribution.sample draws), times scale_factor."""
+    B, C, T, H, W = x5.shape
+    x = x5.permute(0, 2, 1, 3, 4).reshape(B * T, C, H, W)
+    outs = [scale_factor * posterior_sample(vae_encode_moments(sd, x[i:i + 1]), noises[i]) for i in range(x.shape[0])]
+    r = torch.cat(outs, dim=0)
+    return r.reshape(B, T, r.shape[1], r.shape[2], r.shape[3]).permute(0, 2, 1, 3, 4)
+
+
 def decode_first_stage(sd: SD, z5: torch.Tensor, scale_factor: float = 0.18215) -> torch.Tensor:
     """LatentDiffusion.decode_core with perframe_ae, ddpm3d.py:646-667."""
     B, C, T, H, W = z5.shape

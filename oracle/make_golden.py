@@ -153,9 +153,26 @@ def gen_vae():
     print("vae out std", float(y.std()))
 
 
+def gen_vae_enc():
+    """Encoder + quant_conv + DiagonalGaussianDistribution.sample of the unmodified reference (autoencoder.py:97-102)."""
+    enc, qc = ref_shims.build_encoder(ch=32)
+    from lvdm.distributions import DiagonalGaussianDistribution
+    shapes_e = _load_synth(enc, seed=14)
+    qc.load_state_dict(synth.synth_state_dict(synth.module_shapes(qc), 14))
+    g = torch.Generator().manual_seed(16)
+    x = torch.rand(2, 3, 32, 48, generator=g) * 2 - 1
+    noise = torch.randn(2, 4, 4, 6, generator=g)
+    with torch.no_grad():
+        moments = qc(enc(x))
+        z = DiagonalGaussianDistribution(moments).sample(noise=noise)
+    np.savez_compressed(os.path.join(OUT, "vae_enc_ch32.npz"), shapes=shapes_e, x=x.numpy(), moments=moments.numpy(),
+                        noise=noise.numpy(), z=z.numpy())
+    print("vae enc moments std", float(moments.std()), "z std", float(z.std()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["schedule", "ddim", "unet", "vae"]
+    which = sys.argv[1:] or ["schedule", "ddim", "unet", "vae", "vae_enc"]
     with torch.no_grad():
         for w in which:
             globals()["gen_" + w]()

@@ -83,6 +83,17 @@ def build_unet(seed=0, **over):
     return m
 
 
+def build_encoder(seed=0, **over):
+    """Returns (encoder, quant_conv) as the reference AutoencoderKL builds them (autoencoder.py:28-32)."""
+    install()
+    from lvdm.modules.networks.ae_modules import Encoder
+    dd = dict(VAE_DD); dd.update(over)
+    torch.manual_seed(seed)
+    enc = Encoder(**dd).eval()
+    qc = torch.nn.Conv2d(2 * dd["z_channels"], 2 * 4, 1)
+    return enc, qc
+
+
 def build_decoder(seed=0, **over):
     """Returns (decoder, post_quant_conv) as the reference AutoencoderKL builds them (autoencoder.py:28-33)."""
     install()

@@ -198,10 +198,12 @@ def upsample2x(x, N, H, W):
     return _h(_nchw_to_rows(F.interpolate(_rows_to_nchw(x, N, H, W), scale_factor=2, mode="nearest")))
 
 
-def im2col_s2(x, N, H, W, pad_lo=1):
+def im2col_s2(x, N, H, W, pad_lo=1, pad_hi=None):
     Cc = x.shape[1]
-    Ho, Wo = (H + 2 * pad_lo - 3) // 2 + 1, (W + 2 * pad_lo - 3) // 2 + 1
-    cols = F.unfold(_rows_to_nchw(x, N, H, W), 3, padding=pad_lo, stride=2)           # [N, C*9, L]: channel-major, tap-minor
+    pad_hi = pad_lo if pad_hi is None else pad_hi
+    Ho, Wo = (H + pad_lo + pad_hi - 3) // 2 + 1, (W + pad_lo + pad_hi - 3) // 2 + 1
+    img = F.pad(_rows_to_nchw(x, N, H, W), (pad_lo, pad_hi, pad_lo, pad_hi))
+    cols = F.unfold(img, 3, padding=0, stride=2)                                       # [N, C*9, L]: channel-major, tap-minor
     cols = cols.reshape(N, Cc, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(N * Ho * Wo, 9 * Cc)
     return _h(cols), Ho, Wo
 

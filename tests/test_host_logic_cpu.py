@@ -145,3 +145,41 @@ def test_shared_cfg_prefix_and_kv_cache(cpu_ops):
     ctx2[1] = ctx[1]                                                  # in-place write bumps the version counter
     out3 = m(x, t, context=ctx2, fs=fs)
     assert float((out3 - plain).abs().max()) < 0.02
+
+
+def test_vae_encode_host_logic_vs_reference_golden(cpu_ops, golden_dir):
+    """AutoencoderKL.encode (Encoder + folded conv_out/quant_conv + DiagonalGaussianDistribution) on the CPU op double vs the
+    moments / posterior sample produced by the unmodified reference (tests/golden/vae_enc_ch32.npz)."""
+    from viewcrafter_b200.autoencoder import AutoencoderKL
+    g = np.load(os.path.join(golden_dir, "vae_enc_ch32.npz"))
+    vae = AutoencoderKL(dict(VAE_DDCONFIG, ch=32), None, 4).eval()
+    shapes = [(n, tuple(s)) for n, s in json.loads(str(g["shapes"]))]
+    sd = {"encoder." + k: v for k, v in synth.synth_state_dict(shapes, seed=14).items()}
+    sd.update({"quant_conv." + k: v for k, v in synth.synth_state_dict([("weight", (8, 8, 1, 1)), ("bias", (8,))], 14).items()})
+    missing, unexpected = vae.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("decoder.", "post_quant_conv.")) for k in missing)
+    post = vae.encode(torch.from_numpy(g["x"]))
+    err = (post.parameters - torch.from_numpy(g["moments"])).abs()
+    assert post.parameters.shape == g["moments"].shape and float(err.max()) < 0.03, float(err.max())
+    z = post.sample(noise=torch.from_numpy(g["noise"]))
+    assert float((z - torch.from_numpy(g["z"])).abs().max()) < 0.05
+    assert torch.equal(post.mode(), post.mean) and post.logvar.min() >= -30.0 and post.logvar.max() <= 20.0
+
+
+def test_encode_first_stage_perframe_rng_order(cpu_ops):
+    """LatentDiffusion.encode_first_stage: per-frame encodes, each drawing its posterior noise from the CPU generator in frame
+    order (ddpm3d.py:633-639, distributions.py:35-36), scaled by scale_factor; checked against the oracle fed the same draws."""
+    from viewcrafter_b200.diffusion import LatentDiffusion
+    model = LatentDiffusion(dict(UNET_PARAMS, model_channels=64), dict(ddconfig=dict(VAE_DDCONFIG, ch=32), embed_dim=4)).eval()
+    sdv = synth.synth_state_dict(synth.module_shapes(model.first_stage_model), seed=45)
+    model.first_stage_model.load_state_dict(sdv, strict=True)
+    g = torch.Generator().manual_seed(46)
+    x = torch.rand(1, 3, 3, 16, 24, generator=g) * 2 - 1
+    torch.manual_seed(47)
+    z = model.encode_first_stage(x)
+    torch.manual_seed(47)
+    noises = [torch.randn(1, 4, 2, 3) for _ in range(3)]
+    with torch.no_grad():
+        ref = O.encode_first_stage(sdv, x, noises)
+    assert z.shape == (1, 4, 3, 2, 3)
+    assert float((z - ref).abs().max()) < 0.02, float((z - ref).abs().max())

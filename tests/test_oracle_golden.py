@@ -93,3 +93,22 @@ def test_vae_decoder_matches_reference(golden_dir):
     with torch.no_grad():
         y = O.vae_decode(sd, torch.from_numpy(g["z"]))
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=5e-5)
+
+
+def _enc_sd(g):
+    shapes = [(n, tuple(s)) for n, s in json.loads(str(g["shapes"]))]
+    sd = {"encoder." + k: v for k, v in synth.synth_state_dict(shapes, seed=14).items()}
+    sd.update({"quant_conv." + k: v for k, v in synth.synth_state_dict([("weight", (8, 8, 1, 1)), ("bias", (8,))], 14).items()})
+    return sd
+
+
+def test_vae_encoder_matches_reference(golden_dir):
+    """Encoder + quant_conv moments and the posterior sample of the unmodified reference (autoencoder.py:97-102,
+    distributions.py:24-40)."""
+    g = _load(golden_dir, "vae_enc_ch32.npz")
+    sd = _enc_sd(g)
+    with torch.no_grad():
+        m = O.vae_encode_moments(sd, torch.from_numpy(g["x"]))
+        z = O.posterior_sample(m, torch.from_numpy(g["noise"]))
+    np.testing.assert_allclose(m.numpy(), g["moments"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(z.numpy(), g["z"], rtol=0, atol=5e-5)

@@ -63,6 +63,55 @@ def test_vae_decode_full_width_vs_oracle():
     assert float(err.max()) <= 0.03 * max(1.0, float(ref.std())) and float(err.mean()) <= 0.003 * max(1.0, float(ref.std()))
 
 
+def test_vae_encode_matches_reference_golden(golden_dir):
+    """AutoencoderKL.encode on the GPU kernels vs the moments / posterior sample of the unmodified reference."""
+    _need_gpu()
+    from oracle import synth
+    from viewcrafter_b200.autoencoder import AutoencoderKL
+    from viewcrafter_b200.configs import VAE_DDCONFIG
+    g = np.load(os.path.join(golden_dir, "vae_enc_ch32.npz"))
+    vae = AutoencoderKL(dict(VAE_DDCONFIG, ch=32), None, 4)
+    shapes = [(n, tuple(s)) for n, s in json.loads(str(g["shapes"]))]
+    sd = {"encoder." + k: v for k, v in synth.synth_state_dict(shapes, seed=14).items()}
+    sd.update({"quant_conv." + k: v for k, v in synth.synth_state_dict([("weight", (8, 8, 1, 1)), ("bias", (8,))], 14).items()})
+    missing, unexpected = vae.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("decoder.", "post_quant_conv.")) for k in missing)
+    vae = vae.cuda().eval()
+    post = vae.encode(torch.from_numpy(g["x"]).cuda())
+    err = (post.parameters.cpu() - torch.from_numpy(g["moments"])).abs()
+    print(f"vae enc ch32: max err {float(err.max()):.4g} mean {float(err.mean()):.4g} ref std {float(g['moments'].std()):.3g}")
+    assert post.parameters.shape == g["moments"].shape and post.parameters.dtype == torch.float32
+    assert float(err.max()) <= 0.03 and float(err.mean()) <= 0.003
+    z = post.sample(noise=torch.from_numpy(g["noise"]))
+    assert float((z.cpu() - torch.from_numpy(g["z"])).abs().max()) <= 0.05
+
+
+def test_vae_encode_full_width_vs_oracle():
+    """ch=128 encoder (128/256/512/512 channel levels, stride-2 downsamples with right/bottom zero pad, d=512 attention) on
+    two 64x96 frames; also an odd multiple of 8 in width."""
+    _need_gpu()
+    from oracle import lvdm_oracle as O
+    from oracle import synth
+    from viewcrafter_b200.autoencoder import AutoencoderKL
+    from viewcrafter_b200.configs import VAE_DDCONFIG
+    vae = AutoencoderKL(VAE_DDCONFIG, None, 4)
+    sd = synth.synth_state_dict(synth.module_shapes(vae), seed=33)
+    vae.load_state_dict(sd, strict=True)
+    vae = vae.cuda().eval()
+    torch.set_num_threads(os.cpu_count() or 1)
+    for shape, seed in (((2, 3, 64, 96), 34), ((1, 3, 40, 72), 35)):
+        x = torch.rand(*shape, generator=torch.Generator().manual_seed(seed)) * 2 - 1
+        with torch.no_grad():
+            ref = O.vae_encode_moments(sd, x)
+        m = vae.encode(x.cuda()).parameters
+        err = (m.cpu() - ref).abs()
+        print(f"vae enc ch128 {shape}: max err {float(err.max()):.4g} mean {float(err.mean()):.4g} ref std {float(ref.std()):.3g}")
+        assert m.shape == ref.shape
+        assert float(err.max()) <= 0.03 * max(1.0, float(ref.std())) and float(err.mean()) <= 0.003 * max(1.0, float(ref.std()))
+    with pytest.raises(ValueError):
+        vae.encode(torch.zeros(1, 3, 36, 64, device="cuda"))
+
+
 @pytest.mark.parametrize("batch_cfg", [False, True])
 def test_ddim_sample_three_steps_vs_oracle(batch_cfg):
     """DDIMSampler.sample (S=3, eta=1, CFG 7.5, rescale 0.7) with identical x_T and per-step noise on both sides."""

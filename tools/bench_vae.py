@@ -22,7 +22,10 @@ def timed(fn, reps=2):
     return e0.elapsed_time(e1) / reps * 1e-3
 
 
+x = torch.rand(25, 3, 576, 1024, device="cuda") * 2 - 1
 with torch.no_grad():
+    te = timed(lambda: [vae.encode(x[i:i + 1]) for i in range(25)])
+    print(f"per-frame encode (25 calls): {te * 1e3:.1f} ms = {25 / te:.1f} frames/s  ({2.6 * 25 / te:.0f} TFLOP/s at ~2.6 TFLOP/frame)")
     t1 = timed(lambda: [vae.decode(z[i:i + 1]) for i in range(25)])
     print(f"per-frame decode (25 calls): {t1 * 1e3:.1f} ms = {25 / t1:.1f} frames/s  ({5.754 * 25 / t1:.0f} TFLOP/s at 5.754 TFLOP/frame)")
     for nb in (5, 25):

@@ -4,7 +4,9 @@
 (GroupNorm+swish kernel, 9-tap tcgen05 GEMMs, 1x1 nin_shortcut fused as residual), the single-head d=512 AttnBlock
 (QK^T and PV as tcgen05 GEMMs around a row-softmax kernel), nearest-2x upsample + conv, GroupNorm+swish, conv_out.
 State-dict keys match the reference (``post_quant_conv.*``, ``decoder.*``, ``encoder.*``, ``quant_conv.*``).
-``encode`` (conditioning-side, run once per clip) is the next tier and raises for now.
+``encode(x)`` (conditioning renders, once per clip) runs the Encoder on the same kernels: the stride-2
+Downsample (zero-pad right/bottom, ae_modules.py:102-106) is an im2col + GEMM, and conv_out is folded with the 1x1 quant_conv;
+it returns the reference's ``DiagonalGaussianDistribution`` over fp32 moments.
 """
 from __future__ import annotations
 
@@ -12,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .distributions import DiagonalGaussianDistribution
 
 
 def _gn(c):
@@ -123,6 +126,7 @@ class AutoencoderKL(nn.Module):
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self.embed_dim, self.input_dim = embed_dim, input_dim
         self._packed = None
+        self._packed_enc = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
         if ckpt_path is not None:
             sd = torch.load(ckpt_path, map_location="cpu")
@@ -130,9 +134,11 @@ class AutoencoderKL(nn.Module):
 
     def invalidate_packed(self):
         self._packed = None
+        self._packed_enc = None
 
     def _apply(self, fn, *a, **k):
         self._packed = None
+        self._packed_enc = None
         return super()._apply(fn, *a, **k)
 
     @property
@@ -232,9 +238,60 @@ class AutoencoderKL(nn.Module):
         oc = y.shape[1]
         return ops.rows_to_ncthw(y, N, oc, 1, H, W).reshape(N, oc, H, W).to(z.dtype)
 
-    def encode(self, x, **kwargs):
-        raise NotImplementedError("viewcrafter_b200.AutoencoderKL.encode: conditioning-side VAE encode is the next tier "
-                                  "(SURVEY.md 8f f1); use the reference encoder for c_concat")
+    # ------------------------------------------------------------------------------------------
+    def _pack_encoder(self):
+        ops.require_cuda(self.device, "viewcrafter_b200.AutoencoderKL.encode")
+        f = self._f32
+        e = self.encoder
+        P = dict(in_w=ops.pack_conv3x3(e.conv_in.weight.detach(), k_pad=8), in_b=f(e.conv_in.bias),
+                 mid1=self._pack_res(e.mid.block_1), attn=self._pack_attn(e.mid.attn_1), mid2=self._pack_res(e.mid.block_2))
+        downs = []
+        for stage in e.down:
+            S = dict(blocks=[self._pack_res(b) for b in stage.block], attns=[self._pack_attn(a) for a in stage.attn])
+            if hasattr(stage, "downsample"):
+                w = stage.downsample.conv.weight.detach()                                  # [C, C, 3, 3] -> [C, 9*C] tap-major
+                S["down_w"] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.float16).contiguous()
+                S["down_b"] = f(stage.downsample.conv.bias)
+            downs.append(S)
+        P["down"] = downs
+        P["out_gn"] = (f(e.norm_out.weight), f(e.norm_out.bias))
+        # conv_out (3x3, C -> 2z) followed by the 1x1 quant_conv (2z -> 2*embed) is one 3x3 conv with the combined weights
+        # W[o] = sum_m Wq[o, m] * Wc[m],  b = Wq bc + bq   (autoencoder.py:99-100): one GEMM, one rounding of the weights
+        wq = self.quant_conv.weight.detach().float().reshape(self.quant_conv.weight.shape[0], -1)      # [2e, 2z]
+        wc = e.conv_out.weight.detach().float()                                                         # [2z, C, 3, 3]
+        w = torch.einsum("om,mchw->ochw", wq, wc)
+        P["out_w"] = ops.pack_conv3x3(w)
+        P["out_b"] = (wq @ e.conv_out.bias.detach().float() + self.quant_conv.bias.detach().float()).contiguous()
+        self._packed_enc = P
+        return P
 
-    def forward(self, input, sample_posterior=True):
-        raise NotImplementedError("training forward is out of scope")
+    @torch.no_grad()
+    def encode_moments(self, x):
+        """x [N, in_channels, H, W] (H, W multiples of 2^(levels-1)) -> fp32 moments [N, 2*embed_dim, H/8, W/8]
+        (autoencoder.py:97-100, ae_modules.py:430-463)."""
+        P = self._packed_enc or self._pack_encoder()
+        N, Cin, H, W = x.shape
+        nd = len(P["down"]) - 1
+        if H % (1 << nd) or W % (1 << nd):
+            raise ValueError(f"AutoencoderKL.encode: H, W must be multiples of {1 << nd}, got {H}x{W}")
+        rows = torch.zeros((N * H * W, 8), device=x.device, dtype=torch.float16)
+        ops.ncthw_to_rows(x.float().contiguous().reshape(N, Cin, 1, H, W), rows, 0)
+        h = ops.conv3x3(rows, N, H, W, P["in_w"], bias=P["in_b"])
+        for S in P["down"]:
+            for i, B in enumerate(S["blocks"]):
+                h = self._res(B, h, N, H, W)
+                if S["attns"]:
+                    h = self._attn(S["attns"][i], h, N, H, W)
+            if "down_w" in S:
+                cols, H, W = ops.im2col_s2(h, N, H, W, pad_lo=0, pad_hi=1)
+                h = ops.linear(cols, S["down_w"], bias=S["down_b"])
+        h = self._res(P["mid1"], h, N, H, W)
+        h = self._attn(P["attn"], h, N, H, W)
+        h = self._res(P["mid2"], h, N, H, W)
+        y = ops.conv3x3(ops.groupnorm(h, N, *P["out_gn"], 1e-6, True), N, H, W, P["out_w"], bias=P["out_b"], out_f32=True)
+        oc = y.shape[1]
+        return ops.rows_to_ncthw(y, N, oc, 1, H, W).reshape(N, oc, H, W)
+
+    def encode(self, x, **kwargs):
+        """-> DiagonalGaussianDistribution(moments)  (autoencoder.py:97-102); moments are fp32."""
+        return DiagonalGaussianDistribution(self.encode_moments(x))

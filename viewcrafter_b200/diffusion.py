@@ -13,6 +13,7 @@ import torch.nn as nn
 
 from . import schedule
 from .autoencoder import AutoencoderKL
+from .distributions import DiagonalGaussianDistribution
 from .unet import UNetModel
 
 
@@ -68,6 +69,33 @@ class LatentDiffusion(nn.Module):
 
     def predict_eps_from_z_and_v(self, x_t, t, v):
         return self._gather(self.sqrt_alphas_cumprod, t, x_t) * v + self._gather(self.sqrt_one_minus_alphas_cumprod, t, x_t) * x_t
+
+    def get_first_stage_encoding(self, encoder_posterior, noise=None):
+        """ddpm3d.py:611-618."""
+        if isinstance(encoder_posterior, DiagonalGaussianDistribution):
+            z = encoder_posterior.sample(noise=noise)
+        elif isinstance(encoder_posterior, torch.Tensor):
+            z = encoder_posterior
+        else:
+            raise NotImplementedError(f"encoder_posterior of type '{type(encoder_posterior)}' not yet implemented")
+        return self.scale_factor * z
+
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        """[B,3,T,H,W] (or [N,3,H,W]) -> scaled latents, one posterior sample per encode call in the reference's order
+        (per frame when perframe_ae), ddpm3d.py:620-644."""
+        reshape_back = x.dim() == 5
+        if reshape_back:
+            b, c, t, h, w = x.shape
+            x = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+        if not self.perframe_ae:
+            results = self.get_first_stage_encoding(self.first_stage_model.encode(x)).detach()
+        else:
+            results = torch.cat([self.get_first_stage_encoding(self.first_stage_model.encode(x[i:i + 1])).detach()
+                                 for i in range(x.shape[0])], dim=0)
+        if reshape_back:
+            results = results.reshape(b, t, *results.shape[1:]).permute(0, 2, 1, 3, 4)
+        return results
 
     @torch.no_grad()
     def decode_core(self, z, **kwargs):

@@ -329,10 +329,13 @@ def upsample2x(x: torch.Tensor, N: int, H: int, W: int) -> torch.Tensor:
     return out
 
 
-def im2col_s2(x: torch.Tensor, N: int, H: int, W: int, pad_lo: int = 1) -> tuple:
+def im2col_s2(x: torch.Tensor, N: int, H: int, W: int, pad_lo: int = 1, pad_hi: Optional[int] = None) -> tuple:
+    """stride-2 3x3 patches, zero padding pad_lo (top/left) and pad_hi (bottom/right; default = pad_lo).  U-Net Downsample:
+    (1, 1); VAE Downsample: (0, 1) (ae_modules.py:102-106)."""
     _chk16(x, "im2col.x")
     Cc = x.shape[1]
-    Ho, Wo = (H + 2 * pad_lo - 3) // 2 + 1, (W + 2 * pad_lo - 3) // 2 + 1
+    pad_hi = pad_lo if pad_hi is None else pad_hi
+    Ho, Wo = (H + pad_lo + pad_hi - 3) // 2 + 1, (W + pad_lo + pad_hi - 3) // 2 + 1
     out = torch.empty((N * Ho * Wo, 9 * Cc), device=x.device, dtype=torch.float16)
     check(_lib.load().vc_im2col3x3_s2(x.data_ptr(), out.data_ptr(), N, H, W, Cc, pad_lo, Ho, Wo, _stream()), "vc_im2col3x3_s2")
     return out, Ho, Wo
