@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VC_B200_ABI_VERSION 2
+#define VC_B200_ABI_VERSION 3
 
 int vc_abi_version(void);
 const char* vc_last_error(void);
@@ -119,6 +119,9 @@ int vc_rows_f32_to_ncthw(const float* x, int32_t ldx, float* out, int32_t B, int
 int vc_rows_f16_to_nchw_f32(const void* x, int32_t ldx, float* out, int32_t N, int32_t C, int64_t HW, void* stream);
 int vc_cast_f32_to_f16(const float* x, void* out, int64_t n, void* stream);
 int vc_add_f16(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* out = gelu(x), exact-erf GELU on fp16 rows (nn.GELU() between the two bias-free Linears of the Resampler FeedForward,
+ * lvdm/modules/encoders/resampler.py:27-34) */
+int vc_gelu_f16(const void* x, void* out, int64_t n, void* stream);
 
 /* ---- timestep / fps embedding (fp32, tiny) -------------------------------------------------------------------------
  * replaces: timestep_embedding utils_diffusion.py:8-28; time_embed / fps_embedding / emb_layers openaimodel3d.py:370-382,164-170 */

@@ -403,6 +403,42 @@ def decode_first_stage(sd: SD, z5: torch.Tensor, scale_factor: float = 0.18215) 
 
 
 # --------------------------------------------------------------------------------------
+# image-context projector  (lvdm/modules/encoders/resampler.py) -- SURVEY.md 8(f) rank f3
+# --------------------------------------------------------------------------------------
+def perceiver_attention(sd: SD, p: str, x: torch.Tensor, latents: torch.Tensor, heads: int, dim_head: int = 64) -> torch.Tensor:
+    """PerceiverAttention.forward, resampler.py:62-94: queries from the latents, keys/values from cat(image tokens,
+    latents); q and k are each scaled by dim_head**-0.25 before the product; softmax in fp32."""
+    x = F.layer_norm(x, (x.shape[-1],), sd[p + ".norm1.weight"], sd[p + ".norm1.bias"])
+    latents = F.layer_norm(latents, (latents.shape[-1],), sd[p + ".norm2.weight"], sd[p + ".norm2.bias"])
+    b, l, _ = latents.shape
+    q = F.linear(latents, sd[p + ".to_q.weight"])
+    k, v = F.linear(torch.cat((x, latents), dim=-2), sd[p + ".to_kv.weight"]).chunk(2, dim=-1)
+    split = lambda t: t.view(b, t.shape[1], heads, -1).transpose(1, 2)
+    q, k, v = split(q), split(k), split(v)
+    scale = 1 / math.sqrt(math.sqrt(dim_head))
+    w = torch.softmax(((q * scale) @ (k * scale).transpose(-2, -1)).float(), dim=-1)
+    out = (w @ v).permute(0, 2, 1, 3).reshape(b, l, -1)
+    return F.linear(out, sd[p + ".to_out.weight"])
+
+
+def resampler_forward(sd: SD, x: torch.Tensor, heads: int, dim_head: int = 64) -> torch.Tensor:
+    """Resampler.forward, resampler.py:134-145: learned latents (num_queries * video_length of them) attend to the
+    projected CLIP tokens through ``depth`` (PerceiverAttention, FeedForward) pairs, each with a residual;
+    FeedForward = LayerNorm, Linear(no bias), GELU(erf), Linear(no bias) (resampler.py:27-34)."""
+    latents = sd["latents"].repeat(x.shape[0], 1, 1)
+    x = F.linear(x, sd["proj_in.weight"], sd["proj_in.bias"])
+    depth = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("layers."))
+    for i in range(depth):
+        latents = perceiver_attention(sd, f"layers.{i}.0", x, latents, heads, dim_head) + latents
+        f = f"layers.{i}.1"
+        h = F.layer_norm(latents, (latents.shape[-1],), sd[f + ".0.weight"], sd[f + ".0.bias"])
+        h = F.linear(F.gelu(F.linear(h, sd[f + ".1.weight"])), sd[f + ".3.weight"])
+        latents = h + latents
+    latents = F.linear(latents, sd["proj_out.weight"], sd["proj_out.bias"])
+    return F.layer_norm(latents, (latents.shape[-1],), sd["norm_out.weight"], sd["norm_out.bias"])
+
+
+# --------------------------------------------------------------------------------------
 # DDIM sampler  (lvdm/models/samplers/ddim.py)
 # --------------------------------------------------------------------------------------
 def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale):

@@ -170,9 +170,23 @@ def gen_vae_enc():
     print("vae enc moments std", float(moments.std()), "z std", float(z.std()))
 
 
+def gen_resampler():
+    """Resampler.forward of the unmodified reference (resampler.py:96-145) at a reduced width; B=2 so the
+    latents.repeat batch path is covered.  33 CLIP tokens + 4x4 latents -> 49 keys (ragged vs. the 128-key tile)."""
+    over = dict(dim=256, depth=2, dim_head=64, heads=4, num_queries=4, embedding_dim=320, output_dim=192, video_length=4)
+    m = ref_shims.build_resampler(**over)
+    shapes = _load_synth(m, seed=17)
+    g = torch.Generator().manual_seed(18)
+    x = torch.randn(2, 33, 320, generator=g)
+    with torch.no_grad():
+        y = m(x)
+    np.savez_compressed(os.path.join(OUT, "resampler_d256.npz"), shapes=shapes, kwargs=json.dumps(over), x=x.numpy(), y=y.numpy())
+    print("resampler out std", float(y.std()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["schedule", "ddim", "unet", "vae", "vae_enc"]
+    which = sys.argv[1:] or ["schedule", "ddim", "unet", "vae", "vae_enc", "resampler"]
     with torch.no_grad():
         for w in which:
             globals()["gen_" + w]()

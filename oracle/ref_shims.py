@@ -103,3 +103,16 @@ def build_decoder(seed=0, **over):
     dec = Decoder(**dd).eval()
     pq = torch.nn.Conv2d(4, dd["z_channels"], 1)
     return dec, pq
+
+
+RESAMPLER_KW = dict(dim=1024, depth=4, dim_head=64, heads=12, num_queries=16, embedding_dim=1280, output_dim=1024,
+                    ff_mult=4, video_length=16)          # configs/inference_pvd_1024.yaml:100-111
+
+
+def build_resampler(seed=0, **over):
+    """The unmodified reference Resampler (image_proj_model, ddpm3d.py:1038-1039)."""
+    install()
+    from lvdm.modules.encoders.resampler import Resampler
+    kw = dict(RESAMPLER_KW); kw.update(over)
+    torch.manual_seed(seed)
+    return Resampler(**kw).eval()

@@ -72,6 +72,11 @@ def _h(t):
 
 
 def linear(x, w, bias=None, res=None, geglu=False, out=None, out_f32=False, x2=None, ln=None):
+    # the kernel's host-side contract (gemm_tap.cu: TMA strides are 16-byte multiples)
+    # (the double's own norm ops may hand back permuted views; only row-major operands carry a meaningful pitch)
+    assert w.shape[1] % 8 == 0, w.shape
+    for t in (x, w):
+        assert t.stride(1) != 1 or t.shape[0] == 1 or t.stride(0) % 8 == 0, (t.shape, t.stride())
     a = x.float() if x2 is None else torch.cat([x.float(), x2.float()], 1)
     y = a @ w.float().t()
     if ln is not None:
@@ -223,6 +228,10 @@ def rows_f16_to_nchw(x, N, Cc, H, W):
 
 def cast_f16(x):
     return _h(x)
+
+
+def gelu_f16(x):
+    return _h(F.gelu(x.float()))
 
 
 def add_f16(a, b):

@@ -166,6 +166,25 @@ def test_vae_encode_host_logic_vs_reference_golden(cpu_ops, golden_dir):
     assert torch.equal(post.mode(), post.mean) and post.logvar.min() >= -30.0 and post.logvar.max() <= 20.0
 
 
+def test_vae_odd_token_count_attention(cpu_ops):
+    """A 40x72 image gives a 5x9 = 45-token mid AttnBlock: 45 is not a multiple of 8, so the key axis (a GEMM reduction
+    and a row pitch) is padded with zero keys masked to -inf before the softmax.  The op double asserts the kernel's
+    16-byte-stride contract, so an unpadded call fails here the way it fails on the GPU."""
+    from viewcrafter_b200.autoencoder import AutoencoderKL
+    vae = AutoencoderKL(dict(VAE_DDCONFIG, ch=32), None, 4).eval()
+    sd = synth.synth_state_dict(synth.module_shapes(vae), seed=51)
+    vae.load_state_dict(sd, strict=True)
+    x = torch.rand(1, 3, 40, 72, generator=torch.Generator().manual_seed(52)) * 2 - 1
+    with torch.no_grad():
+        ref = O.vae_encode_moments(sd, x)
+        m = vae.encode(x).parameters
+        assert m.shape == ref.shape == (1, 8, 5, 9)
+        assert float((m - ref).abs().max()) < 0.03
+        z = torch.randn(1, 4, 5, 9, generator=torch.Generator().manual_seed(53))
+        y, yr = vae.decode(z), O.vae_decode(sd, z)
+        assert y.shape == yr.shape == (1, 3, 40, 72) and float((y - yr).abs().max()) < 0.03 * max(1.0, float(yr.std()))
+
+
 def test_encode_first_stage_perframe_rng_order(cpu_ops):
     """LatentDiffusion.encode_first_stage: per-frame encodes, each drawing its posterior noise from the CPU generator in frame
     order (ddpm3d.py:633-639, distributions.py:35-36), scaled by scale_factor; checked against the oracle fed the same draws."""
@@ -183,3 +202,21 @@ def test_encode_first_stage_perframe_rng_order(cpu_ops):
         ref = O.encode_first_stage(sdv, x, noises)
     assert z.shape == (1, 4, 3, 2, 3)
     assert float((z - ref).abs().max()) < 0.02, float((z - ref).abs().max())
+
+
+def test_resampler_wiring_matches_reference_golden(cpu_ops, golden_dir):
+    """viewcrafter_b200.Resampler (image_proj_model) on the CPU op double vs the output of the unmodified
+    reference Resampler: same kwargs, same state-dict keys (strict load), same token order; B=2, 33 + 16 ragged keys."""
+    from viewcrafter_b200.resampler import Resampler
+    g = np.load(os.path.join(golden_dir, "resampler_d256.npz"))
+    kw = json.loads(str(g["kwargs"]))
+    m = Resampler(**kw).eval()
+    shapes = [(n, tuple(s)) for n, s in json.loads(str(g["shapes"]))]
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == shapes          # names, shapes AND order of the reference
+    m.load_state_dict(synth.synth_state_dict(shapes, seed=17), strict=True)
+    y = m(torch.from_numpy(g["x"]))
+    err = (y - torch.from_numpy(g["y"])).abs()
+    assert y.shape == g["y"].shape and y.dtype == torch.float32
+    assert float(err.max()) < 0.03 and float(err.mean()) < 0.004, (float(err.max()), float(err.mean()))
+    with pytest.raises(NotImplementedError):
+        Resampler(dim_head=32)

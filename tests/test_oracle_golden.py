@@ -112,3 +112,15 @@ def test_vae_encoder_matches_reference(golden_dir):
         z = O.posterior_sample(m, torch.from_numpy(g["noise"]))
     np.testing.assert_allclose(m.numpy(), g["moments"], rtol=0, atol=5e-5)
     np.testing.assert_allclose(z.numpy(), g["z"], rtol=0, atol=5e-5)
+
+
+def test_resampler_matches_reference(golden_dir):
+    """image_proj_model: Resampler.forward of the unmodified reference (resampler.py:96-145), reduced width, B=2."""
+    g = _load(golden_dir, "resampler_d256.npz")
+    shapes = [(n, tuple(s)) for n, s in json.loads(str(g["shapes"]))]
+    kw = json.loads(str(g["kwargs"]))
+    sd = synth.synth_state_dict(shapes, seed=17)
+    with torch.no_grad():
+        y = O.resampler_forward(sd, torch.from_numpy(g["x"]), heads=kw["heads"], dim_head=kw["dim_head"])
+    assert y.shape == (2, kw["num_queries"] * kw["video_length"], kw["output_dim"])
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=5e-5)

@@ -155,3 +155,34 @@ def test_ddim_sample_three_steps_vs_oracle(batch_cfg):
     assert len(inter["x_inter"]) == len(ref_inter["x_inter"])
     # one CFG step turns a U-Net error e into (1 + 2*7.5) e ~ 16 e: 16 x 0.007 ~ 0.11 worst case per step
     assert float(err.max()) <= 0.15 and float(err.mean()) <= 0.02
+
+
+def test_resampler_matches_reference_golden_and_oracle(golden_dir):
+    """image_proj_model (Resampler, resampler.py:96-145) on the CUDA kernels: reference golden at a reduced width (B=2, ragged
+    49-key attention) and the shipped configuration (dim 1024, depth 4, 12 heads, 16x16 queries, 257 CLIP tokens) vs the oracle."""
+    _need_gpu()
+    from oracle import lvdm_oracle as O
+    from oracle import synth
+    from viewcrafter_b200.resampler import Resampler
+    g = np.load(os.path.join(golden_dir, "resampler_d256.npz"))
+    kw = json.loads(str(g["kwargs"]))
+    shapes = [(n, tuple(s)) for n, s in json.loads(str(g["shapes"]))]
+    m = Resampler(**kw)
+    m.load_state_dict(synth.synth_state_dict(shapes, seed=17), strict=True)
+    m = m.cuda().eval()
+    y = m(torch.from_numpy(g["x"]).cuda())
+    err = (y.cpu() - torch.from_numpy(g["y"])).abs()
+    print(f"resampler d256: max err {float(err.max()):.4g} mean {float(err.mean()):.4g} ref std {float(g['y'].std()):.3g}")
+    assert float(err.max()) <= 0.03 and float(err.mean()) <= 0.004
+    full = dict(dim=1024, depth=4, dim_head=64, heads=12, num_queries=16, embedding_dim=1280, output_dim=1024, ff_mult=4, video_length=16)
+    m = Resampler(**full)
+    sd = synth.synth_state_dict(synth.module_shapes(m), seed=61)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x = torch.randn(1, 257, 1280, generator=torch.Generator().manual_seed(62))
+    with torch.no_grad():
+        ref = O.resampler_forward(sd, x, heads=12)
+    y = m(x.cuda())
+    err = (y.cpu() - ref).abs()
+    print(f"resampler full: max err {float(err.max()):.4g} mean {float(err.mean()):.4g} ref std {float(ref.std()):.3g}")
+    assert y.shape == (1, 256, 1024) and float(err.max()) <= 0.04 and float(err.mean()) <= 0.004

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VC_B200_LIB") or os.path.join(_HERE, "libvc_b200.so")   # override: A/B builds of the kernels
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class VcError(RuntimeError):
@@ -66,6 +66,7 @@ SIGNATURES = {
     "vc_rows_f16_to_nchw_f32": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp]),
     "vc_cast_f32_to_f16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "vc_add_f16": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "vc_gelu_f16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "vc_timestep_embedding": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "vc_small_linear_f32": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vc_ddim_update": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(DdimScalars), _vp, _vp]),

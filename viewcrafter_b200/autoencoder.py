@@ -204,11 +204,18 @@ class AutoencoderKL(nn.Module):
         hn = ops.groupnorm(x, N, *P["gn"], 1e-6, False)
         qk = ops.linear(hn, P["qk_w"], bias=P["qk_b"])                                   # [N*HW, 2C]
         out = torch.empty_like(x)
+        HWp = (HW + 7) // 8 * 8            # the key axis is a GEMM reduction / row pitch: TMA needs 16-byte multiples
         for n in range(N):
             rows = slice(n * HW, (n + 1) * HW)
-            s = ops.linear(qk[rows, :C], qk[rows, C:], out_f32=True)                      # S = Q K^T  [HW, HW] fp32
+            kn, hv = qk[rows, C:], hn[rows]
+            if HWp != HW:                                                                 # odd token counts (e.g. a 5x9 latent): zero key rows,
+                kn = torch.zeros((HWp, C), device=x.device, dtype=torch.float16); kn[:HW] = qk[rows, C:]
+                hv = torch.zeros((HWp, C), device=x.device, dtype=torch.float16); hv[:HW] = hn[rows]
+            s = ops.linear(qk[rows, :C], kn, out_f32=True)                                # S = Q K^T  [HW, HWp] fp32
+            if HWp != HW:
+                s[:, HW:] = float("-inf")                                                 # ... masked out of the softmax
             p = ops.softmax_rows(s, float(C) ** -0.5)                                     # fp16 probabilities
-            vt = ops.linear(P["v_w"], hn[rows])                                           # V^T (bias folded below) [C, HW]
+            vt = ops.linear(P["v_w"], hv)                                                 # V^T (bias folded below) [C, HWp]
             o = ops.linear(p, vt, bias=P["v_b"])                                          # P V + b_v  (rows of P sum to 1)
             ops.linear(o, P["o_w"], bias=P["o_b"], res=x[rows], out=out[rows])
         return out

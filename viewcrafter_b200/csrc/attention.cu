@@ -9,7 +9,10 @@
 //                        refreshed when it grew by more than 2^8 ("lazy rescale"), so O is rarely touched
 //     P (fp16) -> TMEM, O += P V   TS MMA (A from TMEM, V tile MN-major in smem)
 // The next tile's Q K^T is issued as soon as S sits in registers, so the tensor pipe works underneath the
-// MUFU-bound softmax; K/V tiles arrive by TMA through a 2-stage mbarrier ring.  Two CTAs are co-resident per SM.
+// MUFU-bound softmax; K and V tiles arrive by TMA through two separate 2-stage mbarrier rings: a K stage is released as
+// soon as its Q K^T has retired, a V stage when its P V has, so K(j+1) is in flight a whole tile period before
+// Q K^T(j+1) is issued (with one shared K/V ring the load could only start when P V(j-1) had retired, i.e. exactly when
+// it was needed: ncu showed the softmax warps waiting for S 9 % of the time).  Two CTAs are co-resident per SM.
 //
 // Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2..5 = softmax /
 // correction / epilogue (TMEM lane quadrant = warp % 4).
@@ -33,6 +36,18 @@ static constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64;
 static constexpr int ATT_TILE_BYTES = 128 * 64 * 2;                    // 16 KB
 static constexpr int ATT_SMEM = ATT_TILE_BYTES * 5 + 1024 + 256;       // Q + 2x(K,V) + slack + barriers
 static constexpr float ATT_LAZY = 8.0f;                                // rescale only if the max grew by > 2^8
+// A/B switches (side-by-side builds: VC_NVCC_EXTRA="-DVC_ATT_SPLIT_KV=0 ..." + VC_OUT, loaded through VC_B200_LIB)
+#ifndef VC_ATT_SPLIT_KV
+#define VC_ATT_SPLIT_KV 0      // separate K / V rings (0: one ring, a stage is freed when its P V retires)
+#endif
+#ifndef VC_ATT_PARKED_WAIT
+#define VC_ATT_PARKED_WAIT 0   // TMA / MMA warps wait with a suspend hint + nanosleep back-off instead of spinning
+#endif
+#if VC_ATT_PARKED_WAIT
+#define ATT_ROLE_WAIT mbar_wait_parked
+#else
+#define ATT_ROLE_WAIT mbar_wait
+#endif
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -51,7 +66,10 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.99992448f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
 }
-static constexpr int ATT_POLY_PERIOD = 4;                // 0 disables the polynomial path
+#ifndef VC_ATT_POLY_PERIOD
+#define VC_ATT_POLY_PERIOD 4
+#endif
+static constexpr int ATT_POLY_PERIOD = VC_ATT_POLY_PERIOD;   // one pair in every PERIOD pairs on the FMA pipe; 0 disables the polynomial path
 __device__ __forceinline__ float ex2_sel(float x, int e) {
   if (ATT_POLY_PERIOD > 0 && (e % (2 * ATT_POLY_PERIOD)) < 2) return ex2_poly(x);
   return ex2f(x);
@@ -64,13 +82,15 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
   uint8_t* sKV = smem + ATT_TILE_BYTES;                                 // stage s: K at s*32K, V at s*32K+16K
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* kv_full = bars + 1;    // [2]  K tile landed (one-ring build: K and V)
+  uint64_t* kv_empty = bars + 3;   // [2]  K stage free: its Q K^T retired (one-ring build: its P V retired)
   uint64_t* s_full = bars + 5;     // MMA -> softmax: S tile ready
-  uint64_t* s_free = bars + 6;     // softmax -> MMA: S tile copied to registers (128 arrivals)
-  uint64_t* p_full = bars + 7;     // softmax -> MMA: P written, O corrected (128 arrivals)
+  uint64_t* s_free = bars + 6;     // softmax -> MMA: S tile copied to registers (one arrival per softmax warp)
+  uint64_t* p_full = bars + 7;     // softmax -> MMA: P written, O corrected (one arrival per softmax warp)
   uint64_t* o_done = bars + 8;     // MMA -> softmax: P V of the tile retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* v_full = bars + 9;     // [2]  V tile landed
+  uint64_t* v_empty = bars + 11;   // [2]  V stage free: its P V retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_BM, head = blockIdx.y, b = blockIdx.z;
@@ -84,6 +104,8 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
     mbar_init(q_full, 1);
     mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
     mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
+    mbar_init(&v_full[0], 1); mbar_init(&v_full[1], 1);
+    mbar_init(&v_empty[0], 1); mbar_init(&v_empty[1], 1);
     mbar_init(s_full, 1);
     mbar_init(s_free, 4);      // one arrival per softmax warp (512 serialised mbarrier arrivals per tile were measurable)
     mbar_init(p_full, 4);
@@ -109,14 +131,29 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
     __syncwarp();
     for (int j = 0; j < ntiles; ++j) {
       const int s = j & 1;
-      if (j >= 2) mbar_wait(&kv_empty[s], ((j >> 1) - 1) & 1);
+      uint8_t* sk = sKV + s * 2 * ATT_TILE_BYTES;
+#if VC_ATT_SPLIT_KV
+      if (j >= 2) ATT_ROLE_WAIT(&kv_empty[s], ((j >> 1) - 1) & 1);        // Q K^T(j-2) retired
       if (elect_one()) {
-        uint8_t* sk = sKV + s * 2 * ATT_TILE_BYTES;
+        mbar_expect_tx(&kv_full[s], ATT_TILE_BYTES);
+        tma_load_4d(sk, &p.tmap_k, &kv_full[s], 0, head, j * ATT_BN, bk);
+      }
+      __syncwarp();
+      if (j >= 2) ATT_ROLE_WAIT(&v_empty[s], ((j >> 1) - 1) & 1);         // P V(j-2) retired
+      if (elect_one()) {
+        mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
+        tma_load_4d(sk + ATT_TILE_BYTES, &p.tmap_v, &v_full[s], 0, head, j * ATT_BN, bk);
+      }
+      __syncwarp();
+#else
+      if (j >= 2) ATT_ROLE_WAIT(&kv_empty[s], ((j >> 1) - 1) & 1);
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
         tma_load_4d(sk, &p.tmap_k, &kv_full[s], 0, head, j * ATT_BN, bk);
         tma_load_4d(sk + ATT_TILE_BYTES, &p.tmap_v, &kv_full[s], 0, head, j * ATT_BN, bk);
       }
       __syncwarp();
+#endif
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
@@ -124,7 +161,7 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
     const uint32_t aQ = smem_u32(sQ);
     auto issue_qk = [&](int j) {
       const int s = j & 1;
-      mbar_wait(&kv_full[s], (j >> 1) & 1);
+      ATT_ROLE_WAIT(&kv_full[s], (j >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t aK = smem_u32(sKV + s * 2 * ATT_TILE_BYTES);
@@ -132,24 +169,34 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
         for (int k = 0; k < ATT_D / 16; ++k)
           umma_ss(tS, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc_qk, k > 0 ? 1u : 0u);
         umma_commit(s_full);
+#if VC_ATT_SPLIT_KV
+        umma_commit(&kv_empty[s]);                // the K stage is free once this Q K^T has retired
+#endif
       }
       __syncwarp();
     };
-    mbar_wait(q_full, 0);
+    ATT_ROLE_WAIT(q_full, 0);
     issue_qk(0);
     for (int j = 0; j < ntiles; ++j) {
       if (j + 1 < ntiles) {                       // next S as soon as this one has been copied out of TMEM
-        mbar_wait(s_free, j & 1);
+        ATT_ROLE_WAIT(s_free, j & 1);
         issue_qk(j + 1);
       }
-      mbar_wait(p_full, j & 1);
+#if VC_ATT_SPLIT_KV
+      ATT_ROLE_WAIT(&v_full[j & 1], (j >> 1) & 1);
+#endif
+      ATT_ROLE_WAIT(p_full, j & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t aV = smem_u32(sKV + (j & 1) * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)
           umma_ts(tO, tP + k * 8, umma_desc_sw128(aV + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+#if VC_ATT_SPLIT_KV
+        umma_commit(&v_empty[j & 1]);
+#else
         umma_commit(&kv_empty[j & 1]);
+#endif
         umma_commit(o_done);
       }
       __syncwarp();
@@ -176,9 +223,16 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
 
       float mx = -INFINITY;
       if (valid == ATT_BN) {
+        // four independent running maxima (one per 32-column chunk): a single chain is 32 dependent FMNMX deep
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(s0[e]), __uint_as_float(s1[e])), fmaxf(__uint_as_float(s2[e]), __uint_as_float(s3[e]))));
+        for (int e = 0; e < 32; e += 2) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(s0[e]), __uint_as_float(s0[e + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(s1[e]), __uint_as_float(s1[e + 1])));
+          m2 = fmaxf(m2, fmaxf(__uint_as_float(s2[e]), __uint_as_float(s2[e + 1])));
+          m3 = fmaxf(m3, fmaxf(__uint_as_float(s3[e]), __uint_as_float(s3[e + 1])));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       } else {
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
@@ -198,33 +252,33 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
         m = m_cand;
       }
       const float neg_m = -m;
-      float psum = 0.f;
+      float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;     // independent partial row sums (shorter FADD chains)
       // probabilities, packed in place: s0[0..15] <- s0, s0[16..31] <- s1, s2[0..15] <- s2, s2[16..31] <- s3
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
         const float a0 = ex2_sel(fmaf(__uint_as_float(s0[e]), sl2, neg_m), e), a1 = ex2_sel(fmaf(__uint_as_float(s0[e + 1]), sl2, neg_m), e + 1);
-        psum += a0 + a1;
+        ps0 += a0 + a1;
         s0[e / 2] = pack_half2(a0, a1);
       }
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
         const float a0 = ex2_sel(fmaf(__uint_as_float(s1[e]), sl2, neg_m), e), a1 = ex2_sel(fmaf(__uint_as_float(s1[e + 1]), sl2, neg_m), e + 1);
-        psum += a0 + a1;
+        ps1 += a0 + a1;
         s0[16 + e / 2] = pack_half2(a0, a1);
       }
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
         const float a0 = ex2_sel(fmaf(__uint_as_float(s2[e]), sl2, neg_m), e), a1 = ex2_sel(fmaf(__uint_as_float(s2[e + 1]), sl2, neg_m), e + 1);
-        psum += a0 + a1;
+        ps2 += a0 + a1;
         s2[e / 2] = pack_half2(a0, a1);
       }
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
         const float a0 = ex2_sel(fmaf(__uint_as_float(s3[e]), sl2, neg_m), e), a1 = ex2_sel(fmaf(__uint_as_float(s3[e + 1]), sl2, neg_m), e + 1);
-        psum += a0 + a1;
+        ps3 += a0 + a1;
         s2[16 + e / 2] = pack_half2(a0, a1);
       }
-      l += psum;
+      l += (ps0 + ps1) + (ps2 + ps3);
       if (j > 0) {
         mbar_wait(o_done, (j - 1) & 1);                  // P V of the previous tile retired: P and O may be touched
         tc_fence_after();

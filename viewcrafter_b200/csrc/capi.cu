@@ -114,6 +114,11 @@ int vc_add_f16(const void* a, const void* b, void* out, int64_t n, void* stream)
   return add_rows_f16(H(a), H(b), HM(out), n, ST(stream));
 }
 
+int vc_gelu_f16(const void* x, void* out, int64_t n, void* stream) {
+  COUNT(1);
+  return gelu_rows_f16(H(x), HM(out), n, ST(stream));
+}
+
 int vc_softmax_rows_f32(const float* x, int64_t rows, int64_t cols, float scale, void* out, void* stream) {
   COUNT(1);
   return softmax_rows_f32(x, rows, cols, scale, HM(out), ST(stream));

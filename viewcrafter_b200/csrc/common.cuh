@@ -98,6 +98,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Wait for warps with slack (TMA producer, MMA issuer of the attention kernel): try_wait with a suspend-time hint, which
+// compiles to SYNCS.TRYWAIT + NANOSLEEP.SYNCS (the warp sleeps until the barrier event or the time limit).
+// A bare try_wait loop re-issues every ~20 cycles (ncu: 44 M + 38 M TRYWAIT executions in one
+// attention launch, 11 % of all issued instructions) and those warps share schedulers 0/1 with two of the four softmax
+// warps, whose issue slots they take.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) return;
+  }
+}
 
 // ---- TMA (cp.async.bulk.tensor) ----
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

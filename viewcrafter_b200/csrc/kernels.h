@@ -71,6 +71,7 @@ int nhwc_to_nchw_f32_from_f16(const __half* x, int ldx, float* out, int N, int C
 int cast_f32_to_f16(const float* x, __half* out, long long n, cudaStream_t stream);
 int softmax_rows_f32(const float* x, long long rows, long long cols, float scale, __half* out, cudaStream_t stream);
 int add_rows_f16(const __half* a, const __half* b, __half* out, long long n, cudaStream_t stream);
+int gelu_rows_f16(const __half* x, __half* out, long long n, cudaStream_t stream);
 
 // emb path: out[r, n] = bias[n] + sum_k act(x[r,k]) * W[n,k]   (fp32, tiny M); act: 0 none, 1 SiLU
 int small_linear_f32(const float* x, int rows, int K, const float* W, const float* bias, int N, int act_in, float* out,

@@ -134,6 +134,21 @@ __global__ void add_kernel(const __half2* __restrict__ a, const __half2* __restr
     out[i] = __floats2half2_rn(x.x + y.x, x.y + y.y);
   }
 }
+// exact-erf GELU, elementwise (Resampler FeedForward, resampler.py:27-34); erf as in the GEGLU epilogue (common.cuh)
+__global__ void gelu_kernel(const __half2* __restrict__ x, __half2* __restrict__ out, long long n2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const float2 v = __half22float2(x[i]);
+    out[i] = __floats2half2_rn(gelu_erf_fast(v.x), gelu_erf_fast(v.y));
+  }
+}
+int gelu_rows_f16(const __half* x, __half* out, long long n, cudaStream_t stream) {
+  VC_REQUIRE(x && out && n > 0 && n % 2 == 0, "gelu: bad args");
+  const int blocks = (int)min((long long)sm_count() * 16, (n / 2 + 255) / 256);
+  gelu_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __half2*>(x), reinterpret_cast<__half2*>(out), n / 2);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
 int add_rows_f16(const __half* a, const __half* b, __half* out, long long n, cudaStream_t stream) {
   VC_REQUIRE(a && b && out && n % 2 == 0, "add: bad args");
   const int blocks = (int)min((long long)sm_count() * 16, (n / 2 + 255) / 256);

@@ -378,6 +378,15 @@ def add_f16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gelu_f16(x: torch.Tensor) -> torch.Tensor:
+    """exact-erf GELU, elementwise (nn.GELU() of the Resampler FeedForward, resampler.py:27-34)."""
+    _chk16(x, "gelu.x")
+    assert x.is_contiguous()
+    out = torch.empty_like(x)
+    check(_lib.load().vc_gelu_f16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "vc_gelu_f16")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------
 # embedding MLP + DDIM update
 # ----------------------------------------------------------------------------------------------------
