@@ -147,17 +147,28 @@ def kernel_rooflines(wl, device, peaks):
     t_gn = time_kernel(lambda: ops.groupnorm(x, T, gam, bet, 1e-5, True))
     by_gn = 2.0 * M * C * 2                                     # algorithmic: read once + write once, fp16
     r = {
-        "roofline": {"kernel": "gemm_tap_kernel<160> (3x3 conv 320->320 @%dx%dx%d)" % (T, H, W), "bound": "tensor",
+        "roofline": {"kernel": "gemm_tap2_kernel<160> (tcgen05 cta_group::2 tap-GEMM, 3x3 conv 320->320 @%dx%dx%d)" % (T, H, W), "bound": "tensor",
                      "achieved": fl_conv / t_conv / 1e12, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                      "frac": fl_conv / t_conv / 1e12 / peaks["tflops_burst"], "traffic": None, "ms": t_conv * 1e3,
-                     "peak_source": peaks["src"] + " cuBLAS bf16 burst"},
+                     "peak_source": peaks["src"] + " cuBLAS bf16 burst", "algorithmic_flop": fl_conv,
+                     "algorithmic_bytes": 2.0 * M * C * 2 + 9 * C * C * 2},
         "roofline_attention": {"kernel": "flash_attn_d64_kernel (spatial self-attn, %d heads, N=%d)" % (heads, H * W), "bound": "tensor",
                                "achieved": fl_att / t_att / 1e12, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
-                               "frac": fl_att / t_att / 1e12 / peaks["tflops_burst"], "traffic": None, "ms": t_att * 1e3},
-        "roofline_groupnorm": {"kernel": "gn_stats_kernel+gn_apply_kernel (GroupNorm32+SiLU, C=320)", "bound": "hbm",
+                               "frac": fl_att / t_att / 1e12 / peaks["tflops_burst"], "traffic": None, "ms": t_att * 1e3,
+                               "algorithmic_flop": fl_att, "algorithmic_bytes": 4.0 * M * C * 2},
+        "roofline_groupnorm": {"kernel": "gn_fused_kernel (GroupNorm32+SiLU, C=320, one launch)", "bound": "hbm",
                                "achieved": by_gn / t_gn / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                               "frac": by_gn / t_gn / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms": t_gn * 1e3},
+                               "frac": by_gn / t_gn / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms": t_gn * 1e3, "algorithmic_bytes": by_gn},
     }
+    # measured DRAM traffic per launch of the same kernels/shapes, from the committed ncu --set full capture (not re-measured
+    # here: a number taken under a profiler is never a bench value, and ncu cannot run inside the timed process)
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp))
+        for k in r:
+            if k in t:
+                r[k]["traffic"] = t[k]["traffic_bytes"]
+                r[k]["traffic_source"] = t["source"].split(" (")[0] + "; " + t[k]["note"]
     return r
 
 

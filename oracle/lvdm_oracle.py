@@ -450,14 +450,17 @@ def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale):
 
 
 def ddim_update(x, v_cond, v_uncond, sc: np.ndarray, sqrt_ac_t: float, sqrt_1mac_t: float,
-                noise, cfg_scale: float, guidance_rescale: float):
+                noise, cfg_scale: float, guidance_rescale: float, v_uncond_img=None, cfg_img: float = 0.0):
     """Everything in p_sample_ddim after the two apply_model calls, ddim.py:228-281, v-parameterisation
     (ddpm3d.py:239-251).  ``sc`` = step_scalars(...) = [a_t, a_prev, sigma_t, sqrt(1-a_t), scale_t, prev_scale_t];
     sqrt_ac_t / sqrt_1mac_t are the model buffers gathered by the *timestep* t."""
     if v_uncond is None or cfg_scale == 1.0:
         out = v_cond
     else:
-        out = v_uncond + cfg_scale * (v_cond - v_uncond)
+        if v_uncond_img is None:
+            out = v_uncond + cfg_scale * (v_cond - v_uncond)
+        else:       # three-way CFG, ddim_multiplecond.py:227-233
+            out = v_uncond + cfg_img * (v_uncond_img - v_uncond) + cfg_scale * (v_cond - v_uncond_img)
         if guidance_rescale > 0.0:
             out = rescale_noise_cfg(out, v_cond, guidance_rescale)
     f = lambda s: torch.tensor(float(s), dtype=torch.float32)
@@ -472,10 +475,12 @@ def ddim_update(x, v_cond, v_uncond, sc: np.ndarray, sqrt_ac_t: float, sqrt_1mac
 
 def ddim_sample(model_fn, sched, shape, S: int, cond, uncond, x_T: torch.Tensor, noises: List[torch.Tensor],
                 eta=1.0, cfg_scale=7.5, guidance_rescale=0.7, method="uniform_trailing", log_every_t=100,
-                use_dynamic_rescale=True, fixed_prev_scale=True):
+                use_dynamic_rescale=True, fixed_prev_scale=True, uncond_img=None, cfg_img=None):
     """DDIMSampler.sample + ddim_sampling loop, ddim.py:61-205.  ``model_fn(x, t_long, cond)`` plays
     model.apply_model; ``noises[i]`` is the i-th per-step randn draw (the reference draws it with
-    torch.randn at ddim.py:275; the oracle takes it as an input so both sides see identical noise)."""
+    torch.randn at ddim.py:275; the oracle takes it as an input so both sides see identical noise).
+    ``uncond_img`` (+ ``fixed_prev_scale=False``) gives the three-way-CFG sampler of ddim_multiplecond.py:209-287
+    (``cfg_img`` defaults to ``cfg_scale`` like :222-223)."""
     tab = ddim_tables(sched, S, method, eta, fixed_prev_scale)
     if not use_dynamic_rescale:
         tab["scale"] = torch.ones(S); tab["scale_prev"] = torch.ones(S)
@@ -487,10 +492,12 @@ def ddim_sample(model_fn, sched, shape, S: int, cond, uncond, x_T: torch.Tensor,
         ts = torch.full((shape[0],), int(step), dtype=torch.long)
         v_c = model_fn(img, ts, cond)
         v_u = model_fn(img, ts, uncond) if (uncond is not None and cfg_scale != 1.0) else None
+        v_i = model_fn(img, ts, uncond_img) if (uncond_img is not None and v_u is not None) else None
         sc = step_scalars(tab, index)
         img, pred_x0 = ddim_update(img, v_c, v_u, sc, sched["sqrt_alphas_cumprod"][int(step)].item(),
                                    sched["sqrt_one_minus_alphas_cumprod"][int(step)].item(), noises[i],
-                                   cfg_scale, guidance_rescale)
+                                   cfg_scale, guidance_rescale, v_uncond_img=v_i,
+                                   cfg_img=cfg_scale if cfg_img is None else cfg_img)
         if index % log_every_t == 0 or index == S - 1:
             inter["x_inter"].append(img); inter["pred_x0"].append(pred_x0)
     return img, inter

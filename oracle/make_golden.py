@@ -119,6 +119,40 @@ def gen_ddim():
     np.savez_compressed(os.path.join(OUT, "ddim_small.npz"), **out)
 
 
+def gen_ddim_multicond():
+    """The unmodified three-way-CFG sampler (ddim_multiplecond.py) on the toy denoiser: S=5 with cfg_img=2.5 and S=8 with the
+    default cfg_img (= the text scale); base 0.3 so that the un-fixed ddim_scale_arr_prev[0] matters."""
+    ref_shims.install()
+    import lvdm.models.samplers.ddim_multiplecond as mod
+    out = {}
+    for tag, S, cfg_img in (("S5", 5, 2.5), ("S8", 8, None)):
+        model = _stub_model(0.3)
+        model.apply_model = lambda x, t, c, **kw: toy_denoiser(x, t, c)
+        g = torch.Generator().manual_seed(12)
+        shape = (1, 4, 3, 4, 6)
+        x_T = torch.randn(shape, generator=g)
+        noises = [torch.randn(shape, generator=g) for _ in range(S)]
+        cond = {"b": torch.randn(shape, generator=g), "k": torch.tensor([1.3])}
+        uncond = {"b": torch.randn(shape, generator=g), "k": torch.tensor([0.4])}
+        uncond_img = {"b": torch.randn(shape, generator=g), "k": torch.tensor([0.9])}
+        it = iter(noises)
+        mod.noise_like = lambda shape_, device, repeat=False: next(it)
+        smp = mod.DDIMSampler(model)
+        smp.register_buffer = lambda name, attr: setattr(smp, name, attr)
+        samples, inter = smp.sample(S=S, batch_size=1, shape=shape[1:], conditioning=cond, eta=1.0, verbose=False,
+                                    x_T=x_T, unconditional_guidance_scale=7.5, unconditional_conditioning=uncond,
+                                    timestep_spacing="uniform_trailing", guidance_rescale=0.7, cfg_img=cfg_img,
+                                    unconditional_conditioning_img_nonetext=uncond_img)
+        out[f"{tag}_x_T"] = x_T.numpy(); out[f"{tag}_noises"] = torch.stack(noises).numpy()
+        for nm, d in (("cond", cond), ("uncond", uncond), ("uncond_img", uncond_img)):
+            out[f"{tag}_{nm}_b"] = d["b"].numpy()
+        out[f"{tag}_samples"] = samples.numpy()
+        out[f"{tag}_n_inter"] = np.asarray(len(inter["x_inter"]))
+        out[f"{tag}_pred_x0_last"] = inter["pred_x0"][-1].numpy()
+        out[f"{tag}_scale_prev"] = smp.ddim_scale_arr_prev.numpy()
+    np.savez_compressed(os.path.join(OUT, "ddim_multicond_small.npz"), **out)
+
+
 def gen_unet():
     cases = {
         # name: (unet kwargs overrides, T, H, W)
@@ -186,7 +220,7 @@ def gen_resampler():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["schedule", "ddim", "unet", "vae", "vae_enc", "resampler"]
+    which = sys.argv[1:] or ["schedule", "ddim", "ddim_multicond", "unet", "vae", "vae_enc", "resampler"]
     with torch.no_grad():
         for w in which:
             globals()["gen_" + w]()

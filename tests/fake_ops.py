@@ -250,10 +250,11 @@ def small_linear(x, w, b, silu_in=False, add=None):
     return y if add is None else y + add
 
 
-def ddim_update(x, v_cond, v_uncond, noise, sc):
+def ddim_update(x, v_cond, v_uncond, noise, sc, v_uncond_img=None, cfg_img=0.0):
     from oracle import lvdm_oracle as O
     arr = np.asarray([0.0, sc["a_prev"], sc["sigma_t"], 0.0, sc["scale_t"], sc["prev_scale_t"]], dtype=np.float32)
-    return O.ddim_update(x, v_cond, v_uncond, arr, sc["sqrt_ac_t"], sc["sqrt_1mac_t"], noise, sc["cfg_scale"], sc["guidance_rescale"])
+    return O.ddim_update(x, v_cond, v_uncond, arr, sc["sqrt_ac_t"], sc["sqrt_1mac_t"], noise, sc["cfg_scale"], sc["guidance_rescale"],
+                         v_uncond_img=v_uncond_img, cfg_img=cfg_img)
 
 
 def install(monkeypatch):

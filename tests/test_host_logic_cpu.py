@@ -220,3 +220,93 @@ def test_resampler_wiring_matches_reference_golden(cpu_ops, golden_dir):
     assert float(err.max()) < 0.03 and float(err.mean()) < 0.004, (float(err.max()), float(err.mean()))
     with pytest.raises(NotImplementedError):
         Resampler(dim_head=32)
+
+
+@pytest.mark.parametrize("tag,S,cfg_img", [("S5", 5, 2.5), ("S8", 8, None)])
+def test_multicond_sampler_matches_reference_golden(cpu_ops, golden_dir, tag, S, cfg_img):
+    """viewcrafter_b200.ddim_multiplecond.DDIMSampler (three apply_model calls, un-fixed scale_arr_prev[0]) driving the toy
+    denoiser through the reference-shaped model interface vs the output of the unmodified reference sampler."""
+    from viewcrafter_b200.ddim_multiplecond import DDIMSampler
+    from viewcrafter_b200.diffusion import LatentDiffusion
+    g = np.load(os.path.join(golden_dir, "ddim_multicond_small.npz"))
+    model = LatentDiffusion(dict(UNET_PARAMS, model_channels=64), None, base_scale=0.3).eval()
+    calls = []
+
+    def toy(x, t, c, **kw):
+        calls.append(sorted(kw))
+        return torch.tanh(0.7 * x * c["k"] + 0.05 * torch.sin(t.float())[:, None, None, None, None]) + 0.1 * c["b"]
+
+    model.apply_model = toy
+    noises = iter(torch.from_numpy(g[f"{tag}_noises"]))
+    cond = {"k": torch.tensor([1.3]), "b": torch.from_numpy(g[f"{tag}_cond_b"])}
+    unc = {"k": torch.tensor([0.4]), "b": torch.from_numpy(g[f"{tag}_uncond_b"])}
+    unc_img = {"k": torch.tensor([0.9]), "b": torch.from_numpy(g[f"{tag}_uncond_img_b"])}
+    import viewcrafter_b200.ddim_multiplecond as mod
+    real_randn = torch.randn
+    try:
+        mod.torch.randn = lambda shape, device=None: next(noises)                       # inject the recorded per-step draws
+        smp = DDIMSampler(model)
+        out, inter = smp.sample(S=S, batch_size=1, shape=(4, 3, 4, 6), conditioning=cond, eta=1.0, verbose=False,
+                                x_T=torch.from_numpy(g[f"{tag}_x_T"]), unconditional_guidance_scale=7.5,
+                                unconditional_conditioning=unc, timestep_spacing="uniform_trailing", guidance_rescale=0.7,
+                                cfg_img=cfg_img, unconditional_conditioning_img_nonetext=unc_img)
+    finally:
+        mod.torch.randn = real_randn
+    assert np.array_equal(smp.ddim_scale_arr_prev.numpy(), g[f"{tag}_scale_prev"])
+    assert len(calls) == 3 * S and len(inter["x_inter"]) == int(g[f"{tag}_n_inter"])
+    np.testing.assert_allclose(out.numpy(), g[f"{tag}_samples"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(inter["pred_x0"][-1].numpy(), g[f"{tag}_pred_x0_last"], rtol=0, atol=5e-5)
+    with pytest.raises(KeyError):                                                       # ddim_multiplecond.py:224 indexes kwargs
+        smp.p_sample_ddim(torch.zeros(1, 4, 3, 4, 6), cond, torch.tensor([999]), index=S - 1)
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_image_guided_synthesis_vs_oracle(cpu_ops, multi):
+    """viewcrafter_b200.synthesis.image_guided_synthesis (utils/diffusion_utils.py:117-201): conditioning construction, hybrid
+    concat of the per-frame encoded renders, CFG (2-way / 3-way), n_samples loop, decode and the [b, n, c, t, h, w] layout,
+    with every RNG draw (posterior noise per frame, x_T, per-step noise, per sample) in the reference's order."""
+    from viewcrafter_b200.diffusion import LatentDiffusion
+    from viewcrafter_b200.synthesis import image_guided_synthesis
+    model = LatentDiffusion(dict(UNET_PARAMS, model_channels=64), dict(ddconfig=dict(VAE_DDCONFIG, ch=32), embed_dim=4), base_scale=0.7).eval()
+    sd = synth.synth_state_dict(synth.module_shapes(model.model.diffusion_model), seed=71)
+    model.model.diffusion_model.load_state_dict(sd, strict=True)
+    sdv = synth.synth_state_dict(synth.module_shapes(model.first_stage_model), seed=72)
+    model.first_stage_model.load_state_dict(sdv, strict=True)
+    g = torch.Generator().manual_seed(73)
+    W_img, txt, txt_empty = torch.randn(3 * 4 * 4, 256 * 8, generator=g) * 0.1, torch.randn(1, 77, 1024, generator=g), torch.randn(1, 77, 1024, generator=g)
+    model.embedder = lambda img: torch.nn.functional.adaptive_avg_pool2d(img, 4).reshape(img.shape[0], 1, -1)            # [b, 1, 48]
+    model.image_proj_model = lambda e: (e @ W_img).reshape(e.shape[0], 256, 8).repeat(1, 1, 128)                           # [b, 256, 1024]
+    model.get_learned_conditioning = lambda prompts: torch.cat([txt_empty if p == "" else txt for p in prompts], 0)
+    model.uncond_type = "empty_seq"
+    T, H, W, S, n_samples = 2, 8, 8, 2, 2
+    videos = torch.rand(1, 3, T, 8 * H, 8 * W, generator=g) * 2 - 1
+    shape = (1, 4, T, H, W)
+    torch.manual_seed(74)
+    out = image_guided_synthesis(model, ["a photo"], videos, list(shape), n_samples=n_samples, ddim_steps=S, ddim_eta=1.0,
+                                 unconditional_guidance_scale=7.5, cfg_img=(2.0 if multi else None), fs=10, text_input=True,
+                                 multiple_cond_cfg=multi, timestep_spacing="uniform_trailing", guidance_rescale=0.7, condition_index=[0])
+    assert out.shape == (1, n_samples, 3, T, 8 * H, 8 * W)
+    # replay the draws in the reference's order and rebuild the expected result with the oracle
+    torch.manual_seed(74)
+    enc_noise = [torch.randn(1, 4, H, W) for _ in range(T)]
+    img = videos[:, :, 0]
+    ctx = lambda t, im: torch.cat([t, model.image_proj_model(model.embedder(im))], 1)
+    ctx_c, ctx_u, ctx_i = ctx(txt, img), ctx(txt_empty, torch.zeros_like(img)), ctx(txt_empty, img)
+    fs = torch.tensor([10])
+    with torch.no_grad():
+        cc = O.encode_first_stage(sdv, videos, enc_noise)
+    sched = O.model_schedule(base_scale=0.7)
+
+    def model_fn(x, t, cond):
+        with torch.no_grad():
+            return O.unet_forward(sd, torch.cat([x, cc], 1), t, cond, fs)
+
+    for k in range(n_samples):
+        x_T = torch.randn(shape)
+        noises = [torch.randn(shape) for _ in range(S)]
+        extra = dict(fixed_prev_scale=False, uncond_img=ctx_i, cfg_img=2.0) if multi else {}
+        ref, _ = O.ddim_sample(model_fn, sched, shape, S, ctx_c, ctx_u, x_T, noises, **extra)
+        with torch.no_grad():
+            ref_img = O.decode_first_stage(sdv, ref)
+        err = (out[:, k] - ref_img).abs()
+        assert float(err.mean()) < 0.03 * max(1.0, float(ref_img.std())), (k, float(err.mean()), float(ref_img.std()))

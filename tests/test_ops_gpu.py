@@ -315,6 +315,32 @@ def test_ddim_update_matches_oracle(ops, cfg, gr):
         close(x0.cpu(), ref_x0, 2e-5, rtol=2e-5, what=f"pred_x0 index {index}")
 
 
+@pytest.mark.parametrize("gr", [0.0, 0.7])
+def test_ddim_update_three_way_cfg_matches_oracle(ops, gr):
+    """vc_ddim_update3: u + cfg_img (v_img - u) + s (v_cond - v_img) (ddim_multiplecond.py:227-233) + the shared tail."""
+    from oracle import lvdm_oracle as O
+    sched = O.model_schedule(base_scale=0.3)
+    tab = O.ddim_tables(sched, 50, "uniform_trailing", 1.0, fixed_prev_scale=False)
+    shape = (1, 4, 5, 8, 16)
+    g = torch.Generator().manual_seed(65)
+    x, vc_, vu, vi, nz = (torch.randn(shape, generator=g) for _ in range(5))
+    for index in (49, 0):
+        step = int(tab["timesteps"][index])
+        sc = O.step_scalars(tab, index)
+        sa, s1 = sched["sqrt_alphas_cumprod"][step].item(), sched["sqrt_one_minus_alphas_cumprod"][step].item()
+        ref_prev, ref_x0 = O.ddim_update(x, vc_, vu, sc, sa, s1, nz, 7.5, gr, v_uncond_img=vi, cfg_img=2.5)
+        d = dict(cfg_scale=7.5, guidance_rescale=gr, sqrt_ac_t=sa, sqrt_1mac_t=s1, a_prev=float(sc[1]), sigma_t=float(sc[2]),
+                 scale_t=float(sc[4]), prev_scale_t=float(sc[5]))
+        xp, x0 = ops.ddim_update(x.cuda(), vc_.cuda(), vu.cuda(), nz.cuda(), d, v_uncond_img=vi.cuda(), cfg_img=2.5)
+        close(xp.cpu(), ref_prev, 5e-5, rtol=2e-5, what=f"3-way x_prev index {index}")
+        close(x0.cpu(), ref_x0, 5e-5, rtol=2e-5, what=f"3-way pred_x0 index {index}")
+
+
+def test_gelu_matches_torch(ops):
+    x = rnd(257, 4096, seed=66, scale=2.0)
+    close(ops.gelu_f16(x), torch.nn.functional.gelu(x.float()), 2e-3, rtol=2e-3, what="gelu")
+
+
 def test_linear_strided_weight_view(ops):
     """w may be a column slice of a wider matrix (the VAE attention uses K = fused-QK[:, C:] as the 'weight')."""
     M, C = 300, 512

@@ -124,3 +124,21 @@ def test_resampler_matches_reference(golden_dir):
         y = O.resampler_forward(sd, torch.from_numpy(g["x"]), heads=kw["heads"], dim_head=kw["dim_head"])
     assert y.shape == (2, kw["num_queries"] * kw["video_length"], kw["output_dim"])
     np.testing.assert_allclose(y.numpy(), g["y"], rtol=0, atol=5e-5)
+
+
+@pytest.mark.parametrize("tag,S,cfg_img", [("S5", 5, 2.5), ("S8", 8, None)])
+def test_ddim_multicond_loop_matches_reference(golden_dir, tag, S, cfg_img):
+    """Three-way CFG sampler: the unmodified lvdm/models/samplers/ddim_multiplecond.py on the toy denoiser."""
+    g = _load(golden_dir, "ddim_multicond_small.npz")
+    sched = O.model_schedule(base_scale=0.3)
+    x_T = torch.from_numpy(g[f"{tag}_x_T"])
+    noises = [torch.from_numpy(n) for n in g[f"{tag}_noises"]]
+    cond = {"k": torch.tensor([1.3]), "b": torch.from_numpy(g[f"{tag}_cond_b"])}
+    unc = {"k": torch.tensor([0.4]), "b": torch.from_numpy(g[f"{tag}_uncond_b"])}
+    unc_img = {"k": torch.tensor([0.9]), "b": torch.from_numpy(g[f"{tag}_uncond_img_b"])}
+    tab = O.ddim_tables(sched, S, "uniform_trailing", 1.0, fixed_prev_scale=False)
+    assert np.array_equal(tab["scale_prev"].numpy(), g[f"{tag}_scale_prev"])           # the un-fixed [0] entry (ddim_multiplecond.py:33)
+    out, inter = O.ddim_sample(_toy, sched, x_T.shape, S, cond, unc, x_T, noises, fixed_prev_scale=False, uncond_img=unc_img, cfg_img=cfg_img)
+    assert len(inter["x_inter"]) == int(g[f"{tag}_n_inter"])
+    np.testing.assert_allclose(out.numpy(), g[f"{tag}_samples"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(inter["pred_x0"][-1].numpy(), g[f"{tag}_pred_x0_last"], rtol=0, atol=2e-5)

@@ -117,7 +117,7 @@ def test_unet_full_width_block_stack_vs_oracle():
     x = torch.randn(1, 8, 3, 8, 16, generator=g)
     ctx = torch.randn(1, 333, 1024, generator=g)
     t, fs = torch.tensor([499]), torch.tensor([10])
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(max(1, min(os.cpu_count() or 1, 16)))
     with torch.no_grad():
         ref = O.unet_forward(sd, x, t, ctx, fs)
     y = m(x.cuda(), t.cuda(), context=ctx.cuda(), fs=fs.cuda())

@@ -38,7 +38,7 @@ static constexpr int ATT_SMEM = ATT_TILE_BYTES * 5 + 1024 + 256;       // Q + 2x
 static constexpr float ATT_LAZY = 8.0f;                                // rescale only if the max grew by > 2^8
 // A/B switches (side-by-side builds: VC_NVCC_EXTRA="-DVC_ATT_SPLIT_KV=0 ..." + VC_OUT, loaded through VC_B200_LIB)
 #ifndef VC_ATT_SPLIT_KV
-#define VC_ATT_SPLIT_KV 0      // separate K / V rings (0: one ring, a stage is freed when its P V retires)
+#define VC_ATT_SPLIT_KV 1      // separate K / V rings (0: one ring, a stage is freed when its P V retires)
 #endif
 #ifndef VC_ATT_PARKED_WAIT
 #define VC_ATT_PARKED_WAIT 0   // TMA / MMA warps wait with a suspend hint + nanosleep back-off instead of spinning

@@ -141,7 +141,17 @@ int vc_ddim_update(const float* x, const float* v_cond, const float* v_uncond, c
   d.cfg_scale = s->cfg_scale; d.guidance_rescale = s->guidance_rescale; d.sqrt_ac_t = s->sqrt_ac_t; d.sqrt_1mac_t = s->sqrt_1mac_t;
   d.a_prev = s->a_prev; d.sigma_t = s->sigma_t; d.scale_t = s->scale_t; d.prev_scale_t = s->prev_scale_t; d.use_cfg = s->use_cfg;
   COUNT((d.use_cfg && d.guidance_rescale > 0.f) ? 2 : 1);
-  return ddim_update(x, v_cond, v_uncond, noise, x_prev, pred_x0, n, d, reinterpret_cast<double*>(ws), ST(stream));
+  return ddim_update(x, v_cond, v_uncond, nullptr, 0.f, noise, x_prev, pred_x0, n, d, reinterpret_cast<double*>(ws), ST(stream));
+}
+int vc_ddim_update3(const float* x, const float* v_cond, const float* v_uncond, const float* v_uncond_img, float cfg_img,
+                    const float* noise, float* x_prev, float* pred_x0, int64_t n, const vc_ddim_scalars* s, void* ws, void* stream) {
+  if (!s) { set_error("vc_ddim_update3: null scalars"); return VC_ERR_ARG; }
+  if (!v_uncond_img) { set_error("vc_ddim_update3: null image-only branch"); return VC_ERR_ARG; }
+  DdimStepScalars d;
+  d.cfg_scale = s->cfg_scale; d.guidance_rescale = s->guidance_rescale; d.sqrt_ac_t = s->sqrt_ac_t; d.sqrt_1mac_t = s->sqrt_1mac_t;
+  d.a_prev = s->a_prev; d.sigma_t = s->sigma_t; d.scale_t = s->scale_t; d.prev_scale_t = s->prev_scale_t; d.use_cfg = s->use_cfg;
+  COUNT((d.use_cfg && d.guidance_rescale > 0.f) ? 2 : 1);
+  return ddim_update(x, v_cond, v_uncond, v_uncond_img, cfg_img, noise, x_prev, pred_x0, n, d, reinterpret_cast<double*>(ws), ST(stream));
 }
 
 }  // extern "C"

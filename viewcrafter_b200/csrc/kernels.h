@@ -85,7 +85,8 @@ struct DdimStepScalars {
   float scale_t, prev_scale_t;      // dynamic rescale
   int use_cfg;
 };
-int ddim_update(const float* x, const float* v_cond, const float* v_uncond, const float* noise, float* x_prev, float* pred_x0,
-                long long n, const DdimStepScalars& s, double* ws, cudaStream_t stream);
+// v_uncond_img != nullptr: three-way CFG of ddim_multiplecond.py:227-233 with weight cfg_img on the image-only branch
+int ddim_update(const float* x, const float* v_cond, const float* v_uncond, const float* v_uncond_img, float cfg_img, const float* noise,
+                float* x_prev, float* pred_x0, long long n, const DdimStepScalars& s, double* ws, cudaStream_t stream);
 
 }  // namespace vc

@@ -215,11 +215,19 @@ int timestep_embedding_f32(const long long* t, int n, int dim, float* out, cudaS
 // Fused DDIM update (ddim.py:228-281 + utils_diffusion.py:147-158), v-parameterisation, batch 1 per call.
 // pass 1: double-precision sums for the two unbiased stds; pass 2: elementwise update.
 // ------------------------------------------------------------------------------------------------
-__global__ void ddim_stats_kernel(const float* __restrict__ vc_, const float* __restrict__ vu, long long n, float cfg, double* ws) {
+// CFG combine.  Two-way (ddim.py:226): u + s (c - u).  Three-way (ddim_multiplecond.py:233, vi = the "image, no text"
+// branch): u + s_img (vi - u) + s (c - vi), evaluated left to right like the reference expression.
+__device__ __forceinline__ float cfg_combine(float c, float u, const float* __restrict__ vi, long long i, float cfg, float cfg_img) {
+  if (vi == nullptr) return u + cfg * (c - u);
+  const float w = vi[i];
+  return (u + cfg_img * (w - u)) + cfg * (c - w);
+}
+__global__ void ddim_stats_kernel(const float* __restrict__ vc_, const float* __restrict__ vu, const float* __restrict__ vi, long long n,
+                                  float cfg, float cfg_img, double* ws) {
   double s1 = 0, q1 = 0, s2 = 0, q2 = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float c = vc_[i], u = vu[i];
-    const float m = u + cfg * (c - u);
+    const float m = cfg_combine(c, u, vi, i, cfg, cfg_img);
     s1 += c; q1 += (double)c * c;
     s2 += m; q2 += (double)m * m;
   }
@@ -233,6 +241,7 @@ __global__ void ddim_stats_kernel(const float* __restrict__ vc_, const float* __
   }
 }
 __global__ void ddim_apply_kernel(const float* __restrict__ x, const float* __restrict__ vc_, const float* __restrict__ vu,
+                                  const float* __restrict__ vi, float cfg_img,
                                   const float* __restrict__ noise, float* __restrict__ x_prev, float* __restrict__ pred_x0,
                                   long long n, DdimStepScalars s, const double* ws) {
   float factor = 1.f;
@@ -250,7 +259,7 @@ __global__ void ddim_apply_kernel(const float* __restrict__ x, const float* __re
     float m = c;
     if (s.use_cfg) {
       const float u = vu[i];
-      m = u + s.cfg_scale * (c - u);
+      m = cfg_combine(c, u, vi, i, s.cfg_scale, cfg_img);
       if (s.guidance_rescale > 0.f) m = s.guidance_rescale * (m * factor) + (1.f - s.guidance_rescale) * m;
     }
     const float xi = x[i];
@@ -261,17 +270,18 @@ __global__ void ddim_apply_kernel(const float* __restrict__ x, const float* __re
     x_prev[i] = sq_ap * p0 + dir_c * e_t + s.sigma_t * noise[i];
   }
 }
-int ddim_update(const float* x, const float* v_cond, const float* v_uncond, const float* noise, float* x_prev, float* pred_x0,
-                long long n, const DdimStepScalars& s, double* ws, cudaStream_t stream) {
+int ddim_update(const float* x, const float* v_cond, const float* v_uncond, const float* v_uncond_img, float cfg_img, const float* noise,
+                float* x_prev, float* pred_x0, long long n, const DdimStepScalars& s, double* ws, cudaStream_t stream) {
   VC_REQUIRE(x && v_cond && noise && x_prev && pred_x0 && ws && n > 1, "ddim_update: bad args");
   VC_REQUIRE(!s.use_cfg || v_uncond, "ddim_update: CFG needs the unconditional output");
+  VC_REQUIRE(!v_uncond_img || s.use_cfg, "ddim_update: the image-only branch is only defined with CFG on");
   const int blocks = (int)min((long long)sm_count() * 4, (n + 255) / 256);
   if (s.use_cfg && s.guidance_rescale > 0.f) {
     VC_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4 * sizeof(double), stream));
-    ddim_stats_kernel<<<blocks, 256, 0, stream>>>(v_cond, v_uncond, n, s.cfg_scale, ws);
+    ddim_stats_kernel<<<blocks, 256, 0, stream>>>(v_cond, v_uncond, v_uncond_img, n, s.cfg_scale, cfg_img, ws);
     VC_CHECK_CUDA(cudaGetLastError());
   }
-  ddim_apply_kernel<<<blocks, 256, 0, stream>>>(x, v_cond, v_uncond, noise, x_prev, pred_x0, n, s, ws);
+  ddim_apply_kernel<<<blocks, 256, 0, stream>>>(x, v_cond, v_uncond, v_uncond_img, cfg_img, noise, x_prev, pred_x0, n, s, ws);
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -12,7 +12,7 @@ namespace vc {
 
 static constexpr int GN_MAX_SPLITS = 512;
 #ifndef VC_GN_REVERSE
-#define VC_GN_REVERSE 0      // A/B switch: normalise pass walks its rows backwards (L2 reuse of the statistics pass)
+#define VC_GN_REVERSE 1      // A/B switch: normalise pass walks its rows backwards (L2 reuse of the statistics pass)
 #endif
 
 size_t groupnorm_ws_bytes(int samples) { return (size_t)samples * GN_MAX_SPLITS * 64 * sizeof(float) + (size_t)samples * sizeof(unsigned int); }

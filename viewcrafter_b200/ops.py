@@ -409,9 +409,10 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], si
 _ddim_ws = {}
 
 
-def ddim_update(x, v_cond, v_uncond, noise, sc: dict):
-    """Fused ddim.py:228-281.  sc: cfg_scale, guidance_rescale, sqrt_ac_t, sqrt_1mac_t, a_prev, sigma_t, scale_t, prev_scale_t."""
-    for t in (x, v_cond, noise):
+def ddim_update(x, v_cond, v_uncond, noise, sc: dict, v_uncond_img=None, cfg_img: float = 0.0):
+    """Fused ddim.py:228-281.  sc: cfg_scale, guidance_rescale, sqrt_ac_t, sqrt_1mac_t, a_prev, sigma_t, scale_t, prev_scale_t.
+    v_uncond_img / cfg_img: the third ("image, no text") branch of ddim_multiplecond.py:227-233."""
+    for t in (x, v_cond, noise) + ((v_uncond_img,) if v_uncond_img is not None else ()):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
     s = DdimScalars()
     use_cfg = v_uncond is not None and sc["cfg_scale"] != 1.0
@@ -424,6 +425,11 @@ def ddim_update(x, v_cond, v_uncond, noise, sc: dict):
         ws = torch.zeros(4, device=x.device, dtype=torch.float64)
         _ddim_ws[x.device] = ws
     x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
+    if v_uncond_img is not None and use_cfg:
+        check(_lib.load().vc_ddim_update3(x.data_ptr(), v_cond.data_ptr(), v_uncond.data_ptr(), v_uncond_img.data_ptr(), float(cfg_img),
+                                          noise.data_ptr(), x_prev.data_ptr(), pred_x0.data_ptr(), x.numel(), C.byref(s), ws.data_ptr(),
+                                          _stream()), "vc_ddim_update3")
+        return x_prev, pred_x0
     check(_lib.load().vc_ddim_update(x.data_ptr(), v_cond.data_ptr(), _ptr(v_uncond) if use_cfg else None, noise.data_ptr(),
                                      x_prev.data_ptr(), pred_x0.data_ptr(), x.numel(), C.byref(s), ws.data_ptr(), _stream()),
           "vc_ddim_update")
