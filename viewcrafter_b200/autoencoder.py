@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .distributions import DiagonalGaussianDistribution
+from .distributions import DiagonalGaussianDistribution, posterior_class
 
 
 def _gn(c):
@@ -301,4 +301,4 @@ class AutoencoderKL(nn.Module):
 
     def encode(self, x, **kwargs):
         """-> DiagonalGaussianDistribution(moments)  (autoencoder.py:97-102); moments are fp32."""
-        return DiagonalGaussianDistribution(self.encode_moments(x))
+        return posterior_class()(self.encode_moments(x))
