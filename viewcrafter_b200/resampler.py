@@ -76,6 +76,8 @@ class Resampler(nn.Module):
                                                     _feed_forward(dim=dim, mult=ff_mult)]) for _ in range(depth)])
         self.heads = heads
         self._packed = None
+        # fires for a load through any ancestor too (VIPLatentDiffusion.load_state_dict, diffusion_utils.py:83-108)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     # weights are packed (fp16, K-contiguous) once per load / device move
     def invalidate_packed(self):
@@ -84,10 +86,6 @@ class Resampler(nn.Module):
     def _apply(self, fn, *a, **k):
         self._packed = None
         return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._packed = None
-        return super().load_state_dict(*a, **k)
 
     def _pack(self):
         ops.require_cuda(self.latents.device, "viewcrafter_b200.Resampler")
