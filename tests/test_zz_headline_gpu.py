@@ -32,8 +32,9 @@ def test_attention_rows_sum_to_one_and_match_fp32_at_9216_keys(ops):
     g = torch.Generator().manual_seed(91)
     qkv = (torch.randn(B * N, 3 * C, generator=g) * 0.7).half().cuda()
     q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
-    ones = torch.ones_like(v)
-    out1 = ops.flash_attn(q, k, ones, B, N, N, heads).float()
+    qk1 = qkv.clone()
+    qk1[:, 2 * C:] = 1.0                                                # V = ones, in the same [rows, 3C] layout (k and v share a row pitch)
+    out1 = ops.flash_attn(qk1[:, :C], qk1[:, C:2 * C], qk1[:, 2 * C:], B, N, N, heads).float()
     assert float((out1 - 1.0).abs().max()) < 2e-3                      # fp16 P, fp32 row sum: |sum p / l - 1| is a few fp16 ulps
     out = ops.flash_attn(q, k, v, B, N, N, heads)
     for b, h in ((0, 0), (1, 4)):
