@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
 }
 
 int flash_attn_d64(const AttnDesc& d, cudaStream_t stream) {
+  if (flash_attn_bn64_enabled()) return flash_attn_d64_bn64(d, stream);      // opt-in experiment (VC_ATTN_BN64=1), off by default
   VC_REQUIRE(d.q && d.k && d.v && d.out, "flash_attn: null pointer");
   VC_REQUIRE(d.Nq > 0 && d.Nk > 0 && d.B > 0 && d.heads > 0, "flash_attn: empty problem");
   VC_REQUIRE(d.ldq % 8 == 0 && d.ldk % 8 == 0 && d.ldv % 8 == 0 && d.ldo % 8 == 0, "flash_attn: pitches must be multiples of 8");
