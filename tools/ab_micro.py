@@ -16,7 +16,7 @@ def t(fn, reps=5):
     return e0.elapsed_time(e1) / reps * 1e-3
 
 
-tag = os.path.basename(_lib.LIB_PATH) + ("+bn64" if os.environ.get("VC_ATTN_BN64") == "1" else "")
+tag = os.path.basename(_lib.LIB_PATH) + ("+bn64" if os.environ.get("VC_ATTN_BN64") == "1" else "") + ("+lnunroll" if os.environ.get("VC_LN_STATS_UNROLL") == "1" else "")
 T = 25
 torch.manual_seed(0)
 for name, HW, heads in (("l0", 9216, 5), ("l1", 2304, 10), ("l2", 576, 20)):
@@ -46,3 +46,11 @@ for name, H, W, C, samples in (("l0 4-D", 72, 128, 320, 25), ("l0 4-D B=2", 72, 
     ref = ((xr - mu) * torch.rsqrt(var + 1e-5)).reshape(M, C) * g + b
     ref = ref * torch.sigmoid(ref)
     print(f"[{tag}] groupnorm {name:10s} C={C:4d}: {dt*1e6:8.1f} us  {2.0*M*C*2/dt/1e9:7.1f} GB/s (r+w once)  max err {float((y-ref).abs().max()):.2e}")
+for name, M, C in (("l0", 230400, 320), ("l1", 57600, 640), ("l2", 14400, 1280), ("init", 230400, 512)):
+    x = (torch.randn(M, C, device="cuda") * 0.8 + 0.3).half()
+    dt = t(lambda: ops.layernorm_stats(x))
+    st = ops.layernorm_stats(x)
+    xf = x.float()
+    ref_mean, ref_rstd = xf.mean(1), torch.rsqrt(xf.var(1, unbiased=False) + 1e-5)
+    err = max(float((st[:, 0] - ref_mean).abs().max()), float(((st[:, 1] - ref_rstd) / ref_rstd).abs().max()))
+    print(f"[{tag}] ln_stats {name:4s} C={C:4d}: {dt*1e6:8.1f} us  {M*C*2/dt/1e9:7.1f} GB/s  max err {err:.2e}")

@@ -9,6 +9,7 @@ for lib in viewcrafter_b200/libvc_b200.so viewcrafter_b200/libvc_b200_*.so; do
   VC_B200_LIB=$PWD/$lib timeout 120 python tools/ab_micro.py 2>&1 | grep -E "^\[" >> gpurun_out/ab_micro.log
 done
 # opt-in experiments selected by environment (same default library)
+VC_LN_STATS_UNROLL=1 timeout 120 python tools/ab_micro.py 2>&1 | grep -E "^\[.*ln_stats|Error|error" >> gpurun_out/ab_micro.log
 VC_ATTN_BN64=1 timeout 120 python tools/ab_micro.py 2>&1 | grep -E "^\[|Error|error" >> gpurun_out/ab_micro.log
 cat gpurun_out/ab_micro.log
 timeout 200 python bench.py --steps 4 --warmup 3 2>gpurun_out/ab_bench.err | tail -1 > gpurun_out/ab_bench_default.json; cut -c1-160 gpurun_out/ab_bench_default.json

@@ -455,6 +455,74 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const __half* __restrict_
   }
 }
 
+// EXPERIMENTAL, OPT-IN (VC_LN_STATS_UNROLL=1), not yet run on a GPU: the same statistics with every 16-byte load of a
+// warp's 4 rows issued before the first conversion (ITERS x 4 loads in flight per lane instead of 4): ncu shows the loop
+// above reading at 2.9 TB/s (44 % of the HBM peak) with half of the warp slots idle.  Arithmetic and rounding order per
+// lane are those of ln_stats_kernel, so the results are bit-identical.
+template <int ITERS>
+__global__ void __launch_bounds__(256) ln_stats_unrolled_kernel(const __half* __restrict__ x, long long rows, int C, float eps,
+                                                                float2* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int vecs = C >> 3;
+  const float invC = 1.f / (float)C;
+  for (long long row0 = gw * 4; row0 < rows; row0 += nwarps * 4) {
+    float piv[4], s[4], q[4];
+    const __half* rp[4];
+    uint4 u[ITERS][4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const long long row = min(row0 + rr, rows - 1);
+      rp[rr] = x + row * C;
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int v = lane + it * 32;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) u[it][rr] = v < vecs ? *reinterpret_cast<const uint4*>(rp[rr] + v * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      piv[rr] = __half2float(__ldg(rp[rr]));
+      s[rr] = q[rr] = 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      if (lane + it * 32 < vecs) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const __half2* h = reinterpret_cast<const __half2*>(&u[it][rr]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            const float a = f.x - piv[rr], b = f.y - piv[rr];
+            s[rr] += a + b;
+            q[rr] = fmaf(a, a, fmaf(b, b, q[rr]));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s[rr] += __shfl_xor_sync(0xffffffffu, s[rr], o);
+        q[rr] += __shfl_xor_sync(0xffffffffu, q[rr], o);
+      }
+    }
+    if (lane < 4 && row0 + lane < rows) {
+      float sm = s[0], qm = q[0], pm = piv[0];
+#pragma unroll
+      for (int rr = 1; rr < 4; ++rr)
+        if (lane == rr) { sm = s[rr]; qm = q[rr]; pm = piv[rr]; }
+      const float d = sm * invC;
+      const float var = fmaxf(qm * invC - d * d, 0.f);
+      stats[row0 + lane] = make_float2(pm + d, rsqrtf(var + eps));
+    }
+  }
+}
+
 int layernorm_stats(const __half* x, long long rows, int C, float eps, float* stats, cudaStream_t stream) {
   VC_REQUIRE(x && stats, "layernorm_stats: null pointer");
   VC_REQUIRE(C % 8 == 0 && C <= 8192 && rows > 0, "layernorm_stats: unsupported C=%d rows=%lld", C, rows);
@@ -463,7 +531,15 @@ int layernorm_stats(const __half* x, long long rows, int C, float eps, float* st
   long long blocks = (rows + 4 * wpb - 1) / (4 * wpb);
   const long long cap = (long long)sm_count() * 8;              // 8 x 256 threads = 64 warps per SM
   if (blocks > cap) blocks = cap;
-  ln_stats_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, eps, reinterpret_cast<float2*>(stats));
+  static int unroll = -1;                       // opt-in experiment VC_LN_STATS_UNROLL=1 (widths up to 4 x 256 channels)
+  if (unroll < 0) { const char* e = getenv("VC_LN_STATS_UNROLL"); unroll = (e && e[0] == '1') ? 1 : 0; }
+  const int iters = (C / 8 + 31) / 32;
+  if (unroll && iters <= 2)
+    ln_stats_unrolled_kernel<2><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, eps, reinterpret_cast<float2*>(stats));
+  else if (unroll && iters <= 4)
+    ln_stats_unrolled_kernel<4><<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, eps, reinterpret_cast<float2*>(stats));
+  else
+    ln_stats_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(x, rows, C, eps, reinterpret_cast<float2*>(stats));
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;
 }
