@@ -64,8 +64,10 @@ def _toys():
     sys.modules["vc_test_toys"] = m
 
 
-@pytest.mark.parametrize("multi", [False, True])
-def test_reference_pipeline_with_dropins_matches_reference(monkeypatch, multi):
+@pytest.mark.parametrize("multi,T", [(False, 16), (True, 16), (False, 5)])
+def test_reference_pipeline_with_dropins_matches_reference(monkeypatch, multi, T):
+    """T = 16: 77 + 16 T = 333 context tokens -> per-frame image tokens (openaimodel3d.py:556-560); T = 5: the shared-context
+    branch the 25-frame checkpoints take."""
     import yaml
     ref_shims.install()
     _toys()
@@ -98,7 +100,7 @@ def test_reference_pipeline_with_dropins_matches_reference(monkeypatch, multi):
     assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
     mine.load_state_dict(sd, strict=True)                # load_model_checkpoint(..., strict=True), diffusion_utils.py:83-108
 
-    T, H, W = 16, 8, 8
+    H, W = 8, 8
     videos = torch.rand(1, 3, T, 8 * H, 8 * W, generator=torch.Generator().manual_seed(7)) * 2 - 1
     kw = dict(n_samples=1, ddim_steps=(1 if multi else 2), ddim_eta=1.0, unconditional_guidance_scale=7.5, cfg_img=(2.0 if multi else None),
               fs=10, text_input=True, multiple_cond_cfg=multi, timestep_spacing="uniform_trailing", guidance_rescale=0.7, condition_index=[0])
