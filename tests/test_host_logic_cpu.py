@@ -310,3 +310,25 @@ def test_image_guided_synthesis_vs_oracle(cpu_ops, multi):
             ref_img = O.decode_first_stage(sdv, ref)
         err = (out[:, k] - ref_img).abs()
         assert float(err.mean()) < 0.03 * max(1.0, float(ref_img.std())), (k, float(err.mean()), float(ref_img.std()))
+
+
+def test_posterior_class_subclasses_a_loaded_reference_class(monkeypatch):
+    """AutoencoderKL.encode must return an instance of the reference's DiagonalGaussianDistribution whenever lvdm.distributions
+    is loaded (ddpm3d.py:611-618 type-checks it); checked here with a stand-in module so that it also runs without /root/reference."""
+    import sys
+    import types
+    from viewcrafter_b200 import distributions as D
+    ref_mod = types.ModuleType("lvdm.distributions")
+
+    class RefDGD(object):
+        pass
+
+    ref_mod.DiagonalGaussianDistribution = RefDGD
+    monkeypatch.setitem(sys.modules, "lvdm.distributions", ref_mod)
+    cls = D.posterior_class()
+    post = cls(torch.zeros(1, 8, 2, 2))
+    assert isinstance(post, RefDGD) and isinstance(post, D.DiagonalGaussianDistribution)
+    assert D.posterior_class() is cls                                                   # cached per reference class
+    assert post.sample(noise=torch.ones(1, 4, 2, 2)).shape == (1, 4, 2, 2)
+    monkeypatch.delitem(sys.modules, "lvdm.distributions")
+    assert D.posterior_class() is D.DiagonalGaussianDistribution
