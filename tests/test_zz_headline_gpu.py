@@ -57,6 +57,21 @@ def test_groupnorm_moments_at_headline_size(ops):
     assert float(mean.abs().max()) < 2e-3 and float((var - 1.0).abs().max()) < 5e-3, (float(mean.abs().max()), float((var - 1).abs().max()))
 
 
+def test_split_groupnorm_path_equals_fused_single_launch(ops):
+    """The statistics / (all-reduce) / apply form the frame-sharded 5-D GroupNorm uses across GPUs, run on one GPU at the level-1
+    size, against the fused single-launch kernel (same device functions; the statistics are finalised in a different order)."""
+    B, rows, C = 2, T * 36 * 64, 640
+    g = torch.Generator().manual_seed(95)
+    x = (torch.randn(B * rows, C, generator=g) * 1.3 - 0.2).half().cuda()
+    gam, bet = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.1).cuda()
+    st = ops.groupnorm_stats(x, B)
+    assert st.shape[0] == B and st.numel() == B * 64
+    y_split = ops.groupnorm_apply(x, B, st, rows, gam, bet, 1e-5, True).float()
+    y_fused = ops.groupnorm(x, B, gam, bet, 1e-5, True).float()
+    err = (y_split - y_fused).abs()
+    assert float(err.max()) <= 4e-3 + 2e-3 * float(y_fused.abs().max()) and float(err.mean()) < 2e-4, (float(err.max()), float(err.mean()))
+
+
 def test_batched_cfg_step_equals_two_forwards_at_headline_size():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
