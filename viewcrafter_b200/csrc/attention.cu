@@ -41,7 +41,7 @@ static constexpr float ATT_LAZY = 8.0f;                                // rescal
 #define VC_ATT_SPLIT_KV 1      // separate K / V rings (0: one ring, a stage is freed when its P V retires)
 #endif
 #ifndef VC_ATT_PARKED_WAIT
-#define VC_ATT_PARKED_WAIT 0   // TMA / MMA warps wait with a suspend hint + nanosleep back-off instead of spinning
+#define VC_ATT_PARKED_WAIT 0   // TMA / MMA warps wait through try_wait with a suspend-time hint instead of spinning (measured 3 % slower)
 #endif
 #if VC_ATT_PARKED_WAIT
 #define ATT_ROLE_WAIT mbar_wait_parked
