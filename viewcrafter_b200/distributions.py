@@ -9,42 +9,39 @@ from __future__ import annotations
 
 import sys
 
-import numpy as np
 import torch
 
 
 class DiagonalGaussianDistribution(object):
+    """Posterior q(z|x) = N(mean, diag(exp(logvar))) over the VAE moments ``[N, 2*embed, h, w]``.
+
+    Inference surface only -- what ``get_first_stage_encoding`` / ``encode_first_stage`` touch (ddpm3d.py:611-644):
+    ``parameters``, ``mean``, ``logvar`` (clamped to [-30, 20] like distributions.py:28), ``std``, ``var``,
+    ``deterministic``, ``sample(noise=None)`` and ``mode()``.  The training-time ``kl`` / ``nll`` terms are not on the
+    ViewCrafter inference path; inside the reference repo they are inherited from the reference class (posterior_class)."""
+
+    LOGVAR_RANGE = (-30.0, 20.0)
+
     def __init__(self, parameters, deterministic=False):
+        half = parameters.shape[1] // 2
         self.parameters = parameters
-        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
-        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
-        self.deterministic = deterministic
-        self.std = torch.exp(0.5 * self.logvar)
-        self.var = torch.exp(self.logvar)
+        self.deterministic = bool(deterministic)
+        self.mean = parameters[:, :half]
+        self.logvar = parameters[:, half:].clamp(*self.LOGVAR_RANGE)
         if self.deterministic:
-            self.var = self.std = torch.zeros_like(self.mean).to(device=self.parameters.device)
+            self.std = self.var = torch.zeros_like(self.mean)
+        else:
+            self.var = self.logvar.exp()
+            self.std = (0.5 * self.logvar).exp()
 
     def sample(self, noise=None):
-        if noise is None:
-            noise = torch.randn(self.mean.shape)
-        return self.mean + self.std * noise.to(device=self.parameters.device)
+        # the reference draws on the CPU generator with the shape of the mean and only then moves the draw to the device
+        # (distributions.py:35-36); the order of draws is part of the drop-in contract (tests replay it)
+        eps = torch.randn(self.mean.shape) if noise is None else noise
+        return self.mean + eps.to(device=self.parameters.device) * self.std
 
     def mode(self):
         return self.mean
-
-    def kl(self, other=None):
-        if self.deterministic:
-            return torch.Tensor([0.])
-        if other is None:
-            return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
-        return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var - 1.0 - self.logvar + other.logvar,
-                               dim=[1, 2, 3])
-
-    def nll(self, sample, dims=[1, 2, 3]):
-        if self.deterministic:
-            return torch.Tensor([0.])
-        logtwopi = np.log(2.0 * np.pi)
-        return 0.5 * torch.sum(logtwopi + self.logvar + torch.pow(sample - self.mean, 2) / self.var, dim=dims)
 
 
 _subclass_cache = {}
