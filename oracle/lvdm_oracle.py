@@ -1,10 +1,15 @@
-"""CPU oracle for the ViewCrafter DDIM-denoise hot path.  TEST INFRASTRUCTURE ONLY.
+"""Oracle for the ViewCrafter DDIM-denoise hot path.  TEST INFRASTRUCTURE ONLY.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
 legs of ``bench.py`` may import this file.  Nothing in ``viewcrafter_b200/`` does.
 
-This is a functional (state-dict driven, fp32, torch-CPU) restatement of the reference
-algorithm.  Every function cites the reference file:line (paths relative to the upstream
+This is a functional (state-dict driven, fp32, plain-torch) restatement of the reference
+algorithm.  It is device-agnostic: on the CPU it is the checker of the small parity cases; on a
+CUDA device (tensors + state dict moved there, TF32 off -- see ``exact_fp32``) it is the checker
+at the BASELINE.json sizes (25x4x40x64, 25x4x72x128) where a CPU run takes minutes, and, run under
+``torch.autocast(fp16)`` with ``attention_mode("sdpa")``, it is the stand-in for "the unmodified
+reference in PyTorch eager on the same B200" (viewcrafter.py:98 runs the reference under autocast;
+attention.py:175-190 uses xformers' fused attention when present).  Every function cites the reference file:line (paths relative to the upstream
 repo root) it follows.  The block structure is recovered from the *state-dict keys* (which
 are the reference's load-bearing interface), not from a copy of the
 reference constructor.
@@ -18,6 +23,7 @@ reference modules).
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, List, Optional
 
@@ -27,6 +33,37 @@ import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
 
+_ATTN = {"mode": "naive", "chunk_bytes": 2 << 30}
+
+
+@contextlib.contextmanager
+def attention_mode(mode: str):
+    """'naive' = the in-tree softmax(QK^T)V of attention.py:103-120 (evaluated in batch chunks so the score matrix
+    stays below 2 GiB; rows are independent, so the result is the unchunked one).  'sdpa' = one fused
+    scaled_dot_product_attention call per attention, the math xformers.ops.memory_efficient_attention performs in
+    the reference's efficient_forward (attention.py:146-190)."""
+    old = _ATTN["mode"]
+    _ATTN["mode"] = mode
+    try:
+        yield
+    finally:
+        _ATTN["mode"] = old
+
+
+@contextlib.contextmanager
+def exact_fp32():
+    """fp32 means fp32: no TF32 in cuBLAS / cuDNN while the oracle runs on a CUDA device."""
+    a, b = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    prec = torch.get_float32_matmul_precision()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = a, b
+        torch.set_float32_matmul_precision(prec)
+
 
 # --------------------------------------------------------------------------------------
 # schedule / scalar tables  (lvdm/models/utils_diffusion.py, lvdm/models/ddpm3d.py)
@@ -34,7 +71,7 @@ SD = Dict[str, torch.Tensor]
 def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     """cos||sin sinusoid, lvdm/models/utils_diffusion.py:8-28."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(timesteps.device)
     args = timesteps[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
@@ -158,9 +195,20 @@ def _heads(t: torch.Tensor, h: int):
 
 
 def _attend(q, k, v, scale):
-    """naive softmax attention, attention.py:103-120."""
-    sim = torch.einsum("bhid,bhjd->bhij", q, k) * scale
-    return torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v)
+    """naive softmax attention, attention.py:103-120 (see attention_mode)."""
+    if _ATTN["mode"] == "sdpa":
+        return F.scaled_dot_product_attention(q, k, v, scale=scale)
+    b, h, n, _ = q.shape
+    per_b = h * n * k.shape[2] * 4
+    bs = max(1, _ATTN["chunk_bytes"] // max(per_b, 1))
+    if bs >= b:
+        sim = torch.einsum("bhid,bhjd->bhij", q, k) * scale
+        return torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v)
+    outs = []
+    for i in range(0, b, bs):
+        sim = torch.einsum("bhid,bhjd->bhij", q[i:i + bs], k[i:i + bs]) * scale
+        outs.append(torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v[i:i + bs]))
+    return torch.cat(outs, 0)
 
 
 def cross_attention(sd: SD, p: str, x: torch.Tensor, ctx: Optional[torch.Tensor], d_head: int = 64, text_len: int = 77):
@@ -274,7 +322,7 @@ def unet_forward(sd: SD, x: torch.Tensor, timesteps: torch.Tensor, context: torc
     emb = emb.repeat_interleave(T, dim=0)
     if "fps_embedding.0.weight" in sd:
         if fs is None:
-            fs = torch.tensor([default_fs] * B, dtype=torch.long)
+            fs = torch.tensor([default_fs] * B, dtype=torch.long, device=x.device)
         fe = _lin(F.silu(_lin(timestep_embedding(fs, mc), sd, "fps_embedding.0")), sd, "fps_embedding.2")
         emb = emb + fe.repeat_interleave(T, dim=0)
     h = x.permute(0, 2, 1, 3, 4).reshape(B * T, -1, H, W).float()
@@ -489,7 +537,7 @@ def ddim_sample(model_fn, sched, shape, S: int, cond, uncond, x_T: torch.Tensor,
     order = np.flip(tab["timesteps"])
     for i, step in enumerate(order):
         index = S - i - 1
-        ts = torch.full((shape[0],), int(step), dtype=torch.long)
+        ts = torch.full((shape[0],), int(step), dtype=torch.long, device=img.device)
         v_c = model_fn(img, ts, cond)
         v_u = model_fn(img, ts, uncond) if (uncond is not None and cfg_scale != 1.0) else None
         v_i = model_fn(img, ts, uncond_img) if (uncond_img is not None and v_u is not None) else None

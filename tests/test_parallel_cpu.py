@@ -59,7 +59,8 @@ def _worker(rank, world, port, T, B, H, q):
     mpx.undo()
 
 
-@pytest.mark.parametrize("world,T,B,H", [(2, 5, 1, 8), (2, 4, 2, 8), (4, 6, 1, 16)])
+# T=16 with the 333-token context is the per-frame image-token branch (L == 77 + 16*T, openaimodel3d.py:556-560) under sharding
+@pytest.mark.parametrize("world,T,B,H", [(2, 5, 1, 8), (2, 4, 2, 8), (4, 6, 1, 16), (2, 16, 1, 8)])
 def test_frame_sharded_forward_matches_single_process(world, T, B, H):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

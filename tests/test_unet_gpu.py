@@ -124,3 +124,31 @@ def test_unet_full_width_block_stack_vs_oracle():
     err = (y.cpu() - ref).abs()
     print(f"mc320: max err {float(err.max()):.4g} mean err {float(err.mean()):.4g} ref std {float(ref.std()):.3g}")
     assert float(err.max()) <= MAX_ERR and float(err.mean()) <= MEAN_ERR
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager():
+    """enable_cuda_graph(): call 1 runs eagerly, call 2 captures, calls 3+ replay -- with different x / t each call; every result
+    must equal the eager forward bit for bit (same kernels in the same order), also with the shared-CFG-prefix batch."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import synth
+    from viewcrafter_b200.unet import UNetModel
+    kw = dict(UNET_KW); kw.update(model_channels=64)
+    shapes = synth.module_shapes(UNetModel(**kw))
+    m, _ = _build(dict(model_channels=64), shapes, seed=31)
+    g = torch.Generator().manual_seed(32)
+    ctx = torch.randn(2, 333, 1024, generator=g).cuda()
+    fs = torch.tensor([10, 10]).cuda()
+    xs = [torch.randn(1, 8, 5, 8, 16, generator=g).cuda() for _ in range(4)]
+    ts = [torch.tensor([t, t]).cuda() for t in (999, 979, 499, 19)]
+    eager = [m(torch.cat([x, x], 0), t, context=ctx, fs=fs, cfg_shared_prefix=True) for x, t in zip(xs, ts)]
+    m.enable_cuda_graph()
+    for i, (x, t) in enumerate(zip(xs, ts)):
+        y = m(torch.cat([x, x], 0), t, context=ctx, fs=fs, cfg_shared_prefix=True)
+        assert torch.equal(y, eager[i]), (i, float((y - eager[i]).abs().max()))
+    assert sum(e["graph"] is not None for e in m._graphs.values()) == 1
+    ctx.add_(0.25)                                                      # in-place write to the context: the graph must not be reused
+    y = m(torch.cat([xs[0], xs[0]], 0), ts[0], context=ctx, fs=fs, cfg_shared_prefix=True)
+    m.enable_cuda_graph(False)
+    ref = m(torch.cat([xs[0], xs[0]], 0), ts[0], context=ctx, fs=fs, cfg_shared_prefix=True)
+    assert torch.equal(y, ref) and not torch.equal(y, eager[0])

@@ -137,9 +137,17 @@ class AutoencoderKL(nn.Module):
         self._packed_enc = None
 
     def _apply(self, fn, *a, **k):
+        # a pure device move carries the packed kernel operands along; a dtype change drops them (cf. UNetModel._apply)
+        keep = ops.is_device_only(fn)
+        packed, packed_enc = (self._packed, self._packed_enc) if keep else (None, None)
         self._packed = None
         self._packed_enc = None
-        return super()._apply(fn, *a, **k)
+        r = super()._apply(fn, *a, **k)
+        if packed is not None:
+            self._packed = ops.tree_apply(packed, fn)
+        if packed_enc is not None:
+            self._packed_enc = ops.tree_apply(packed_enc, fn)
+        return r
 
     @property
     def device(self):
@@ -167,7 +175,6 @@ class AutoencoderKL(nn.Module):
                     o_w=ops.pack_linear(m.proj_out.weight.detach()), o_b=f(m.proj_out.bias))
 
     def _pack(self):
-        ops.require_cuda(self.device, "viewcrafter_b200.AutoencoderKL.decode")
         f = self._f32
         d = self.decoder
         zc = self.post_quant_conv.weight.shape[1]
@@ -223,6 +230,7 @@ class AutoencoderKL(nn.Module):
     @torch.no_grad()
     def decode(self, z, **kwargs):
         """z [N, z_channels, h, w] -> [N, out_ch, 8h, 8w] in z.dtype (autoencoder.py:104-107, ae_modules.py:539-578)."""
+        ops.require_cuda(z.device, "viewcrafter_b200.AutoencoderKL.decode")
         P = self._packed or self._pack()
         N, zc, H, W = z.shape
         rows = torch.zeros((N * H * W, 8), device=z.device, dtype=torch.float16)
@@ -247,7 +255,6 @@ class AutoencoderKL(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _pack_encoder(self):
-        ops.require_cuda(self.device, "viewcrafter_b200.AutoencoderKL.encode")
         f = self._f32
         e = self.encoder
         P = dict(in_w=ops.pack_conv3x3(e.conv_in.weight.detach(), k_pad=8), in_b=f(e.conv_in.bias),
@@ -276,6 +283,7 @@ class AutoencoderKL(nn.Module):
     def encode_moments(self, x):
         """x [N, in_channels, H, W] (H, W multiples of 2^(levels-1)) -> fp32 moments [N, 2*embed_dim, H/8, W/8]
         (autoencoder.py:97-100, ae_modules.py:430-463)."""
+        ops.require_cuda(x.device, "viewcrafter_b200.AutoencoderKL.encode")
         P = self._packed_enc or self._pack_encoder()
         N, Cin, H, W = x.shape
         nd = len(P["down"]) - 1

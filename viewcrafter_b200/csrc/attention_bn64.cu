@@ -323,10 +323,10 @@ int flash_attn_d64_bn64(const AttnDesc& d, cudaStream_t stream) {
   p.out = d.out; p.ldo = d.ldo; p.Nq = d.Nq; p.Nk = d.Nk; p.kv_shared = shared;
   p.scale_log2 = d.scale * 1.4426950408889634f;
   p.accumulate = d.accumulate;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (device_once_needed(configured)) {
     VC_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d64_bn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A64_SMEM));
-    configured = true;
+    device_once_mark(configured);
   }
   dim3 grid((d.Nq + A64_BM - 1) / A64_BM, d.heads, d.B);
   flash_attn_d64_bn64_kernel<<<grid, 192, A64_SMEM, stream>>>(p);

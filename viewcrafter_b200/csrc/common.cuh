@@ -41,7 +41,16 @@ const char* last_error();
 int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
-int sm_count();
+int sm_count();   // of the CURRENT device (cached per device)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device property: launch wrappers keep one bit per device
+// ordinal in a DeviceOnce and configure the kernel the first time each device is used.  Setting it twice (two threads racing)
+// is harmless, so a plain atomic bit mask is enough.
+struct DeviceOnce {
+  unsigned long long done[4] = {0, 0, 0, 0};          // 256 device ordinals
+};
+bool device_once_needed(DeviceOnce& o);   // true: the caller must configure, then call device_once_mark
+void device_once_mark(DeviceOnce& o);
 
 // ----------------------------------------------------------------------------------------------
 // device-side PTX wrappers

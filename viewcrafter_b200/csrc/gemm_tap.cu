@@ -175,10 +175,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
 template <int BN>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (device_once_needed(configured)) {
     VC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tap_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
+    device_once_mark(configured);
   }
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
   gemm_tap_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);

@@ -213,10 +213,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
 template <int BN>
 static int launch_gemm2(const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (device_once_needed(configured)) {
     VC_CHECK_CUDA(cudaFuncSetAttribute(gemm_tap2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
+    device_once_mark(configured);
   }
   int nclusters = sm_count() / 2;
   if (nclusters > p.total_tiles) nclusters = p.total_tiles;

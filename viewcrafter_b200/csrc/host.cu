@@ -20,13 +20,30 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[256];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const int slot = dev & 255;
+  int n = cache[slot].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[slot].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+static inline int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  return dev & 255;
+}
+bool device_once_needed(DeviceOnce& o) {
+  const int s = device_slot();
+  return (__atomic_load_n(&o.done[s >> 6], __ATOMIC_ACQUIRE) & (1ull << (s & 63))) == 0;
+}
+void device_once_mark(DeviceOnce& o) {
+  const int s = device_slot();
+  __atomic_fetch_or(&o.done[s >> 6], 1ull << (s & 63), __ATOMIC_RELEASE);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

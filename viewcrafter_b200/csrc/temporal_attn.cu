@@ -186,10 +186,10 @@ int temporal_attn(const __half* q, const __half* k, const __half* v, int ld, __h
   VC_REQUIRE(q && k && v && out, "temporal_attn: null pointer");
   VC_REQUIRE(T >= 1 && T <= 32, "temporal_attn: T=%d unsupported (1..32)", T);
   VC_REQUIRE(ld % 8 == 0 && ldo % 8 == 0, "temporal_attn: pitches must be multiples of 8");
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (device_once_needed(configured)) {
     VC_CHECK_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
-    configured = true;
+    device_once_mark(configured);
   }
   const long long pairs = sites * heads;
   long long blocks = (pairs + TA_WARPS - 1) / TA_WARPS;

@@ -104,6 +104,9 @@ class DDIMSampler(object):
                       unconditional_conditioning=None, verbose=True, precision=None, fs=None, guidance_rescale=0.0, **kwargs):
         if ddim_use_original_steps or timesteps is not None:
             raise NotImplementedError("viewcrafter_b200.DDIMSampler: only the DDIM sub-sequence path is implemented")
+        if precision is not None and int(precision) == 16:
+            raise NotImplementedError("viewcrafter_b200.DDIMSampler: precision=16 (fp16 latents between steps, ddim.py:155-157) is not "
+                                      "implemented; the latents stay fp32 and the U-Net computes in fp16 internally")
         if mask is not None:
             raise NotImplementedError("viewcrafter_b200.DDIMSampler: mask/x0 blending is not on the ViewCrafter path (mask=None)")
         device = self._device()
@@ -137,9 +140,9 @@ class DDIMSampler(object):
         each step lets it keep the cross-attention K/V projections.  Also reports whether the
         c_concat entries of the two branches are the same tensors (utils/diffusion_utils.py:152-153)."""
         ents = [(a, u) for k in c for a, u in zip(c[k], uc[k])]
-        sig = [(a, a._version, u, u._version) for a, u in ents]
+        sig = [(a, ops.tensor_version(a), u, ops.tensor_version(u)) for a, u in ents]
         cached = getattr(self, "_cat_cache", None)
-        if cached is not None and len(cached[0]) == len(sig) and all(
+        if cached is not None and len(cached[0]) == len(sig) and all(va is not None and vu is not None for _, va, _, vu in sig) and all(
                 a is a0 and va == va0 and u is u0 and vu == vu0 for (a, va, u, vu), (a0, va0, u0, vu0) in zip(sig, cached[0])):
             return cached[1], cached[2]
         cat = {k: [torch.cat([a, u], 0) for a, u in zip(c[k], uc[k])] for k in c}

@@ -29,9 +29,50 @@ def require_cuda(device, who: str):
         raise _lib.VcError(f"{who} runs only on a CUDA (sm_100a) device; there is no CPU path")
 
 
+VcError = _lib.VcError
+
+
 def _chk16(t: torch.Tensor, name: str):
     if t.dtype != torch.float16 or not t.is_cuda:
         raise _lib.VcError(f"{name}: expected a CUDA fp16 tensor, got {t.dtype} on {t.device}")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device's stream: a tensor of another GPU would be dereferenced on the wrong device
+        raise _lib.VcError(f"{name}: tensor lives on {t.device} but the current CUDA device is {torch.cuda.current_device()}; "
+                           f"wrap the call in torch.cuda.device({t.device.index})")
+
+
+def launch_count() -> int:
+    """Kernel launches issued by the library from the host so far (a captured launch counts once, at capture)."""
+    return int(_lib.load().vc_launch_count())
+
+
+def is_device_only(fn) -> bool:
+    """True if an nn.Module._apply function only moves tensors (keeps fp16 and fp32 dtypes)."""
+    try:
+        a, b = fn(torch.empty(1, dtype=torch.float16)), fn(torch.empty(1, dtype=torch.float32))
+        return a.dtype == torch.float16 and b.dtype == torch.float32
+    except Exception:
+        return False
+
+
+def tree_apply(obj, fn):
+    """fn over every tensor of a nested dict / list / tuple (packed kernel operands)."""
+    if isinstance(obj, torch.Tensor):
+        return fn(obj)
+    if isinstance(obj, dict):
+        return {k: tree_apply(v, fn) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(tree_apply(v, fn) for v in obj)
+    return obj
+
+
+def tensor_version(t: torch.Tensor):
+    """The in-place version counter, or None for inference tensors (torch.inference_mode()), which do not track one --
+    callers then skip caching instead of failing."""
+    try:
+        return t._version
+    except RuntimeError:
+        return None
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -420,10 +461,11 @@ def ddim_update(x, v_cond, v_uncond, noise, sc: dict, v_uncond_img=None, cfg_img
     s.sqrt_ac_t, s.sqrt_1mac_t = sc["sqrt_ac_t"], sc["sqrt_1mac_t"]
     s.a_prev, s.sigma_t, s.scale_t, s.prev_scale_t = sc["a_prev"], sc["sigma_t"], sc["scale_t"], sc["prev_scale_t"]
     s.use_cfg = int(use_cfg)
-    ws = _ddim_ws.get(x.device)
+    key = (x.device, torch.cuda.current_stream().cuda_stream)
+    ws = _ddim_ws.get(key)
     if ws is None:
         ws = torch.zeros(4, device=x.device, dtype=torch.float64)
-        _ddim_ws[x.device] = ws
+        _ddim_ws[key] = ws
     x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
     if v_uncond_img is not None and use_cfg:
         check(_lib.load().vc_ddim_update3(x.data_ptr(), v_cond.data_ptr(), v_uncond.data_ptr(), v_uncond_img.data_ptr(), float(cfg_img),

@@ -217,6 +217,9 @@ class UNetModel(nn.Module):
         self._kv_caches = []        # cross-attention K/V projections of the last two contexts (see _kv_projector)
         self._kv_cache = {}
         self._comm = None           # set by viewcrafter_b200.parallel.shard_model for frame-sharded multi-GPU execution
+        self._graph_mode = os.environ.get("VC_UNET_GRAPH", "0") == "1"     # see enable_cuda_graph
+        self._graphs = {}
+        self.graph_replayed_launches = 0    # kernels of this library executed through graph replays (bench.py's gpu_launches)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     # ------------------------------------------------------------------------------------------
@@ -225,11 +228,32 @@ class UNetModel(nn.Module):
     def invalidate_packed(self):
         self._packed = None
         self._kv_caches, self._kv_cache = [], {}
+        self._graphs = {}
+
+    def enable_cuda_graph(self, on: bool = True):
+        """Replay the whole forward as ONE CUDA graph: the denoise loop calls forward ~100 times per
+        clip with the same shapes, the same context tensor and the same weights, so the ~1000 kernel launches (and their
+        host-side tensor-map encodes) of a forward are captured on the second call with a given (shape, context) and replayed
+        afterwards: per call the host does two small input copies and one graph launch.  Results are those of the eager path
+        (same kernels, same order).  Off by default; bench.py / synthesis.py switch it on.  A new context tensor, an in-place
+        write to it, a new shape or new weights lead to a new capture; at most 4 graphs are kept."""
+        self._graph_mode = bool(on)
+        if not on:
+            self._graphs = {}
+        return self
 
     def _apply(self, fn, *a, **k):
+        # a pure device move (.cuda() / .to(device)) carries the packed kernel operands along (H2D copies, no repacking);
+        # anything that changes dtypes drops them
+        packed = self._packed if ops.is_device_only(fn) else None
         self._packed = None
         self._kv_caches, self._kv_cache = [], {}
-        return super()._apply(fn, *a, **k)
+        self._graphs = {}
+        r = super()._apply(fn, *a, **k)
+        if packed is not None:
+            self._packed = ops.tree_apply(packed, fn)
+            self._packed["device"] = self.time_embed[0].weight.device
+        return r
 
     @staticmethod
     def _f32(t):
@@ -315,8 +339,7 @@ class UNetModel(nn.Module):
 
     def _pack(self):
         f = self._f32
-        dev = self.time_embed[0].weight.device
-        ops.require_cuda(dev, "viewcrafter_b200.UNetModel")
+        dev = self.time_embed[0].weight.device          # packing is plain tensor math: it may run before the move to the GPU
         P = dict(device=dev)
         P["time"] = [f(self.time_embed[0].weight), f(self.time_embed[0].bias), f(self.time_embed[2].weight), f(self.time_embed[2].bias)]
         if self.fs_condition:
@@ -444,13 +467,14 @@ class UNetModel(nn.Module):
         holds the last two contexts (a few MB of fp16 each)."""
         # keyed on the tensor OBJECT (kept alive by the cache, so its storage cannot be recycled under the key) + its version
         # counter (bumped by any in-place write).  Two entries: an unbatched sampler alternates cond / uncond contexts.
+        ver = ops.tensor_version(context)
         cache = None
         for cnd in self._kv_caches:
-            if cnd["ref"] is context and cnd["ver"] == context._version and cnd["rng"] == img_range:
+            if cnd["ref"] is context and cnd["ver"] == ver and ver is not None and cnd["rng"] == img_range:
                 cache = cnd
                 break
         if cache is None:
-            cache = {"ref": context, "ver": context._version, "rng": img_range}
+            cache = {"ref": context, "ver": ver, "rng": img_range}
             self._kv_caches = [cache] + [cnd for cnd in self._kv_caches if cnd["ref"] is not context][:1]
         else:
             self._kv_caches = [cache] + [cnd for cnd in self._kv_caches if cnd is not cache][:1]
@@ -470,7 +494,48 @@ class UNetModel(nn.Module):
         in x.dtype (openaimodel3d.py:548-603).  Extra kwargs are accepted and ignored like the reference does."""
         if features_adapter is not None:
             _unsupported("features_adapter")
+        if self._graph_mode and x.is_cuda and context is not None and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graphed(x, timesteps, context, fs, kwargs)
+        return self._forward_impl(x, timesteps, context, fs, kwargs)
+
+    def _forward_graphed(self, x, timesteps, context, fs, kwargs):
+        ver = ops.tensor_version(context)
+        flags = tuple(sorted((k, bool(v)) for k, v in kwargs.items() if k == "cfg_shared_prefix"))
+        key = (tuple(x.shape), x.dtype, id(context), ver, fs is None, flags, id(self._comm))
+        e = self._graphs.get(key)
+        if ver is None or (e is not None and e["ctx"] is not context):
+            return self._forward_impl(x, timesteps, context, fs, kwargs)
+        if e is None:                                   # first sight: run eagerly (packs weights, fills the K/V cache)
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = dict(ctx=context, graph=None)
+            return self._forward_impl(x, timesteps, context, fs, kwargs)
+        dev = x.device
+        if e["graph"] is None:                          # second call: capture
+            e["x"] = x.clone()
+            e["t"] = timesteps.to(device=dev, dtype=torch.int64).clone()
+            e["fs"] = None if fs is None else fs.to(device=dev, dtype=torch.int64).clone()
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                e["out"] = self._forward_impl(e["x"], e["t"], context, e["fs"], kwargs)
+            e["graph"] = g
+            e["launches"] = ops.launch_count() - n0     # kernels of this library inside the graph (launched again by every replay)
+            e["kv"] = list(self._kv_caches)             # the captured kernels read these K/V projections: keep them alive
+        e["x"].copy_(x)
+        e["t"].copy_(timesteps)
+        if e["fs"] is not None:
+            e["fs"].copy_(fs)
+        e["graph"].replay()
+        self.graph_replayed_launches += e["launches"]
+        return e["out"].clone()
+
+    def _forward_impl(self, x, timesteps, context, fs, kwargs):
+        ops.require_cuda(x.device, "viewcrafter_b200.UNetModel")
         P = self._packed or self._pack()
+        if P["device"] != x.device:
+            raise ops.VcError(f"UNetModel weights are on {P['device']} but the input is on {x.device}")
         comm = self._comm
         T_all = x.shape[2]
         if comm:                                   # frame sharding: this rank owns frames [f0, f1) for every spatial op
@@ -491,8 +556,8 @@ class UNetModel(nn.Module):
             if fs is None:
                 fs = torch.full((B,), self.default_fs, dtype=torch.int64, device=dev)
             fw = P["fps"]
-            f1 = ops.small_linear(ops.timestep_embedding(fs.to(device=dev, dtype=torch.int64).contiguous(), self.model_channels), fw[0], fw[1])
-            emb = ops.small_linear(f1, fw[2], fw[3], silu_in=True, add=emb)
+            fs_h = ops.small_linear(ops.timestep_embedding(fs.to(device=dev, dtype=torch.int64).contiguous(), self.model_channels), fw[0], fw[1])
+            emb = ops.small_linear(fs_h, fw[2], fw[3], silu_in=True, add=emb)
         # --- context: text[:77] | image tokens; per-frame image tokens when L == 77 + 16*T (openaimodel3d.py:556-560) ---
         ctx16 = ops.cast_f16(context.float().contiguous())
         L = context.shape[1]
