@@ -13,6 +13,10 @@ for mb in 0 32 48 64 96; do
   VC_GN_L2_MB=$mb timeout 200 python tools/ab_micro.py 2>&1 | grep -E "groupnorm" | sed "s/^/[GN_L2_MB=$mb] /" >> $O/c1_ab.txt
 done
 timeout 200 python tools/ab_micro.py 2>&1 | grep -vE "groupnorm" >> $O/c1_ab.txt
+for lib in viewcrafter_b200/libvc_b200_*.so; do
+  [ -f "$lib" ] || continue
+  VC_B200_LIB=$PWD/$lib timeout 200 python tools/ab_micro.py 2>&1 | grep -E "attn" >> $O/c1_ab.txt
+done
 VC_ATTN_BN64=1 timeout 200 python tools/ab_micro.py 2>&1 | grep -E "attn" >> $O/c1_ab.txt
 VC_LN_STATS_UNROLL=1 timeout 200 python tools/ab_micro.py 2>&1 | grep -E "ln_stats" >> $O/c1_ab.txt
 cat $O/c1_ab.txt

@@ -75,6 +75,32 @@ __device__ __forceinline__ float ex2_sel(float x, int e) {
   return ex2f(x);
 }
 
+#ifndef VC_ATT_F32X2
+#define VC_ATT_F32X2 1
+#endif
+#ifndef VC_ATT_MERGED
+#define VC_ATT_MERGED 0      // 1: a single role warp issues TMA loads and MMAs (A/B switch)
+#endif
+// two exponentials at once: both on MUFU, or (one pair in every ATT_POLY_PERIOD) both through the polynomial in packed fp32x2
+__device__ __forceinline__ float2 ex2_pair(float2 x, int e) {
+  if (ATT_POLY_PERIOD > 0 && (e % (2 * ATT_POLY_PERIOD)) < 2) {
+    x.x = fmaxf(x.x, -125.0f);
+    x.y = fmaxf(x.y, -125.0f);
+    const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+    const float2 xf = __fadd2_rn(x, magic);                                   // integer part in the low mantissa bits
+    const float2 t = __fadd2_rn(xf, nmagic);
+    const float2 f = __ffma2_rn(t, make_float2(-1.f, -1.f), x);               // f in [-0.5, 0.5]
+    float2 p = __ffma2_rn(f, make_float2(0.05592204f, 0.05592204f), make_float2(0.24264008f, 0.24264008f));
+    p = __ffma2_rn(p, f, make_float2(0.69312102f, 0.69312102f));
+    p = __ffma2_rn(p, f, make_float2(0.99992448f, 0.99992448f));
+    float2 r;
+    r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(xf.x) << 23));
+    r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xf.y) << 23));
+    return r;
+  }
+  return make_float2(ex2f(x.x), ex2f(x.y));
+}
+
 __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -122,6 +148,78 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
 
+#if VC_ATT_MERGED
+  // ONE role warp issues both the TMA loads and the MMAs.  Every stage hand-back the separate producer warp used to wait for
+  // is implied by an event this warp has already waited on, so no "empty" barriers (and no second spinning warp: ncu round 1
+  // counted 44 M try_wait polls of the producer per launch) are needed:
+  //   K stage j&1 is free once Q K^T(j) retired  <=  s_free(j)  (the softmax warps read S(j) only after s_full(j))
+  //   V stage j&1 is free once P V(j) retired    <=  p_full(j+1) (the softmax warps wait o_done(j) before arriving)
+  if (warp == 0) {
+    // idle: parks at the final barrier
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);      // B = V is MN-major
+    const uint32_t aQ = smem_u32(sQ);
+    auto load_k = [&](int j) {
+      if (elect_one()) {
+        uint8_t* sk = sKV + (j & 1) * 2 * ATT_TILE_BYTES;
+        mbar_expect_tx(&kv_full[j & 1], ATT_TILE_BYTES);
+        tma_load_4d(sk, &p.tmap_k, &kv_full[j & 1], 0, head, j * ATT_BN, bk);
+      }
+      __syncwarp();
+    };
+    auto load_v = [&](int j) {
+      if (elect_one()) {
+        uint8_t* sv = sKV + (j & 1) * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES;
+        mbar_expect_tx(&v_full[j & 1], ATT_TILE_BYTES);
+        tma_load_4d(sv, &p.tmap_v, &v_full[j & 1], 0, head, j * ATT_BN, bk);
+      }
+      __syncwarp();
+    };
+    auto issue_qk = [&](int j) {
+      const int s = j & 1;
+      mbar_wait(&kv_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t aK = smem_u32(sKV + s * 2 * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_ss(tS, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc_qk, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    };
+    if (elect_one()) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_4d(sQ, &p.tmap_q, q_full, 0, head, q0, b);
+    }
+    __syncwarp();
+    load_k(0);
+    if (ntiles > 1) load_k(1);
+    load_v(0);
+    if (ntiles > 1) load_v(1);
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < ntiles; ++j) {
+      if (j + 1 < ntiles) {                       // next S as soon as this one has been copied out of TMEM
+        mbar_wait(s_free, j & 1);
+        issue_qk(j + 1);
+        if (j + 2 < ntiles) load_k(j + 2);        // Q K^T(j) retired before s_free(j): its K stage is free
+      }
+      mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+      mbar_wait(p_full, j & 1);
+      if (j >= 1 && j + 1 < ntiles) load_v(j + 1);  // p_full(j) implies P V(j-1) retired: stage (j+1)&1 is free
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t aV = smem_u32(sKV + (j & 1) * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k)
+          umma_ts(tO, tP + k * 8, umma_desc_sw128(aV + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(o_done);
+      }
+      __syncwarp();
+    }
+#else
   // warps 0/1 run warp-uniform loops and ONE elected lane issues TMA / MMA (keeps operands in uniform registers)
   if (warp == 0) {
     if (elect_one()) {
@@ -201,6 +299,7 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
       }
       __syncwarp();
     }
+#endif
   } else {
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
@@ -252,6 +351,27 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
         m = m_cand;
       }
       const float neg_m = -m;
+#if VC_ATT_F32X2
+      // packed fp32x2 arithmetic (FFMA2 / FADD2, sm_100): the softmax warps are issue-slot bound (ncu round 1: 7.9 warp
+      // instructions per 32 scores, issue slots 65 % busy, tensor pipe 36 %), and the scale-subtract, the row sums and the
+      // polynomial exp2 are all two-at-a-time.  Per score: 0.5 FFMA2 + 1 MUFU (or the polynomial) + 0.5 FADD2 + 0.5 F2FP.
+      const float2 sl2v = make_float2(sl2, sl2), negm2 = make_float2(neg_m, neg_m);
+      float2 ps0 = make_float2(0.f, 0.f), ps1 = ps0, ps2 = ps0, ps3 = ps0;
+#define VC_ATT_CHUNK(SRC, DST, OFF, PS)                                                                       \
+  _Pragma("unroll") for (int e = 0; e < 32; e += 2) {                                                         \
+    const float2 x = __ffma2_rn(make_float2(__uint_as_float(SRC[e]), __uint_as_float(SRC[e + 1])), sl2v, negm2); \
+    const float2 a = ex2_pair(x, e);                                                                          \
+    PS = __fadd2_rn(PS, a);                                                                                   \
+    DST[OFF + e / 2] = pack_half2(a.x, a.y);                                                                  \
+  }
+      VC_ATT_CHUNK(s0, s0, 0, ps0)
+      VC_ATT_CHUNK(s1, s0, 16, ps1)
+      VC_ATT_CHUNK(s2, s2, 0, ps2)
+      VC_ATT_CHUNK(s3, s2, 16, ps3)
+#undef VC_ATT_CHUNK
+      const float2 pst = __fadd2_rn(__fadd2_rn(ps0, ps1), __fadd2_rn(ps2, ps3));
+      l += pst.x + pst.y;
+#else
       float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;     // independent partial row sums (shorter FADD chains)
       // probabilities, packed in place: s0[0..15] <- s0, s0[16..31] <- s1, s2[0..15] <- s2, s2[16..31] <- s3
 #pragma unroll
@@ -279,6 +399,7 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
         s2[16 + e / 2] = pack_half2(a0, a1);
       }
       l += (ps0 + ps1) + (ps2 + ps3);
+#endif
       if (j > 0) {
         mbar_wait(o_done, (j - 1) & 1);                  // P V of the previous tile retired: P and O may be touched
         tc_fence_after();
