@@ -394,13 +394,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- N > 1: numerics of the sharded forward against the unsharded one on the same GPU (one forward, t = 499) ----
+    unet_m = model.model.diffusion_model
+    comm = unet_m._comm
+    shard_err = None
+    if world > 1 and comm is not None:
+        gm = unet_m._graph_mode
+        unet_m.enable_cuda_graph(False)
+        xc = torch.cat([dev["x_T"], dev["c_concat"]], 1)
+        t499 = torch.full((1,), 499, device=device, dtype=torch.long)
+        comm.bytes_moved = 0
+        y_sh = unet_m(xc, t499, context=dev["ctx_c"], fs=fs)
+        comm.bytes_per_forward = comm.bytes_moved
+        unet_m._comm = None
+        y_1 = unet_m(xc, t499, context=dev["ctx_c"], fs=fs)
+        unet_m._comm = comm
+        e = (y_sh - y_1).abs().max().reshape(1)
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        shard_err = {"max_abs_err": float(e), "out_std": float(y_1.std()),
+                     "what": "one U-Net forward (t=499): frame-sharded over this rank's group vs the same weights unsharded on one GPU"}
+        del y_sh, y_1
+        comm.bytes_moved = 0
+        unet_m.enable_cuda_graph(gm)
+
     # ---- device-resident throughput ("value") ----
     x = dev["x_T"]
     for i in range(args.warmup):
         x, _ = run_step(x, i)
     barrier()
     lib.vc_reset_launch_count()
-    unet_m = model.model.diffusion_model
     unet_m.graph_replayed_launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
@@ -439,6 +461,14 @@ def main():
     f1.record()
     barrier()
     t_e2e = torch.tensor([f0.elapsed_time(f1) * 1e-3], device=device, dtype=torch.float64)
+    comm_info = None
+    if world > 1:
+        from viewcrafter_b200 import parallel as _par
+        comm_info = {"layout": "2-way CFG split x %d-way frame sharding" % (world // 2) if world % 2 == 0 else "%d-way frame sharding" % world,
+                     "impl": ("NVLink peer-memory exchange kernels (csrc/peer.cu), GroupNorm statistics fused into the frames->sites switch"
+                              if isinstance(comm, _par.PeerFrameComm) else ("NCCL all_to_all_single + all_reduce" if comm is not None else "none (CFG split only)")),
+                     "bytes_sent_per_forward_rank0": None if comm is None else int(getattr(comm, "bytes_per_forward", 0)),
+                     "cfg_exchange_bytes_per_step": int(dev["x_T"].numel() * 4) if world % 2 == 0 else 0}
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -460,6 +490,9 @@ def main():
             "published_context": {"a100_readme_steps_per_s": A100_README_STEPS_PER_S[args.workload],
                                   "speedup_vs_a100_readme": value / A100_README_STEPS_PER_S[args.workload],
                                   "note": "README.md:117-122 (A100 40GB, whole-pipeline time / 50 steps); other hardware, so vs_baseline stays null"}}
+    if world > 1:
+        line["sharded_vs_single_max_err"] = shard_err
+        line["comm"] = comm_info
     if world == 1:
         line.update(kernel_rooflines(wl, device, peaks))
         if not args.no_gpu_baseline:

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VC_B200_ABI_VERSION 3
+#define VC_B200_ABI_VERSION 4
 
 int vc_abi_version(void);
 const char* vc_last_error(void);
@@ -99,6 +99,9 @@ int vc_groupnorm_stats(const void* x1, int32_t C1, const void* x2, int32_t C2, i
 int vc_groupnorm_apply(const void* x1, int32_t C1, const void* x2, int32_t C2, int32_t samples, int64_t rows_per_sample,
                        const float* stats, int64_t stat_rows, const float* gamma, const float* beta, float eps, int32_t silu, void* out,
                        void* stream);
+/* pass 2 with UN-reduced statistics: parts = [samples][n_parts][32][2] partial (sum, sumsq), summed in index order */
+int vc_groupnorm_apply_parts(const void* x1, int32_t C1, int32_t samples, int64_t rows_per_sample, const float* parts, int32_t n_parts,
+                             int64_t stat_rows, const float* gamma, const float* beta, float eps, int32_t silu, void* out, void* stream);
 /* statistics half of nn.LayerNorm: stats[row] = (mean, 1/sqrt(var + eps)) in fp32; the normalisation is applied by the
  * consuming vc_gemm_tap (ln_stats / ln_colsum), so the normalised activation is never written to memory */
 int vc_layernorm_stats(const void* x, int64_t rows, int32_t C, float eps, float* stats, void* stream);
@@ -145,6 +148,35 @@ int vc_ddim_update(const float* x, const float* v_cond, const float* v_uncond, c
  * replaces: lvdm/models/samplers/ddim_multiplecond.py:227-236 (+ the shared tail :238-287) */
 int vc_ddim_update3(const float* x, const float* v_cond, const float* v_uncond, const float* v_uncond_img, float cfg_img,
                     const float* noise, float* x_prev, float* pred_x0, int64_t n, const vc_ddim_scalars* s, void* ws32bytes, void* stream);
+
+/* ---- multi-GPU: frame <-> site layout exchange over NVLink peer memory ------------------------------------------------
+ * New functionality (the reference is single-GPU).  The frame-sharded U-Net runs its spatial ops on
+ * [(b, t_local, hw), C] rows and its temporal ops (TemporalTransformer attention.py:365-412, TemporalConvBlock
+ * openaimodel3d.py:239-279) on [(b, t_all, hw_local), C] rows.  One kernel per switch: every rank stores its rows straight
+ * into the receive buffers of the owning ranks (mapped into this process with CUDA IPC by the caller) and, for
+ * frames -> sites, publishes the GroupNorm(32) partial sums of the tensor it just streamed; a device-side sequence number +
+ * release/acquire flags in peer memory replace the NCCL collective.  All ranks of the group must issue the same sequence of
+ * vc_peer_* calls.  After the call (in stream order) cur_stats holds [B][world][32][2] partial (sum, sumsq) of all ranks
+ * (frames -> sites with with_stats, and vc_peer_groupnorm_stats): feed it to vc_groupnorm_apply_parts with n_parts = world. */
+typedef struct vc_peer_comm {
+  int32_t world, rank;               /* ranks of the frame group (<= 8) and this rank's index in it               */
+  void* flags;                       /* own uint32[world], zero-initialised before the peers map it                 */
+  void* peer_flags[8];               /* rank p's flags as mapped in this process (peer_flags[rank] == flags)        */
+  void* seq;                         /* own uint32: collectives completed (zero-initialised)                        */
+  void* done;                        /* own uint32: scratch (zero-initialised)                                      */
+  void* stats_slots[8];              /* rank p's float[2][Bmax][world][64] as mapped here                           */
+  void* cur_stats;                   /* own float[Bmax][world][64]                                                  */
+  int32_t Bmax;                      /* batch samples per rank the slots were sized for (1 or 2)                    */
+} vc_peer_comm;
+int vc_enable_peer_access(int32_t peer_device);
+/* src: local fp16 rows; dst[p]: rank p's receive buffer as mapped here; f0[world+1]: frame range boundaries of the ranks.
+ * to_sites = 1: [(b, t_local, hw), C] -> [(b, t_all, hw_local), C]; 0: the reverse.  ws: >= B * 512 * 64 floats. */
+int vc_peer_exchange(const vc_peer_comm* c, const void* src, void* const* dst, int32_t to_sites, int32_t B, int32_t T, int32_t HW,
+                     int32_t C, const int32_t* f0, int32_t with_stats, void* ws, size_t ws_bytes, void* stream);
+/* GroupNorm statistics of this rank's rows + exchange with all peers -> cur_stats (the site-sharded 5-D GroupNorms in the
+ * middle of a temporal block, openaimodel3d.py:256-265) */
+int vc_peer_groupnorm_stats(const vc_peer_comm* c, const void* x, int32_t C, int32_t samples, int64_t rows_per_sample, void* ws,
+                            size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

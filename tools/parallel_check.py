@@ -1,4 +1,7 @@
-"""torchrun target: frame-sharded U-Net forward over NCCL vs the single-GPU forward and the CPU oracle (rank 0 prints)."""
+"""torchrun target: frame-sharded U-Net forward vs the single-GPU forward and the CPU oracle (rank 0 prints).
+VC_PEER_COMM=1 (default): layout switches / GroupNorm statistics through the library's NVLink peer-memory kernels (csrc/peer.cu);
+VC_PEER_COMM=0: NCCL collectives.  Also checks the peer kernels against the NCCL path tensor by tensor, and the CUDA-graph replay
+of the sharded forward against the eager one."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -22,12 +25,52 @@ x, ctx = torch.randn(B, 8, T, H, W, generator=g), torch.randn(B, 333, 1024, gene
 t = torch.tensor([499, 19])
 y_single = m(x.cuda(), t.cuda(), context=ctx.cuda())
 comm = parallel.shard_model(m, dist, rank, world)
+peer_mode = isinstance(comm, parallel.PeerFrameComm)
+ok_unit = True
+if peer_mode:
+    # unit check of the exchange kernels against the NCCL implementation of the same layout switch (incl. GroupNorm statistics)
+    from viewcrafter_b200 import ops
+    ref_comm = parallel.FrameComm(dist, rank, world, None)
+    f0, f1 = comm.bind(T); ref_comm.bind(T)
+    for (Bq, HWq, Cq) in ((2, 256, 64), (1, 64, 320), (2, 16, 1280)):
+        gq = torch.Generator().manual_seed(100 + rank)
+        hq = (torch.randn(Bq * (f1 - f0) * HWq, Cq, generator=gq) * 1.5 + 0.3).half().cuda()
+        a = comm.to_sites(hq, Bq, HWq)
+        b = ref_comm.to_sites(hq, Bq, HWq)
+        same_sites = torch.equal(a, b)
+        gam, bet = torch.rand(Cq, device="cuda") + 0.5, torch.randn(Cq, device="cuda") * 0.1
+        n1 = comm.groupnorm5d(a, Bq, gam, bet, 1e-5, True, T * HWq, True)
+        n2 = ref_comm.groupnorm5d(b, Bq, gam, bet, 1e-5, True, T * HWq, True)
+        n3 = comm.groupnorm5d(b.clone(), Bq, gam, bet, 1e-5, True, T * HWq, False)      # statistics through vc_peer_groupnorm_stats
+        e12, e13 = float((n1.float() - n2.float()).abs().max()), float((n3.float() - n2.float()).abs().max())
+        back = comm.to_frames(a.clone(), Bq, HWq)
+        same_back = torch.equal(back, hq)
+        torch.cuda.synchronize()
+        good = same_sites and same_back and e12 < 4e-3 and e13 < 4e-3
+        ok_unit = ok_unit and good
+        if rank == 0:
+            print(f"peer exchange B={Bq} HW={HWq} C={Cq}: to_sites==nccl {same_sites}, round trip {same_back}, GN(fused stats) err {e12:.2e}, GN(peer stats) err {e13:.2e}")
 y_sharded = m(x.cuda(), t.cuda(), context=ctx.cuda())
 torch.cuda.synchronize()
+# CUDA-graph replay of the sharded forward (call 1 eager, call 2 capture, call 3 replay)
+xc, tc, cc_ = x.cuda(), t.cuda(), ctx.cuda()
+m.enable_cuda_graph()
+ok_graph = True
+for it in range(3):
+    yg = m(xc, tc, context=cc_)
+    torch.cuda.synchronize()
+    dg = float((yg - y_sharded).abs().max())
+    ok_graph = ok_graph and dg < 5e-3          # GroupNorm's shared-memory float atomics make runs differ by rounding flips
+m.enable_cuda_graph(False)
+gflag = torch.tensor([1.0 if (ok_graph and ok_unit) else 0.0], device="cuda")
+dist.all_reduce(gflag, op=dist.ReduceOp.MIN)
+ok_graph = bool(gflag.item() > 0)
+if rank == 0:
+    print(f"world {world}: peer kernels {peer_mode}; graph replay of the sharded forward + unit checks ok: {ok_graph}")
 dmax = (y_sharded - y_single).abs().max().reshape(1)
 dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
 d_single = float(dmax)
-ok = d_single < 0.02
+ok = d_single < 0.02 and ok_graph
 if rank == 0:
     with torch.no_grad():
         ref = O.unet_forward(sd, x, t, ctx, None, default_fs=10)

@@ -19,6 +19,7 @@ for lib in viewcrafter_b200/libvc_b200_*.so; do
 done
 VC_ATTN_BN64=1 timeout 200 python tools/ab_micro.py 2>&1 | grep -E "attn" >> $O/c1_ab.txt
 VC_LN_STATS_UNROLL=1 timeout 200 python tools/ab_micro.py 2>&1 | grep -E "ln_stats" >> $O/c1_ab.txt
-cat $O/c1_ab.txt
+timeout 200 python tools/bench_gemm.py > $O/c1_gemm.txt 2>&1
+cat $O/c1_ab.txt; cat $O/c1_gemm.txt
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file $O/c1_smoke_launches.csv python -c "import __graft_entry__ as g; g.smoke()" > $O/c1_smoke.log 2>&1
 python tools/launch_summary.py $O/c1_smoke_launches.csv 2>/dev/null | head -30

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VC_B200_LIB") or os.path.join(_HERE, "libvc_b200.so")   # override: A/B builds of the kernels
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class VcError(RuntimeError):
@@ -40,6 +40,12 @@ class DdimScalars(C.Structure):
                 ("scale_t", C.c_float), ("prev_scale_t", C.c_float), ("use_cfg", C.c_int32)]
 
 
+class PeerComm(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("flags", C.c_void_p), ("peer_flags", C.c_void_p * 8),
+                ("seq", C.c_void_p), ("done", C.c_void_p), ("stats_slots", C.c_void_p * 8), ("cur_stats", C.c_void_p),
+                ("Bmax", C.c_int32)]
+
+
 _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); must list every symbol include/vc_b200.h declares (tests check this)
@@ -56,6 +62,11 @@ SIGNATURES = {
     "vc_groupnorm_nhwc": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp, _vp, _f32, _i32, _vp, _vp, _sz, _vp]),
     "vc_groupnorm_stats": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp, _vp, _sz, _vp]),
     "vc_groupnorm_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _f32, _i32, _vp, _vp]),
+    "vc_groupnorm_apply_parts": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _i32, _i64, _vp, _vp, _f32, _i32, _vp, _vp]),
+    "vc_enable_peer_access": (C.c_int, [_i32]),
+    "vc_peer_exchange": (C.c_int, [C.POINTER(PeerComm), _vp, C.POINTER(C.c_void_p), _i32, _i32, _i32, _i32, _i32, C.POINTER(C.c_int32), _i32,
+                                   _vp, _sz, _vp]),
+    "vc_peer_groupnorm_stats": (C.c_int, [C.POINTER(PeerComm), _vp, _i32, _i32, _i64, _vp, _sz, _vp]),
     "vc_layernorm_stats": (C.c_int, [_vp, _i64, _i32, _f32, _vp, _vp]),
     "vc_layernorm": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp]),
     "vc_softmax_rows_f32": (C.c_int, [_vp, _i64, _i64, _f32, _vp, _vp]),

@@ -6,7 +6,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr ${VC_NVCC_EXTRA:-}"
 OUT=${VC_OUT:-../libvc_b200.so}          # VC_OUT / VC_BUILD_DIR / VC_NVCC_EXTRA: side-by-side A/B builds (load with VC_B200_LIB)
 BUILD=${VC_BUILD_DIR:-build}
-SRCS="host.cu capi.cu gemm_tap.cu gemm_tap2.cu attention.cu attention_bn64.cu temporal_attn.cu norm.cu misc.cu"
+SRCS="host.cu capi.cu gemm_tap.cu gemm_tap2.cu attention.cu attention_bn64.cu temporal_attn.cu norm.cu misc.cu peer.cu"
 mkdir -p $BUILD
 pids=()
 for f in $SRCS; do

@@ -74,6 +74,11 @@ int vc_groupnorm_apply(const void* x1, int32_t C1, const void* x2, int32_t C2, i
   COUNT(1);
   return groupnorm_apply(H(x1), C1, H(x2), C2, samples, rows_per_sample, stats, stat_rows, gamma, beta, eps, silu, HM(out), ST(stream));
 }
+int vc_groupnorm_apply_parts(const void* x1, int32_t C1, int32_t samples, int64_t rows_per_sample, const float* parts, int32_t n_parts,
+                             int64_t stat_rows, const float* gamma, const float* beta, float eps, int32_t silu, void* out, void* stream) {
+  COUNT(1);
+  return groupnorm_apply(H(x1), C1, nullptr, 0, samples, rows_per_sample, parts, stat_rows, gamma, beta, eps, silu, HM(out), ST(stream), n_parts);
+}
 int vc_layernorm_stats(const void* x, int64_t rows, int32_t C, float eps, float* stats, void* stream) {
   COUNT(1);
   return layernorm_stats(H(x), rows, C, eps, stats, ST(stream));
@@ -153,5 +158,7 @@ int vc_ddim_update3(const float* x, const float* v_cond, const float* v_uncond, 
   COUNT((d.use_cfg && d.guidance_rescale > 0.f) ? 2 : 1);
   return ddim_update(x, v_cond, v_uncond, v_uncond_img, cfg_img, noise, x_prev, pred_x0, n, d, reinterpret_cast<double*>(ws), ST(stream));
 }
+
+/* vc_enable_peer_access / vc_peer_exchange / vc_peer_groupnorm_stats: peer.cu */
 
 }  // extern "C"

@@ -56,7 +56,7 @@ int groupnorm_stats(const __half* x1, int C1, const __half* x2, int C2, int samp
                     float* partial_ws, size_t ws_bytes, cudaStream_t stream);
 int groupnorm_apply(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample,
                     const float* stats, long long stat_rows, const float* gamma, const float* beta, float eps, int silu, __half* out,
-                    cudaStream_t stream);
+                    cudaStream_t stream, int stat_parts = 1);
 
 int layernorm_stats(const __half* x, long long rows, int C, float eps, float* stats, cudaStream_t stream);
 int layernorm_rows(const __half* x, long long rows, int C, const float* gamma, const float* beta, float eps, __half* out,

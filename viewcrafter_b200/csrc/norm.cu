@@ -330,14 +330,29 @@ int groupnorm_stats(const __half* x1, int C1, const __half* x2, int C2, int samp
   return VC_OK;
 }
 
+// pass 1 alone: leaves splits_out records of (sum, sumsq) per group and sample in partial_ws[sample][split][64]
+int groupnorm_stats_partials(const __half* x1, int C1, int samples, long long rows_per_sample, float* partial_ws, size_t ws_bytes,
+                             int* splits_out, cudaStream_t stream) {
+  VC_REQUIRE(partial_ws && splits_out, "groupnorm_stats_partials: null pointer");
+  GnGeom g;
+  int rc = gn_geometry(g, x1, C1, nullptr, 0, samples, rows_per_sample);
+  if (rc) return rc;
+  VC_REQUIRE(ws_bytes >= (size_t)samples * g.splits * 64 * sizeof(float), "groupnorm: workspace too small");
+  dim3 grid(g.splits, samples);
+  gn_stats_kernel<<<grid, g.vecs * g.ppi, 2 * g.C * sizeof(float), stream>>>(x1, nullptr, g, partial_ws);
+  VC_CHECK_CUDA(cudaGetLastError());
+  *splits_out = g.splits;
+  return VC_OK;
+}
+
 int groupnorm_apply(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample,
                     const float* stats, long long stat_rows, const float* gamma, const float* beta, float eps, int silu, __half* out,
-                    cudaStream_t stream) {
-  VC_REQUIRE(out && gamma && beta && stats && stat_rows >= rows_per_sample, "groupnorm_apply: bad args");
+                    cudaStream_t stream, int stat_parts) {
+  VC_REQUIRE(out && gamma && beta && stats && stat_rows >= rows_per_sample && stat_parts >= 1, "groupnorm_apply: bad args");
   GnGeom g;
   int rc = gn_geometry(g, x1, C1, x2, C2, samples, rows_per_sample);
   if (rc) return rc;
-  g.stat_splits = 1;
+  g.stat_splits = stat_parts;                   // stats = [samples][stat_parts][32][2] partial sums (1: already reduced)
   g.stat_rows = stat_rows;
   dim3 grid(g.splits, samples);
   gn_apply_kernel<<<grid, g.vecs * g.ppi, 0, stream>>>(x1, x2, g, stats, gamma, beta, eps, silu, out);

@@ -77,45 +77,188 @@ class FrameComm:
     def all_reduce(self, t: torch.Tensor):
         self.dist.all_reduce(t, group=self.group)
 
+    def groupnorm5d(self, x, B, gamma, beta, eps, silu, stat_rows, fresh: bool):
+        """GroupNorm(32) of a site-layout tensor whose statistics span the ranks of the group.  `fresh`: x is the tensor the
+        last to_sites() returned (the peer-memory path already holds its statistics)."""
+        from . import ops
+        st = ops.groupnorm_stats(x, B)
+        self.all_reduce(st)
+        return ops.groupnorm_apply(x, B, st, stat_rows, gamma, beta, eps, silu)
+
     def gather_frames(self, y_local: torch.Tensor, T: int) -> torch.Tensor:
         """[B,C,T_local,H,W] per rank -> the full [B,C,T,H,W] on every rank (3.7 MB at the headline size)."""
         B, C, _, H, W = y_local.shape
-        full = torch.zeros((B, C, T, H, W), device=y_local.device, dtype=y_local.dtype)
-        f0, f1 = self.ranges[self.rank]
-        full[:, :, f0:f1] = y_local
-        self.dist.all_reduce(full, group=self.group)
-        return full
+        tmax = max(f1 - f0 for f0, f1 in self.ranges)
+        mine = y_local.new_zeros((B, C, tmax, H, W))
+        mine[:, :, :y_local.shape[2]] = y_local
+        parts = y_local.new_empty((self.world, B, C, tmax, H, W))
+        self.dist.all_gather_into_tensor(parts.view(-1), mine.view(-1), group=self.group)       # uneven frame counts: padded to the largest shard
+        return torch.cat([parts[r, :, :, :f1 - f0] for r, (f0, f1) in enumerate(self.ranges)], dim=2)
+
+
+class PeerFrameComm(FrameComm):
+    """FrameComm whose layout switches and GroupNorm statistics run as this library's own kernels over NVLink peer memory
+    (csrc/peer.cu) instead of NCCL collectives: every rank maps the receive buffers, flag words and statistics slots of the
+    other ranks of its group (CUDA IPC through torch's shared-storage handles, exchanged once over the process group) and
+      * to_sites / to_frames are ONE kernel each (rows stored straight into the owning rank's buffer; no pack / unpack copy),
+      * the statistics of the 5-D GroupNorm that follows every to_sites ride along with it (no statistics pass, no all-reduce),
+      * the GroupNorms in the middle of a temporal block exchange 2 x 32 floats per sample through the same flag protocol.
+    The receive buffers are reused by every switch (one per direction): tensors returned by to_sites()/to_frames() are views
+    of them and are only valid until the next switch in the same direction -- UNetModel clones the ones it keeps as skips."""
+
+    def __init__(self, dist, rank: int, world: int, group, device, bmax: int = 2):
+        super().__init__(dist, rank, world, group)
+        from . import _lib
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.bmax = bmax
+        self._bufs = {}            # name -> (local tensor, [remote views], nbytes)
+        self._keep = []            # remote storages must stay alive
+        self._ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+        with torch.cuda.device(self.device):
+            flags = torch.zeros(world, dtype=torch.int32, device=self.device)
+            slots = torch.zeros((2, bmax, world, 64), dtype=torch.float32, device=self.device)
+            self.seq = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.done = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.cur_stats = torch.zeros((bmax, world, 32, 2), dtype=torch.float32, device=self.device)
+            self.ws = torch.empty(bmax * 512 * 64, dtype=torch.float32, device=self.device)
+            torch.cuda.synchronize()
+        self.flags, self.peer_flags = self._share(flags)
+        self.slots, self.peer_slots = self._share(slots)
+        c = _lib.PeerComm()
+        c.world, c.rank, c.Bmax = world, rank, bmax
+        c.flags, c.seq, c.done, c.cur_stats = self.flags.data_ptr(), self.seq.data_ptr(), self.done.data_ptr(), self.cur_stats.data_ptr()
+        for q in range(world):
+            c.peer_flags[q] = self.peer_flags[q].data_ptr()
+            c.stats_slots[q] = self.peer_slots[q].data_ptr()
+        self.c = c
+        self._stats_of = None      # data_ptr of the tensor whose statistics cur_stats holds
+
+    # -- CUDA IPC plumbing (setup only) -------------------------------------------------------------
+    def _share(self, t: torch.Tensor):
+        """Map `t` of every rank of the group into this process; returns (own tensor, [view of rank q's tensor])."""
+        import ctypes as C
+        from . import _lib
+        handle = (t.untyped_storage()._share_cuda_(), t.storage_offset(), tuple(t.shape), t.dtype)
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle, group=self.group)
+        views = []
+        for q, (h, off, shape, dtype) in enumerate(handles):
+            if q == self.rank:
+                views.append(t)
+                continue
+            _lib.check(self.lib.vc_enable_peer_access(int(h[0])), "vc_enable_peer_access")
+            st = torch.UntypedStorage._new_shared_cuda(*h)
+            v = torch.empty(0, dtype=dtype, device=st.device).set_(st, off, shape)
+            self._keep.append(st)
+            views.append(v)
+        self.dist.barrier(group=self.group)
+        return t, views
+
+    def _buffer(self, name: str, numel: int, dtype=torch.float16):
+        """Receive buffer `name` with room for `numel` elements on EVERY rank (collective: all ranks grow it together)."""
+        ent = self._bufs.get(name)
+        if ent is None or ent[0].numel() < numel:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PeerFrameComm: a receive buffer must grow during CUDA-graph capture; run one eager forward first")
+            torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)          # nobody still writes into the old mapping
+            with torch.cuda.device(self.device):
+                t = torch.empty(numel, dtype=dtype, device=self.device)
+            ent = self._share(t)
+            self._bufs[name] = ent
+        return ent
+
+    def _exchange(self, h: torch.Tensor, B: int, HW: int, to_sites: bool) -> torch.Tensor:
+        import ctypes as C
+        from . import _lib
+        P, Cc = self.world, h.shape[1]
+        assert HW % P == 0, f"H*W={HW} must be divisible by the world size {P}"
+        assert h.is_contiguous() and h.dtype == torch.float16 and B <= self.bmax
+        HWl = HW // P
+        Tl = self.ranges[self.rank][1] - self.ranges[self.rank][0]
+        tmax = max(f1 - f0 for f0, f1 in self.ranges)
+        out_rows = B * self.T * HWl if to_sites else B * Tl * HW
+        cap = B * (self.T * HWl if to_sites else tmax * HW) * Cc        # same on every rank
+        own, views, = self._buffer("sites" if to_sites else "frames", cap)
+        dst = (C.c_void_p * P)(*[v.data_ptr() for v in views])
+        f0 = (C.c_int32 * (P + 1))(*([r[0] for r in self.ranges] + [self.T]))
+        _lib.check(self.lib.vc_peer_exchange(C.byref(self.c), h.data_ptr(), dst, int(to_sites), B, self.T, HW, Cc, f0, int(to_sites),
+                                             self.ws.data_ptr(), self.ws.numel() * 4, torch.cuda.current_stream().cuda_stream), "vc_peer_exchange")
+        sent = h.numel() * 2
+        self.bytes_moved += sent * (P - 1) // P if to_sites else sent - B * Tl * HWl * Cc * 2
+        out = own[:out_rows * Cc].view(out_rows, Cc)
+        self._stats_of = out.data_ptr() if to_sites else None
+        return out
+
+    def to_sites(self, h: torch.Tensor, B: int, HW: int) -> torch.Tensor:
+        return self._exchange(h, B, HW, True)
+
+    def to_frames(self, t: torch.Tensor, B: int, HW: int) -> torch.Tensor:
+        return self._exchange(t, B, HW, False)
+
+    def groupnorm5d(self, x, B, gamma, beta, eps, silu, stat_rows, fresh: bool):
+        import ctypes as C
+        from . import _lib, ops
+        stream = torch.cuda.current_stream().cuda_stream
+        rows, Cc = x.shape
+        if not (fresh and self._stats_of == x.data_ptr()):
+            _lib.check(self.lib.vc_peer_groupnorm_stats(C.byref(self.c), x.data_ptr(), Cc, B, rows // B, self.ws.data_ptr(), self.ws.numel() * 4,
+                                                        stream), "vc_peer_groupnorm_stats")
+        self._stats_of = None
+        out = torch.empty_like(x)
+        _lib.check(self.lib.vc_groupnorm_apply_parts(x.data_ptr(), Cc, B, rows // B, self.cur_stats.data_ptr(), self.world, stat_rows,
+                                                     gamma.data_ptr(), beta.data_ptr(), eps, int(silu), out.data_ptr(), stream),
+                   "vc_groupnorm_apply_parts")
+        return out
+
+    def owns(self, t: torch.Tensor) -> bool:
+        """True if `t` is a view of one of the reusable receive buffers."""
+        p = t.data_ptr()
+        return any(ent[0].data_ptr() <= p < ent[0].data_ptr() + ent[0].numel() * 2 for ent in self._bufs.values())
 
 
 class CfgComm:
     """Classifier-free-guidance split: the conditional and unconditional U-Net forwards of a DDIM step are independent
     (ddim.py:223-224), so the first half of the ranks computes `cond`, the second half `uncond`, and rank i swaps its
-    3.7 MB prediction with rank i + world/2 through a 2-rank all-reduce."""
+    3.7 MB prediction with rank i + world/2 through a 2-rank all-gather."""
 
     def __init__(self, dist, branch: int, pair_group):
         self.dist, self.branch, self.pair_group = dist, branch, pair_group
 
     def exchange(self, v_mine: torch.Tensor):
-        buf = torch.zeros((2, *v_mine.shape), device=v_mine.device, dtype=v_mine.dtype)
-        buf[self.branch] = v_mine
-        self.dist.all_reduce(buf, group=self.pair_group)
+        buf = v_mine.new_empty((2, *v_mine.shape))
+        self.dist.all_gather_into_tensor(buf.view(-1), v_mine.contiguous().view(-1), group=self.pair_group)   # pair group rank order = (cond, uncond)
         return buf[0], buf[1]
 
 
-def shard_model(model, dist, rank: int, world: int, cfg_split: bool = True):
+def _make_comm(dist, rank, world, group, device, peer: bool):
+    if peer and world > 1 and device is not None and torch.device(device).type == "cuda":
+        return PeerFrameComm(dist, rank, world, group, device)
+    return FrameComm(dist, rank, world, group)
+
+
+def shard_model(model, dist, rank: int, world: int, cfg_split: bool = True, peer: bool = None):
     """Distribute the denoise step over `world` ranks (weights stay replicated: 2.9 GB fp16 per GPU).
 
     world even and cfg_split: 2-way CFG split x (world/2)-way frame sharding -- e.g. 8 GPUs = 2 x 4 with frames 7/6/6/6
     (ideal 7.1x) instead of 8-way frames 4/3x7 (ideal 6.25x).  Otherwise pure frame sharding.
     Every rank must call this (it creates process groups collectively).  Returns the FrameComm (or None)."""
     unet = model.model.diffusion_model if hasattr(model, "model") else model
+    try:
+        device = next(unet.parameters()).device
+    except StopIteration:
+        device = None
+    if peer is None:           # NVLink peer-memory kernels on CUDA (VC_PEER_COMM=0: NCCL collectives); the CPU double uses gloo
+        import os
+        peer = os.environ.get("VC_PEER_COMM", "1") != "0"
     if cfg_split and world % 2 == 0 and hasattr(model, "model"):
         P = world // 2
         frame_groups = [dist.new_group(list(range(b * P, (b + 1) * P))) for b in range(2)]
         pair_groups = [dist.new_group([i, i + P]) for i in range(P)]
         branch, r = rank // P, rank % P
         model._cfg = CfgComm(dist, branch, pair_groups[r])
-        unet._comm = FrameComm(dist, r, P, frame_groups[branch]) if P > 1 else None
+        unet._comm = _make_comm(dist, r, P, frame_groups[branch], device, peer) if P > 1 else None
         return unet._comm
-    unet._comm = FrameComm(dist, rank, world, None)
+    unet._comm = _make_comm(dist, rank, world, None, device, peer)
     return unet._comm

@@ -374,19 +374,18 @@ class UNetModel(nn.Module):
             t = ident = comm.to_sites(h2, B, HW) if comm else h2
             Tg, HWl = (comm.T, HW // comm.world) if comm else (T, HW)
             for i, (g, be, w3, b3) in enumerate(P["tconv"]):
-                t = UNetModel._gn5d(t, B, g, be, 1e-5, True, comm, Tg * HW)               # statistics over (C/32, T, H, W)
+                t = UNetModel._gn5d(t, B, g, be, 1e-5, True, comm, Tg * HW, fresh=(i == 0))   # statistics over (C/32, T, H, W)
                 t = ops.conv_temporal(t, B, Tg, HWl, w3, bias=b3, res=ident if i == 3 else None)
             h2 = comm.to_frames(t, B, HW) if comm else t
         return h2
 
     @staticmethod
-    def _gn5d(x, B, gamma, beta, eps, silu, comm, stat_rows):
-        """GroupNorm whose statistics span all frames (and, when sharded, all GPUs: one tiny all-reduce of [B,32,2])."""
+    def _gn5d(x, B, gamma, beta, eps, silu, comm, stat_rows, fresh=False):
+        """GroupNorm whose statistics span all frames (and, when sharded, all GPUs: [B,32,2] partial sums are exchanged --
+        riding on the layout switch when `fresh`, i.e. x is what comm.to_sites() just returned)."""
         if not comm:
             return ops.groupnorm(x, B, gamma, beta, eps, silu)
-        st = ops.groupnorm_stats(x, B)
-        comm.all_reduce(st)
-        return ops.groupnorm_apply(x, B, st, stat_rows, gamma, beta, eps, silu)
+        return comm.groupnorm5d(x, B, gamma, beta, eps, silu, stat_rows, fresh)
 
     @staticmethod
     def _spatial_tf(P, h, ctx, B, T, H, W, expand=False):
@@ -427,7 +426,7 @@ class UNetModel(nn.Module):
         C = heads * 64
         Tg, HWl = (comm.T, HW // comm.world) if comm else (T, HW)
         t_in = comm.to_sites(h, B, HW) if comm else h
-        x = ops.linear(UNetModel._gn5d(t_in, B, *P["gn"], 1e-6, False, comm, Tg * HW), P["in_w"], bias=P["in_b"])
+        x = ops.linear(UNetModel._gn5d(t_in, B, *P["gn"], 1e-6, False, comm, Tg * HW, fresh=True), P["in_w"], bias=P["in_b"])
         for Q in P["blocks"]:
             for ln, wqkv, ow, ob in (("ln1", "qkv1", "o1_w", "o1_b"), ("ln2", "qkv2", "o2_w", "o2_b")):
                 qkv = _ln_linear(Q, x, wqkv, ln)
@@ -600,6 +599,8 @@ class UNetModel(nn.Module):
             h, H, W = self._run_stage(stage, h, None, emb, ctx, B, T, H, W)
             if i == 0 and self.addition_attention:
                 h, H, W = self._run_stage(P["init_attn"], h, None, emb, ctx, B, T, H, W)
+            if comm and getattr(comm, "owns", None) and comm.owns(h):
+                h = h.clone()                      # a skip outlives the reusable peer receive buffer it was delivered in
             hs.append(h)
         h, H, W = self._run_stage(P["middle"], h, None, emb, ctx, B, T, H, W)
         for stage in P["output"]:
