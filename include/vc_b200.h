@@ -56,6 +56,9 @@ typedef struct vc_gemm_desc {
    * out[r,n] = rstd[r] * (acc[r,n] - mean[r] * ln_colsum[n]) + bias[n].  NULL = plain GEMM.  num_taps must be 1. */
   const float* ln_stats;             /* [rows][2] fp32 (mean, rstd) from vc_layernorm_stats                */
   const float* ln_colsum;            /* [N] fp32: sum_k w[n,k] of the fp16 weights                         */
+  /* optional by-product for the NEXT LayerNorm: partial (sum, sumsq) of the fp16-rounded output, per row and 32-column chunk,
+   * ln_part[(n/32) * M + row][2]; plain fp16 [M,N] outputs with N % 32 == 0 only.  vc_layernorm_stats_from_parts finishes them. */
+  float* ln_part;
 } vc_gemm_desc;
 int vc_gemm_tap(const vc_gemm_desc* d, void* stream);
 /* N-tile width the kernel will use for (N, geglu): needed to interleave GEGLU weights on the host */
@@ -105,6 +108,8 @@ int vc_groupnorm_apply_parts(const void* x1, int32_t C1, int32_t samples, int64_
 /* statistics half of nn.LayerNorm: stats[row] = (mean, 1/sqrt(var + eps)) in fp32; the normalisation is applied by the
  * consuming vc_gemm_tap (ln_stats / ln_colsum), so the normalised activation is never written to memory */
 int vc_layernorm_stats(const void* x, int64_t rows, int32_t C, float eps, float* stats, void* stream);
+/* the same statistics from the partial sums a producing vc_gemm_tap left in ln_part ([C/32][rows][2] fp32): no re-read of x */
+int vc_layernorm_stats_from_parts(const float* parts, int64_t rows, int32_t C, float eps, float* stats, void* stream);
 /* nn.LayerNorm over the last dim (attention.py:233-235), fp16 in/out, fp32 statistics */
 int vc_layernorm(const void* x, int64_t rows, int32_t C, const float* gamma, const float* beta, float eps, void* out,
                  void* stream);

@@ -71,7 +71,7 @@ def _h(t):
     return t.to(torch.float16)
 
 
-def linear(x, w, bias=None, res=None, geglu=False, out=None, out_f32=False, x2=None, ln=None):
+def linear(x, w, bias=None, res=None, geglu=False, out=None, out_f32=False, x2=None, ln=None, ln_out=False):
     # the kernel's host-side contract (gemm_tap.cu: TMA strides are 16-byte multiples)
     # (the double's own norm ops may hand back permuted views; only row-major operands carry a meaningful pitch)
     assert w.shape[1] % 8 == 0, w.shape
@@ -94,8 +94,8 @@ def linear(x, w, bias=None, res=None, geglu=False, out=None, out_f32=False, x2=N
     y = y if out_f32 else _h(y)
     if out is not None:
         out[:, :y.shape[1]].copy_(y)
-        return out
-    return y
+        y = out
+    return (y, layernorm_stats(y)) if ln_out else y
 
 
 def _rows_to_nchw(x, frames, H, W):

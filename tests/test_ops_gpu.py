@@ -389,3 +389,21 @@ def test_gemm_cta_pair_path(ops):
 def test_softmax_rows(ops):
     x = rnd(200, 1000, seed=71, dtype=torch.float32, scale=20.0)
     close(ops.softmax_rows(x, 0.044), torch.softmax(x * 0.044, -1), 1e-4, rtol=2e-3, what="softmax_rows")
+
+
+@pytest.mark.parametrize("M,K,N,res", [(777, 320, 320, True), (4096, 1280, 640, True), (300, 512, 512, False)])
+def test_linear_emits_layernorm_statistics_of_its_output(ops, M, K, N, res):
+    """ops.linear(..., ln_out=True): the (mean, rstd) the producing GEMM's epilogue gathers equal a statistics pass over the stored
+    fp16 output (both use the fp16-rounded values); the output itself is unchanged."""
+    x, w = rnd(M, K, seed=41), rnd(N, K, scale=0.05, seed=42)
+    b = torch.randn(N, generator=torch.Generator().manual_seed(43)).cuda() * 0.1
+    r = rnd(M, N, seed=44) if res else None
+    y_ref = ops.linear(x, w, bias=b, res=r)
+    y, st = ops.linear(x, w, bias=b, res=r, ln_out=True)
+    assert torch.equal(y, y_ref)
+    ref = ops.layernorm_stats(y_ref)
+    yf = y_ref.float()
+    mean, rstd = yf.mean(1), torch.rsqrt(yf.var(1, unbiased=False) + 1e-5)
+    assert float((st[:, 0] - mean).abs().max()) < 2e-4 * max(1.0, float(mean.abs().max()))
+    assert float(((st[:, 1] - rstd) / rstd).abs().max()) < 2e-4
+    assert float((st - ref).abs().max()) < 1e-3

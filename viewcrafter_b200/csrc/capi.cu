@@ -33,7 +33,7 @@ int vc_gemm_tap(const vc_gemm_desc* c, void* stream) {
   for (int i = 0; i < 9; ++i) { d.tap_dx[i] = c->tap_dx[i]; d.tap_dy[i] = c->tap_dy[i]; }
   d.out = HM(c->out); d.out_f32 = reinterpret_cast<float*>(c->out_f32); d.ldo = c->ldo;
   d.bias = c->bias; d.bias_z_div = c->bias_z_div; d.res = H(c->res); d.ldr = c->ldr; d.geglu = c->geglu;
-  d.ln_stats = c->ln_stats; d.ln_colsum = c->ln_colsum;
+  d.ln_stats = c->ln_stats; d.ln_colsum = c->ln_colsum; d.ln_part = c->ln_part;
   COUNT(1);
   return gemm_tap(d, ST(stream));
 }
@@ -82,6 +82,10 @@ int vc_groupnorm_apply_parts(const void* x1, int32_t C1, int32_t samples, int64_
 int vc_layernorm_stats(const void* x, int64_t rows, int32_t C, float eps, float* stats, void* stream) {
   COUNT(1);
   return layernorm_stats(H(x), rows, C, eps, stats, ST(stream));
+}
+int vc_layernorm_stats_from_parts(const float* parts, int64_t rows, int32_t C, float eps, float* stats, void* stream) {
+  COUNT(1);
+  return layernorm_stats_from_parts(parts, rows, C, eps, stats, ST(stream));
 }
 int vc_layernorm(const void* x, int64_t rows, int32_t C, const float* gamma, const float* beta, float eps, void* out, void* stream) {
   COUNT(1);

@@ -39,6 +39,16 @@ static inline FastDiv make_fastdiv(int d) {
 __device__ __forceinline__ int fast_div(const FastDiv& f, int n) { return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr); }
 #endif
 
+// the profiling branches are compiled out of the shipped kernels (they sat inside the producer / MMA / epilogue loops)
+#ifndef VC_GEMM_DEBUG_BUILD
+#define VC_GEMM_DEBUG_BUILD 0
+#endif
+#if VC_GEMM_DEBUG_BUILD
+#define VC_GEMM_DBG(p, bit) ((p).debug & (bit))
+#else
+#define VC_GEMM_DBG(p, bit) 0
+#endif
+
 struct GemmParams {
   CUtensorMap tmap_a;
   CUtensorMap tmap_a2;
@@ -65,10 +75,12 @@ struct GemmParams {
   int geglu;
   const float* ln_stats;   // folded LayerNorm: per-row (mean, rstd); nullptr = plain
   const float* ln_colsum;  // folded LayerNorm: per-column sum of the (gamma-scaled) weights
+  float2* ln_part;         // optional: per (32-column chunk, row) partial (sum, sumsq) of the fp16-rounded outputs, [N/32][ln_rows]:
+  long long ln_rows;       //   the LayerNorm statistics of the tensor this GEMM writes, gathered while it is still in registers
   int out_tma;           // fp16 output written by TMA stores from per-warp staging tiles (full-line, LSU-free)
   int vec_ok;            // rows are 32-byte aligned: the 256-bit epilogue path may be used
-  int debug;             // profiling aid (VC_GEMM_DEBUG): 1 = skip the MMAs (feed rate only), 2 = skip TMA (MMA rate only),
-                         // 4 = skip the epilogue body; results are garbage in these modes
+  int debug;             // profiling aid, only honoured by builds with -DVC_GEMM_DEBUG_BUILD=1 (env VC_GEMM_DEBUG): 1 = skip the MMAs
+                         // (feed rate only), 2 = skip TMA (MMA rate only), 4 = skip the epilogue body; results are garbage then
 };
 
 struct TileCoord {
@@ -308,7 +320,7 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, int tile
 
       mbar_wait(&tmem_full_bar[acc], aph);          // accumulator complete
       tc_fence_after();
-      if (!(p.debug & 4)) {
+      if (!VC_GEMM_DBG(p, 4)) {
 #pragma unroll
         for (int j = 0; j < MAXC; ++j) {
           if (j >= nmy) break;                       // warp-uniform
@@ -359,6 +371,16 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, int tile
           // rres is free again: request the residual of this warp's next chunk before storing this one
           if (j + 1 < nmy) epi_res_prefetch<BN>(p, cur, c + EPI_PER_QUAD, rres);
           else if (has_next) epi_res_prefetch<BN>(p, nxt, nxt.c_first, rres);
+          if (p.ln_part) {                           // LayerNorm statistics of the OUTPUT row, as stored (fp16-rounded)
+            float2 s2 = make_float2(0.f, 0.f), q2 = s2;
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const float2 r = __half22float2(__floats2half2_rn(f[e], f[e + 1]));
+              s2 = __fadd2_rn(s2, r);
+              q2 = __ffma2_rn(r, r, q2);
+            }
+            if (cur.row_ok) p.ln_part[(long long)(nb >> 5) * p.ln_rows + cur.orow] = make_float2(s2.x + s2.y, q2.x + q2.y);
+          }
           epi_store32(p, cur, nb, p.N, f, p.res != nullptr && !vec, stage, lane);
         }
       }
@@ -383,7 +405,7 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, int tile
       const float nm = -ln.x;
       mbar_wait(&tmem_full_bar[acc], aph);
       tc_fence_after();
-      if (!(p.debug & 4)) {
+      if (!VC_GEMM_DBG(p, 4)) {
 #pragma unroll
         for (int j = 0; j < MAXC; ++j) {
           const int c = cur.c_first + j * EPI_PER_QUAD;

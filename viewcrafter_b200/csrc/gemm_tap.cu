@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
           if (elect_one()) {
             uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
-            if (p.debug & 2) {
+            if (VC_GEMM_DBG(p, 2)) {
               mbar_arrive(&full_bar[s]);
             } else {
               mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (elect_one()) {
-          if (p.debug & 1) {
+          if (VC_GEMM_DBG(p, 1)) {
             mbar_arrive(&empty_bar[s]);
           } else {
             const uint32_t la = desc_lo + (uint32_t)(s * (Cfg::STAGE_BYTES >> 4));
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       if (elect_one()) {
-        if (p.debug & 1) mbar_arrive(&tmem_full_bar[acc]);
+        if (VC_GEMM_DBG(p, 1)) mbar_arrive(&tmem_full_bar[acc]);
         else umma_commit(&tmem_full_bar[acc]);   // accumulator complete
       }
       __syncwarp();
@@ -289,6 +289,10 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   VC_REQUIRE(!d.ln_stats || ((reinterpret_cast<uintptr_t>(d.ln_stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(d.ln_colsum) & 15) == 0),
              "gemm_tap: ln_stats / ln_colsum misaligned");
   p.ln_stats = d.ln_stats; p.ln_colsum = d.ln_colsum;
+  VC_REQUIRE(!d.ln_part || (d.num_taps == 1 && d.N % 32 == 0 && d.Y == 1 && d.Z == 1 && !d.geglu && d.out && !d.out_f32 &&
+                            (reinterpret_cast<uintptr_t>(d.ln_part) & 7) == 0),
+             "gemm_tap: LayerNorm partial sums need a plain fp16 [M,N] output with N %% 32 == 0");
+  p.ln_part = reinterpret_cast<float2*>(d.ln_part); p.ln_rows = d.X;
   // 256-bit epilogue accesses need 32-byte aligned rows (true for every activation on the U-Net / VAE path); anything
   // else (odd pitches, the 4- and 3-channel output convs) takes the predicated scalar path inside the kernel
   const bool o_al = ((reinterpret_cast<uintptr_t>(optr) & 31) == 0) && ((long long)d.ldo * esz) % 32 == 0;

@@ -27,6 +27,9 @@ struct GemmDesc {
   // ln_stats: [rows][2] fp32 (mean, rstd) from layernorm_stats; ln_colsum[n] = sum_k w[n,k] (of the fp16 weights). 1 tap only.
   const float* ln_stats = nullptr;
   const float* ln_colsum = nullptr;
+  // LayerNorm statistics of the OUTPUT, gathered in the epilogue: ln_part[(n / 32) * X + row] = (sum, sumsq) over the 32 output
+  // columns [n, n + 32) of the row, of the fp16-rounded values; layernorm_stats_from_parts turns them into (mean, rstd)
+  float* ln_part = nullptr;
 };
 int gemm_tap(const GemmDesc& d, cudaStream_t stream);
 
@@ -59,6 +62,7 @@ int groupnorm_apply(const __half* x1, int C1, const __half* x2, int C2, int samp
                     cudaStream_t stream, int stat_parts = 1);
 
 int layernorm_stats(const __half* x, long long rows, int C, float eps, float* stats, cudaStream_t stream);
+int layernorm_stats_from_parts(const float* parts, long long rows, int C, float eps, float* stats, cudaStream_t stream);
 int layernorm_rows(const __half* x, long long rows, int C, const float* gamma, const float* beta, float eps, __half* out,
                    cudaStream_t stream);
 

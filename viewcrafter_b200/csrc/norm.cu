@@ -581,6 +581,30 @@ __global__ void __launch_bounds__(256) ln_stats_unrolled_kernel(const __half* __
   }
 }
 
+// (mean, rstd) per row from the per-32-column partial sums a producing GEMM left in parts[C/32][rows] (GemmDesc::ln_part):
+// reads C/32 * 8 bytes per row instead of 2 C bytes -- the LayerNorm statistics pass without re-reading the activation.
+__global__ void __launch_bounds__(256) ln_finalize_kernel(const float2* __restrict__ parts, long long rows, int nchunks, float invC, float eps,
+                                                          float2* __restrict__ stats) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  float s = 0.f, q = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float2 v = __ldg(parts + (long long)c * rows + row);
+    s += v.x; q += v.y;
+  }
+  const float mean = s * invC;
+  const float var = fmaxf(q * invC - mean * mean, 0.f);
+  stats[row] = make_float2(mean, rsqrtf(var + eps));
+}
+
+int layernorm_stats_from_parts(const float* parts, long long rows, int C, float eps, float* stats, cudaStream_t stream) {
+  VC_REQUIRE(parts && stats && rows > 0 && C % 32 == 0, "layernorm_stats_from_parts: bad args");
+  ln_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float2*>(parts), rows, C / 32, 1.f / (float)C, eps,
+                                                                        reinterpret_cast<float2*>(stats));
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
 int layernorm_stats(const __half* x, long long rows, int C, float eps, float* stats, cudaStream_t stream) {
   VC_REQUIRE(x && stats, "layernorm_stats: null pointer");
   VC_REQUIRE(C % 8 == 0 && C <= 8192 && rows > 0, "layernorm_stats: unsupported C=%d rows=%lld", C, rows);

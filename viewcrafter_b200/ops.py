@@ -7,6 +7,7 @@ falls back to a PyTorch implementation.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -143,11 +144,16 @@ def _gemm(desc: GemmDesc):
     check(_lib.load().vc_gemm_tap(C.byref(desc), _stream()), "vc_gemm_tap")
 
 
+LN_FROM_PRODUCER = os.environ.get("VC_LN_FROM_PRODUCER", "1") != "0"   # A/B switch: LayerNorm statistics from the producing GEMM's epilogue
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
            geglu: bool = False, out: Optional[torch.Tensor] = None, out_f32: bool = False,
-           x2: Optional[torch.Tensor] = None, ln=None) -> torch.Tensor:
+           x2: Optional[torch.Tensor] = None, ln=None, ln_out: bool = False):
     """y = [x|x2] @ w.T (+bias) (GEGLU) (+res).  x: [M,K1] fp16 (row pitch = x.stride(0)), w: [N,K] fp16.
-    ln = (stats [M,2] fp32 from layernorm_stats(x), colsum [N] fp32): LayerNorm folded into the epilogue (fold_layernorm)."""
+    ln = (stats [M,2] fp32 from layernorm_stats(x), colsum [N] fp32): LayerNorm folded into the epilogue (fold_layernorm).
+    ln_out: also return the LayerNorm statistics [M,2] (mean, rstd) of y -- y feeds a LayerNorm next (attention.py:283-292); the
+    epilogue leaves per-32-column partial sums of the rows it is writing and a tiny kernel finishes them, so y is not re-read."""
     _chk16(x, "linear.x"); _chk16(w, "linear.w")
     M, K1 = x.shape
     N, K = w.shape
@@ -178,8 +184,18 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         assert stats.shape == (M, 2) and stats.dtype == torch.float32 and stats.is_contiguous()
         assert colsum.shape == (N,) and colsum.dtype == torch.float32 and colsum.is_contiguous()
         d.ln_stats, d.ln_colsum = stats.data_ptr(), colsum.data_ptr()
+    if not ln_out:
+        _gemm(d)
+        return out
+    if not (LN_FROM_PRODUCER and n_out % 32 == 0 and not geglu and not out_f32 and out.is_contiguous()):
+        _gemm(d)
+        return out, layernorm_stats(out)
+    parts = torch.empty((n_out // 32, M, 2), device=x.device, dtype=torch.float32)
+    d.ln_part = parts.data_ptr()
     _gemm(d)
-    return out
+    st = torch.empty((M, 2), device=x.device, dtype=torch.float32)
+    check(_lib.load().vc_layernorm_stats_from_parts(parts.data_ptr(), M, n_out, 1e-5, st.data_ptr(), _stream()), "vc_layernorm_stats_from_parts")
+    return out, st
 
 
 def _conv_box(H: int, W: int):

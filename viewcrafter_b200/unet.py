@@ -33,10 +33,11 @@ def _zero(m: nn.Module) -> nn.Module:
 _LN_FOLD = os.environ.get("VC_LN_FOLD", "1") != "0"   # fold norm1/2/3 into their consumer GEMMs (A/B switch, read at import)
 
 
-def _ln_linear(Q: dict, x: torch.Tensor, name: str, ln: str, **kw) -> torch.Tensor:
-    """LayerNorm -> Linear of a transformer block: folded (statistics pass + GEMM epilogue) or as two passes."""
+def _ln_linear(Q: dict, x: torch.Tensor, name: str, ln: str, st=None, **kw) -> torch.Tensor:
+    """LayerNorm -> Linear of a transformer block: folded (row statistics + GEMM epilogue) or as two passes.  `st`: the (mean, rstd)
+    of x if the GEMM that produced x already gathered them (ops.linear(..., ln_out=True)); otherwise a statistics pass reads x."""
     if Q[name + "_cs"] is not None:
-        return ops.linear(x, Q[name], bias=Q[name + "_b"], ln=(ops.layernorm_stats(x), Q[name + "_cs"]), **kw)
+        return ops.linear(x, Q[name], bias=Q[name + "_b"], ln=(st if st is not None else ops.layernorm_stats(x), Q[name + "_cs"]), **kw)
     return ops.linear(ops.layernorm(x, *Q[ln]), Q[name], bias=Q[name + "_b"], **kw)
 
 
@@ -395,15 +396,19 @@ class UNetModel(nn.Module):
         Bc = 1 if expand else B
         BT, HW, heads = Bc * T, H * W, P["heads"]
         C = heads * 64
-        x = ops.linear(ops.groupnorm(h, BT, *P["gn"], 1e-6, False), P["in_w"], bias=P["in_b"])
+        fold = _LN_FOLD
+        x = ops.linear(ops.groupnorm(h, BT, *P["gn"], 1e-6, False), P["in_w"], bias=P["in_b"], ln_out=fold)
+        x, st = x if fold else (x, None)
         for Q in P["blocks"]:
-            qkv = _ln_linear(Q, x, "qkv1", "ln1")
+            qkv = _ln_linear(Q, x, "qkv1", "ln1", st)
             a = ops.flash_attn(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], BT, HW, HW, heads)
-            x = ops.linear(a, Q["o1_w"], bias=Q["o1_b"], res=x)
+            x = ops.linear(a, Q["o1_w"], bias=Q["o1_b"], res=x, ln_out=fold)
+            x, st = x if fold else (x, None)
             if expand:
                 x, h = torch.cat([x, x], 0), torch.cat([h, h], 0)
+                st = torch.cat([st, st], 0) if st is not None else None
                 expand, Bc, BT = False, B, B * T
-            q = _ln_linear(Q, x, "q2", "ln2")
+            q = _ln_linear(Q, x, "q2", "ln2", st)
             a = torch.empty_like(q)
             for b in range(Bc):
                 rows = slice(b * T * HW, (b + 1) * T * HW)
@@ -415,9 +420,12 @@ class UNetModel(nn.Module):
                         ops.flash_attn(q[rows], ki[:, :C], ki[:, C:], T, HW, ki.shape[0] // T, heads, out=a[rows], accumulate=True)
                     else:
                         ops.flash_attn(q[rows], ki[:, :C], ki[:, C:], T, HW, ki.shape[0], heads, kv_shared=True, out=a[rows], accumulate=True)
-            x = ops.linear(a, Q["o2_w"], bias=Q["o2_b"], res=x)
-            g = _ln_linear(Q, x, "ff1", "ln3", geglu=True)
-            x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x)
+            x = ops.linear(a, Q["o2_w"], bias=Q["o2_b"], res=x, ln_out=fold)
+            x, st = x if fold else (x, None)
+            g = _ln_linear(Q, x, "ff1", "ln3", st, geglu=True)
+            last = Q is P["blocks"][-1]
+            x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x, ln_out=fold and not last)
+            x, st = x if (fold and not last) else (x, None)
         return ops.linear(x, P["out_w"], bias=P["out_b"], res=h)
 
     @staticmethod
@@ -426,17 +434,22 @@ class UNetModel(nn.Module):
         C = heads * 64
         Tg, HWl = (comm.T, HW // comm.world) if comm else (T, HW)
         t_in = comm.to_sites(h, B, HW) if comm else h
-        x = ops.linear(UNetModel._gn5d(t_in, B, *P["gn"], 1e-6, False, comm, Tg * HW, fresh=True), P["in_w"], bias=P["in_b"])
+        fold = _LN_FOLD
+        x = ops.linear(UNetModel._gn5d(t_in, B, *P["gn"], 1e-6, False, comm, Tg * HW, fresh=True), P["in_w"], bias=P["in_b"], ln_out=fold)
+        x, st = x if fold else (x, None)
         for Q in P["blocks"]:
             for ln, wqkv, ow, ob in (("ln1", "qkv1", "o1_w", "o1_b"), ("ln2", "qkv2", "o2_w", "o2_b")):
-                qkv = _ln_linear(Q, x, wqkv, ln)
+                qkv = _ln_linear(Q, x, wqkv, ln, st)
                 a = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=torch.float16)
                 for b in range(B):
                     rows = slice(b * Tg * HWl, (b + 1) * Tg * HWl)
                     ops.temporal_attn(qkv[rows, :C], qkv[rows, C:2 * C], qkv[rows, 2 * C:], Tg, HWl, heads, out=a[rows])
-                x = ops.linear(a, Q[ow], bias=Q[ob], res=x)
-            g = _ln_linear(Q, x, "ff1", "ln3", geglu=True)
-            x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x)
+                x = ops.linear(a, Q[ow], bias=Q[ob], res=x, ln_out=fold)
+                x, st = x if fold else (x, None)
+            g = _ln_linear(Q, x, "ff1", "ln3", st, geglu=True)
+            last = Q is P["blocks"][-1]
+            x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x, ln_out=fold and not last)
+            x, st = x if (fold and not last) else (x, None)
         out = ops.linear(x, P["out_w"], bias=P["out_b"], res=t_in)
         return comm.to_frames(out, B, HW) if comm else out
 
