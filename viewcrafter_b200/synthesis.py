@@ -11,6 +11,8 @@ What differs from the reference, all parity-preserving:
   * the sampler is created with ``batch_cfg=True``: cond + uncond run as one B=2 U-Net forward with the context-free prefix
     computed once, and -- because the same ``cond`` / ``uc`` tensors are handed to every step and every ``n_samples``
     iteration -- the cross-attention K/V projections are computed once per clip;
+  * ``cuda_graph=True`` lets the viewcrafter_b200 U-Net replay its forward as one captured CUDA graph from the third call on
+    (``UNetModel.enable_cuda_graph``): same kernels in the same order, ~1000 launches -> 1 per forward;
   * nothing else: conditioning tensors, ``x_T`` / per-step noise draws and the decode are the reference's, in its order.
 """
 from __future__ import annotations
@@ -32,7 +34,11 @@ def get_latent_z(model, videos):
 @torch.no_grad()
 def image_guided_synthesis(model, prompts, videos, noise_shape, n_samples=1, ddim_steps=50, ddim_eta=1.,
                            unconditional_guidance_scale=1.0, cfg_img=None, fs=None, text_input=False, multiple_cond_cfg=False,
-                           timestep_spacing='uniform', guidance_rescale=0.0, condition_index=None, batch_cfg=True, **kwargs):
+                           timestep_spacing='uniform', guidance_rescale=0.0, condition_index=None, batch_cfg=True, cuda_graph=True,
+                           **kwargs):
+    unet = getattr(getattr(model, "model", None), "diffusion_model", None)
+    if cuda_graph and hasattr(unet, "enable_cuda_graph") and next(unet.parameters()).is_cuda:
+        unet.enable_cuda_graph()              # the ~100 forwards of a clip share shapes, weights and context: capture once, replay
     ddim_sampler = DDIMSampler(model, batch_cfg=batch_cfg) if not multiple_cond_cfg else DDIMSampler_multicond(model, batch_cfg=batch_cfg)
     batch_size = noise_shape[0]
     fs = torch.tensor([fs] * batch_size, dtype=torch.long, device=model.device)

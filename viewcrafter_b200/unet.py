@@ -215,7 +215,8 @@ class UNetModel(nn.Module):
         self.out = nn.Sequential(nn.GroupNorm(32, ch), nn.SiLU(), _zero(nn.Conv2d(mc, out_channels, 3, padding=1)))
 
         self._packed = None
-        self._kv_caches = []        # cross-attention K/V projections of the last two contexts (see _kv_projector)
+        self._kv_caches = []        # cross-attention K/V projections of the last three contexts (see _kv_projector)
+        self._canon = []            # [ref, version, private snapshot] of the last three contexts (see _canonical_context)
         self._kv_cache = {}
         self._comm = None           # set by viewcrafter_b200.parallel.shard_model for frame-sharded multi-GPU execution
         self._graph_mode = os.environ.get("VC_UNET_GRAPH", "0") == "1"     # see enable_cuda_graph
@@ -228,7 +229,7 @@ class UNetModel(nn.Module):
     # ------------------------------------------------------------------------------------------
     def invalidate_packed(self):
         self._packed = None
-        self._kv_caches, self._kv_cache = [], {}
+        self._kv_caches, self._kv_cache, self._canon = [], {}, []
         self._graphs = {}
 
     def enable_cuda_graph(self, on: bool = True):
@@ -248,7 +249,7 @@ class UNetModel(nn.Module):
         # anything that changes dtypes drops them
         packed = self._packed if ops.is_device_only(fn) else None
         self._packed = None
-        self._kv_caches, self._kv_cache = [], {}
+        self._kv_caches, self._kv_cache, self._canon = [], {}, []
         self._graphs = {}
         r = super()._apply(fn, *a, **k)
         if packed is not None:
@@ -473,6 +474,30 @@ class UNetModel(nn.Module):
                 h = ops.conv3x3(h, B * T, H, W, P["w"], bias=P["b"])
         return h, H, W
 
+    def _canonical_context(self, context: torch.Tensor) -> torch.Tensor:
+        """Map a context tensor to a private, immutable snapshot with the same CONTENT.  The K/V cache and the captured graphs are
+        keyed on the snapshot, so they survive callers that rebuild an equal context every step -- the reference's own
+        DiffusionWrapper does ``torch.cat(c_crossattn, 1)`` per call (ddpm3d.py:1442).  Fast path: same tensor object with the
+        same version counter (no device work).  Otherwise the content is compared with the cached snapshots of the same shape
+        (one ``torch.equal`` = one small device->host sync per forward); a genuinely new context is cloned (1.3 MB)."""
+        ver = ops.tensor_version(context)
+        for ent in self._canon:
+            if ent[0] is context and ent[1] == ver and ver is not None:
+                return ent[2]
+        for i, ent in enumerate(self._canon):
+            snap = ent[2]
+            if snap.shape == context.shape and snap.dtype == context.dtype and snap.device == context.device and bool(torch.equal(snap, context)):
+                ent[0], ent[1] = context, ver
+                self._canon.insert(0, self._canon.pop(i))
+                return snap
+        snap = context.detach().clone()
+        self._canon.insert(0, [context, ver, snap])
+        for ent in self._canon[3:]:                         # evicted snapshots take their K/V projections and graphs along
+            self._kv_caches = [c for c in self._kv_caches if c["ref"] is not ent[2]]
+            self._graphs = {k: g for k, g in self._graphs.items() if g["ctx"] is not ent[2]}
+        del self._canon[3:]
+        return snap
+
     def _kv_projector(self, context: torch.Tensor, img_range):
         """to_k / to_v (and to_k_ip / to_v_ip) of the cross-attentions see only the context, which a sampling run feeds
         unchanged for all its steps: project once per (context tensor, version) and reuse.  The cache
@@ -487,9 +512,9 @@ class UNetModel(nn.Module):
                 break
         if cache is None:
             cache = {"ref": context, "ver": ver, "rng": img_range}
-            self._kv_caches = [cache] + [cnd for cnd in self._kv_caches if cnd["ref"] is not context][:1]
+            self._kv_caches = [cache] + [cnd for cnd in self._kv_caches if cnd["ref"] is not context][:2]
         else:
-            self._kv_caches = [cache] + [cnd for cnd in self._kv_caches if cnd is not cache][:1]
+            self._kv_caches = [cache] + [cnd for cnd in self._kv_caches if cnd is not cache][:2]
         self._kv_cache = cache                     # most recent entry (introspection / tests)
 
         def project(Q, name, tokens, b):
@@ -506,8 +531,10 @@ class UNetModel(nn.Module):
         in x.dtype (openaimodel3d.py:548-603).  Extra kwargs are accepted and ignored like the reference does."""
         if features_adapter is not None:
             _unsupported("features_adapter")
-        if self._graph_mode and x.is_cuda and context is not None and not torch.cuda.is_current_stream_capturing():
-            return self._forward_graphed(x, timesteps, context, fs, kwargs)
+        if x.is_cuda and context is not None and not torch.cuda.is_current_stream_capturing():
+            context = self._canonical_context(context)
+            if self._graph_mode:
+                return self._forward_graphed(x, timesteps, context, fs, kwargs)
         return self._forward_impl(x, timesteps, context, fs, kwargs)
 
     def _forward_graphed(self, x, timesteps, context, fs, kwargs):
