@@ -14,5 +14,5 @@ for f in $SRCS; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT $BUILD/*.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $BUILD/*.o -lcudart
 echo "built $(realpath $OUT)"
