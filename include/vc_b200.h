@@ -59,6 +59,10 @@ typedef struct vc_gemm_desc {
   /* optional by-product for the NEXT LayerNorm: partial (sum, sumsq) of the fp16-rounded output, per row and 32-column chunk,
    * ln_part[(n/32) * M + row][2]; plain fp16 [M,N] outputs with N % 32 == 0 only.  vc_layernorm_stats_from_parts finishes them. */
   float* ln_part;
+  /* optional output pitches in elements along Y and Z (0 = dense: ldo*X and ldo*X*Y); non-dense outputs require an fp16 output
+   * with N % 32 == 0 and no residual.  Upsample (F.interpolate nearest x2, openaimodel3d.py:80-106) + 3x3 conv runs as four
+   * parity sub-convolutions with 2x2 pre-summed taps on the SMALL image, each writing every second pixel of the large one. */
+  int64_t ldo_y, ldo_z;
 } vc_gemm_desc;
 int vc_gemm_tap(const vc_gemm_desc* d, void* stream);
 /* N-tile width the kernel will use for (N, geglu): needed to interleave GEGLU weights on the host */

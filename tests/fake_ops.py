@@ -16,6 +16,7 @@ from viewcrafter_b200 import ops as real
 pack_conv3x3 = real.pack_conv3x3
 pack_conv_temporal = real.pack_conv_temporal
 pack_linear = real.pack_linear
+pack_upconv3x3 = real.pack_upconv3x3
 
 
 def require_cuda(device, who):
@@ -104,6 +105,21 @@ def _rows_to_nchw(x, frames, H, W):
 
 def _nchw_to_rows(y):
     return y.permute(0, 2, 3, 1).reshape(-1, y.shape[1])
+
+
+def upconv3x3(x, frames, H, W, packs, bias=None):
+    """the four parity sub-convolutions exactly as the kernel runs them (2x2 pre-summed taps on the small image)"""
+    xi = _rows_to_nchw(x, frames, H, W)
+    N = packs[0].shape[0] // 4
+    out = torch.zeros((frames, N, 2 * H, 2 * W))
+    for a in (0, 1):
+        for b in (0, 1):
+            w4 = packs[a * 2 + b].float().reshape(2, 2, N, -1).permute(2, 3, 0, 1)        # [N, K, r, c]
+            xp = F.pad(xi, (1 - b, b, 1 - a, a))                                           # taps at i + r + a - 1, j + c + b - 1
+            out[:, :, a::2, b::2] = F.conv2d(xp, w4)
+    if bias is not None:
+        out = out + bias.view(1, -1, 1, 1)
+    return _h(_nchw_to_rows(out))
 
 
 def conv3x3(x, frames, H, W, w9, bias=None, res=None, x2=None, bias_z_div=0, out_f32=False, out=None):

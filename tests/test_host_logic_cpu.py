@@ -332,3 +332,21 @@ def test_posterior_class_subclasses_a_loaded_reference_class(monkeypatch):
     assert post.sample(noise=torch.ones(1, 4, 2, 2)).shape == (1, 4, 2, 2)
     monkeypatch.delitem(sys.modules, "lvdm.distributions")
     assert D.posterior_class() is D.DiagonalGaussianDistribution
+
+
+def test_upsample_conv_parity_decomposition_equals_interpolate_then_conv():
+    """pack_upconv3x3: Upsample(nearest x2) + conv3x3 as four 2x2 sub-convolutions with pre-summed taps (openaimodel3d.py:80-106)."""
+    import torch.nn.functional as F
+    from tests import fake_ops
+    g = torch.Generator().manual_seed(77)
+    N, H, W, Ci, Co = 2, 5, 6, 8, 32
+    x = torch.randn(N, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, 3, 3, generator=g) * 0.2
+    b = torch.randn(Co, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, b, padding=1)
+    rows = x.permute(0, 2, 3, 1).reshape(-1, Ci).half()
+    y = fake_ops.upconv3x3(rows, N, H, W, fake_ops.pack_upconv3x3(w), bias=b)
+    y = y.float().reshape(N, 2 * H, 2 * W, Co).permute(0, 3, 1, 2)
+    ref16 = F.conv2d(F.interpolate(x.half().float(), scale_factor=2, mode="nearest"), w, b, padding=1)
+    assert float((y - ref16).abs().max()) < 2e-2, float((y - ref16).abs().max())
+    assert float((y - ref).abs().max()) < 3e-2

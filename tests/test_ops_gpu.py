@@ -407,3 +407,16 @@ def test_linear_emits_layernorm_statistics_of_its_output(ops, M, K, N, res):
     assert float((st[:, 0] - mean).abs().max()) < 2e-4 * max(1.0, float(mean.abs().max()))
     assert float(((st[:, 1] - rstd) / rstd).abs().max()) < 2e-4
     assert float((st - ref).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("frames,H,W,Ci,Co", [(3, 9, 16, 64, 64), (2, 18, 32, 320, 160), (2, 36, 64, 128, 96), (1, 5, 7, 32, 32)])
+def test_upsample_conv_fused(ops, frames, H, W, Ci, Co):
+    """ops.upconv3x3 (four parity sub-convolutions on the small image, strided TMA stores) vs F.interpolate(nearest x2) + conv2d."""
+    x = rnd(frames * H * W, Ci, seed=51)
+    w = torch.randn(Co, Ci, 3, 3, generator=torch.Generator().manual_seed(52)) * (1.0 / math.sqrt(9 * Ci))
+    b = torch.randn(Co, generator=torch.Generator().manual_seed(53)).cuda() * 0.1
+    y = ops.upconv3x3(x, frames, H, W, [p.cuda() for p in ops.pack_upconv3x3(w)], bias=b)
+    xi = x.float().reshape(frames, H, W, Ci).permute(0, 3, 1, 2)
+    ref = F.conv2d(F.interpolate(xi, scale_factor=2, mode="nearest"), w.cuda(), b, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Co)
+    close(y, ref, atol=6e-3, what="upconv3x3")

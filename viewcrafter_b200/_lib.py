@@ -24,7 +24,8 @@ class GemmDesc(C.Structure):
                 ("tap_dx", C.c_int32 * 9), ("tap_dy", C.c_int32 * 9),
                 ("out", C.c_void_p), ("out_f32", C.c_void_p), ("ldo", C.c_int32),
                 ("bias", C.c_void_p), ("bias_z_div", C.c_int32), ("res", C.c_void_p), ("ldr", C.c_int32),
-                ("geglu", C.c_int32), ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_part", C.c_void_p)]
+                ("geglu", C.c_int32), ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_part", C.c_void_p),
+                ("ldo_y", C.c_int64), ("ldo_z", C.c_int64)]
 
 
 class AttnDesc(C.Structure):

@@ -187,7 +187,7 @@ class AutoencoderKL(nn.Module):
         for stage in d.up:
             S = dict(blocks=[self._pack_res(b) for b in stage.block], attns=[self._pack_attn(a) for a in stage.attn])
             if hasattr(stage, "upsample"):
-                S["up_w"], S["up_b"] = ops.pack_conv3x3(stage.upsample.conv.weight.detach()), f(stage.upsample.conv.bias)
+                S["up_w"], S["up_b"] = ops.pack_upconv3x3(stage.upsample.conv.weight.detach()), f(stage.upsample.conv.bias)
             ups.append(S)
         P["up"] = ups
         P["out_gn"] = (f(d.norm_out.weight), f(d.norm_out.bias))
@@ -247,7 +247,7 @@ class AutoencoderKL(nn.Module):
                 if S["attns"]:
                     h = self._attn(S["attns"][i], h, N, H, W)
             if "up_w" in S:
-                h = ops.conv3x3(ops.upsample2x(h, N, H, W), N, 2 * H, 2 * W, S["up_w"], bias=S["up_b"])
+                h = ops.upconv3x3(h, N, H, W, S["up_w"], bias=S["up_b"])                # upsample folded into four parity sub-convolutions
                 H, W = 2 * H, 2 * W
         y = ops.conv3x3(ops.groupnorm(h, N, *P["out_gn"], 1e-6, True), N, H, W, P["out_w"], bias=P["out_b"], out_f32=True)
         oc = y.shape[1]

@@ -34,6 +34,7 @@ int vc_gemm_tap(const vc_gemm_desc* c, void* stream) {
   d.out = HM(c->out); d.out_f32 = reinterpret_cast<float*>(c->out_f32); d.ldo = c->ldo;
   d.bias = c->bias; d.bias_z_div = c->bias_z_div; d.res = H(c->res); d.ldr = c->ldr; d.geglu = c->geglu;
   d.ln_stats = c->ln_stats; d.ln_colsum = c->ln_colsum; d.ln_part = c->ln_part;
+  d.ldo_y = c->ldo_y; d.ldo_z = c->ldo_z;
   COUNT(1);
   return gemm_tap(d, ST(stream));
 }

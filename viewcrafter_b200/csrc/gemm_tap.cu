@@ -307,11 +307,15 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
     if (p.out_tma) {
       const uint32_t bw = d.bx < 32 ? d.bx : 32;
       uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)d.X, (uint64_t)d.Y, (uint64_t)d.Z};
-      uint64_t str[3] = {(uint64_t)d.ldo * 2, (uint64_t)d.ldo * 2 * d.X, (uint64_t)d.ldo * 2 * d.X * d.Y};
+      const long long py = d.ldo_y > 0 ? d.ldo_y : (long long)d.ldo * d.X;
+      const long long pz = d.ldo_z > 0 ? d.ldo_z : py * d.Y;
+      uint64_t str[3] = {(uint64_t)d.ldo * 2, (uint64_t)py * 2, (uint64_t)pz * 2};
       uint32_t box[4] = {32, bw, 32 / bw, 1};
       int rc = encode_tmap_f16(&p.tmap_out, d.out, 4, dims, str, box, 64);
       if (rc) return rc;
     }
+    VC_REQUIRE((d.ldo_y == 0 && d.ldo_z == 0) || (p.out_tma && !d.res && !d.ln_part),
+               "gemm_tap: strided (ldo_y / ldo_z) outputs need the TMA-store epilogue (fp16, N %% 32 == 0) and no residual");
   }
   {
     static int dbg = -1;

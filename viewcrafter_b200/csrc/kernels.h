@@ -19,6 +19,9 @@ struct GemmDesc {
   int num_taps = 1;
   int tap_dx[9] = {0}; int tap_dy[9] = {0};
   __half* out = nullptr; float* out_f32 = nullptr; int ldo = 0;
+  // optional output pitches (elements) along Y and Z; 0 = dense (ldo * X, ldo * X * Y).  Non-dense outputs are written by the
+  // TMA-store epilogue only (fp16, N % 32 == 0): used to interleave the four parity sub-convolutions of upsample+conv.
+  long long ldo_y = 0, ldo_z = 0;
   const float* bias = nullptr; int bias_z_div = 0;
   const __half* res = nullptr; int ldr = 0;
   int geglu = 0;

@@ -243,6 +243,54 @@ def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w9: torch.Tensor, bias
     return out
 
 
+def pack_upconv3x3(w: torch.Tensor):
+    """Upsample(nearest x2) followed by a 3x3 / pad 1 conv (openaimodel3d.py:80-106) == four 2x2 convolutions on the SMALL image,
+    one per output parity (a, b) = (row & 1, col & 1):  out[2i+a, 2j+b] = sum_{r,c in 0..1} Wab[r][c] . x[i + r + a - 1, j + c + b - 1]
+    with the 3x3 taps that land on the same source pixel pre-summed (in fp32, then rounded to fp16): rows a=0: {W[0]}, {W[1]+W[2]};
+    a=1: {W[0]+W[1]}, {W[2]}; columns alike.  4/9 of the FLOPs, and the 4x larger upsampled tensor is never materialised.
+    Returns 4 packed tensors [(4*Cout), Cin] (tap = r*2 + c) for parities (0,0), (0,1), (1,0), (1,1)."""
+    w32 = w.detach().float()
+    co, ci = w32.shape[0], w32.shape[1]
+    rows = {0: [w32[:, :, 0], w32[:, :, 1] + w32[:, :, 2]], 1: [w32[:, :, 0] + w32[:, :, 1], w32[:, :, 2]]}     # [co, ci, kx] each
+    packs = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = []
+            for r in (0, 1):
+                wr = rows[a][r]
+                cols = [wr[:, :, 0], wr[:, :, 1] + wr[:, :, 2]] if b == 0 else [wr[:, :, 0] + wr[:, :, 1], wr[:, :, 2]]
+                taps.extend(cols)
+            packs.append(torch.stack(taps, 0).reshape(4 * co, ci).to(torch.float16).contiguous())
+    return packs
+
+
+def upconv3x3(x: torch.Tensor, frames: int, H: int, W: int, packs, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv3x3(upsample2x(x)) on [frames*H*W, Cin] rows -> [frames*2H*2W, Cout]; packs = pack_upconv3x3(weight)."""
+    _chk16(x, "upconv3x3.x")
+    M, K = x.shape
+    assert M == frames * H * W
+    N = packs[0].shape[0] // 4
+    assert N % 32 == 0, "upconv3x3 writes through the TMA-store epilogue: Cout must be a multiple of 32"
+    out = torch.empty((frames * 4 * H * W, N), device=x.device, dtype=torch.float16)
+    for a in (0, 1):
+        for b in (0, 1):
+            w4 = packs[a * 2 + b]
+            _chk16(w4, "upconv3x3.w")
+            d = GemmDesc()
+            d.a, d.lda = x.data_ptr(), x.stride(0)
+            d.X, d.Y, d.Z = W, H, frames
+            d.bx, d.by = _conv_box(H, W)
+            d.K, d.K1, d.w, d.N, d.num_taps = K, K, w4.data_ptr(), N, 4
+            for t in range(4):
+                d.tap_dx[t] = (t % 2) + b - 1
+                d.tap_dy[t] = (t // 2) + a - 1
+            d.out = out.data_ptr() + ((a * 2 * W + b) * N) * 2          # pixel (a, b) of the large image
+            d.ldo, d.ldo_y, d.ldo_z = 2 * N, 4 * W * N, 4 * W * H * N   # every second pixel along x and y
+            d.bias = _ptr(bias)
+            _gemm(d)
+    return out
+
+
 def conv_temporal(x: torch.Tensor, B: int, T: int, HW: int, w3: torch.Tensor, bias: Optional[torch.Tensor] = None,
                   res: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Conv3d (3,1,1) pad (1,0,0) on [(B T) HW, C] rows: three row-shifted GEMM taps; batches never mix (Z = B)."""

@@ -332,7 +332,7 @@ class UNetModel(nn.Module):
                 w = m.op.weight.detach()
                 out.append(dict(kind="D", w=w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.float16).contiguous(), b=f(m.op.bias)))
             elif isinstance(m, _Up):
-                out.append(dict(kind="U", w=ops.pack_conv3x3(m.conv.weight.detach()), b=f(m.conv.bias)))
+                out.append(dict(kind="U", w=ops.pack_upconv3x3(m.conv.weight.detach()), b=f(m.conv.bias)))
             elif isinstance(m, nn.Conv2d):
                 out.append(dict(kind="C", w=ops.pack_conv3x3(m.weight.detach(), k_pad=8), b=f(m.bias), cin=m.in_channels))
             else:
@@ -468,7 +468,7 @@ class UNetModel(nn.Module):
                 cols, H, W = ops.im2col_s2(h, B * T, H, W)
                 h = ops.linear(cols, P["w"], bias=P["b"])
             elif k == "U":
-                h = ops.conv3x3(ops.upsample2x(h, B * T, H, W), B * T, 2 * H, 2 * W, P["w"], bias=P["b"])
+                h = ops.upconv3x3(h, B * T, H, W, P["w"], bias=P["b"])      # upsample folded into four parity sub-convolutions
                 H, W = 2 * H, 2 * W
             elif k == "C":
                 h = ops.conv3x3(h, B * T, H, W, P["w"], bias=P["b"])
