@@ -231,7 +231,49 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  const int BN = pick_bn(d.N, d.geglu);
+  int BN = pick_bn(d.N, d.geglu);
+  int tuned = 0;                              // 0: default pair rule; 1: tuned -> CTA pairs; 2: tuned -> single CTAs
+  {
+    // Wave quantisation: the persistent grid runs ceil(tiles / slots) rounds.  A frame shard of a multi-GPU run (7 frames at
+    // 18x32: 32 row tiles x 1280 columns) gives 80 pair tiles on 74 SM pairs -- two rounds, the second 8 % full.  When the default
+    // tiling fills its rounds to less than 80 %, compare (pair | single CTA) x (BN 256 | 160 | 128) by
+    // rounds x tile area / relative tile efficiency and take the cheapest.  GEGLU keeps the tile its weights were interleaved for.
+    static int tune = -1;                     // tuning switch VC_GEMM_WAVE_TUNE=0 keeps the fixed choice
+    if (tune < 0) { const char* e = getenv("VC_GEMM_WAVE_TUNE"); tune = (e && e[0] == '0') ? 0 : 1; }
+    const long long mt = (long long)((d.X + d.bx - 1) / d.bx) * ((d.Y + d.by - 1) / d.by) * d.Z;
+    const int k_it = d.num_taps * ((d.K + BK - 1) / BK);
+    const int sms = sm_count();
+    auto cost = [&](int bn, bool pair, double* fill) -> double {
+      const long long nt = (d.N + bn - 1) / bn;
+      const long long tiles = (pair ? (mt + 1) / 2 : mt) * nt;
+      const long long slots = pair ? sms / 2 : sms;
+      const long long rounds = (tiles + slots - 1) / slots;
+      if (fill) *fill = (double)tiles / (double)(rounds * slots);
+      const double eff = (pair ? 1.08 : 1.0) * (bn == 256 ? 1.0 : bn == 160 ? 0.97 : 0.94);
+      return (double)rounds * (pair ? 2.0 : 1.0) * bn / eff;
+    };
+    auto pair_ok = [&](int bn) { return pair_mode() && d.N % bn == 0 && k_it >= 5 && (mt / 2) * ((d.N + bn - 1) / bn) >= 1; };
+    if (tune && !d.geglu && d.N >= 128 && (BN == 256 || BN == 160 || BN == 128)) {
+      double fill = 1.0;
+      const bool def_pair = pair_ok(BN) && (mt / 2) * ((d.N + BN - 1) / BN) >= sms;
+      double best = cost(BN, def_pair, &fill);
+      if (fill < 0.8) {
+        int best_bn = BN; bool best_pair = def_pair;
+        const int cands[3] = {256, 160, 128};
+        for (int ci = 0; ci < 3; ++ci) {
+          const int bn = cands[ci];
+          if (d.N % bn != 0) continue;
+          for (int pr = 0; pr < 2; ++pr) {
+            if (pr && !pair_ok(bn)) continue;
+            const double c = cost(bn, pr != 0, nullptr);
+            if (c < best * 0.97) { best = c; best_bn = bn; best_pair = pr != 0; }
+          }
+        }
+        BN = best_bn;
+        tuned = best_pair ? 1 : 2;
+      }
+    }
+  }
   p.bx = d.bx; p.by = d.by; p.X = d.X; p.Y = d.Y; p.Z = d.Z;
   p.tiles_x = (d.X + d.bx - 1) / d.bx;
   p.tiles_y = (d.Y + d.by - 1) / d.by;
@@ -250,8 +292,10 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
   const int k_iters = d.num_taps * ((d.K + BK - 1) / BK);
   static int pair_min_k = -1;                  // tuning switch VC_GEMM_PAIR_MINK: shortest reduction (in 64-wide k-blocks) routed to CTA pairs
   if (pair_min_k < 0) { const char* e = getenv("VC_GEMM_PAIR_MINK"); pair_min_k = e ? atoi(e) : 5; }
-  const bool use_pair = pair_mode() && (BN == 128 || BN == 160 || BN == 256) && d.N % BN == 0 && k_iters >= pair_min_k &&
-                        (m_tiles / 2) * p.n_tiles >= sm_count();
+  // default rule: pairs once every SM pair has work; a wave-tuned choice (above) decides by its cost model instead
+  const bool use_pair = tuned == 1 ? true : tuned == 2 ? false :
+                        (pair_mode() && (BN == 128 || BN == 160 || BN == 256) && d.N % BN == 0 && k_iters >= pair_min_k &&
+                         (m_tiles / 2) * p.n_tiles >= sm_count());
 
   // A: (K, X, Y, Z) with row pitch lda
   {
