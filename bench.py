@@ -162,8 +162,10 @@ def kernel_rooflines(wl, device, peaks):
     }
     # measured DRAM traffic per launch of the same kernels/shapes, from the committed ncu --set full capture (not re-measured
     # here: a number taken under a profiler is never a bench value, and ncu cannot run inside the timed process)
-    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tp) and (T, H, W) == (25, 72, 128):                  # the capture is of the headline shapes only
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_ncu_traffic.json")))
+    tp = cands[-1] if cands else ""                                       # the newest committed capture
+    if tp and (T, H, W) == (25, 72, 128):                                  # the capture is of the headline shapes only
         t = json.load(open(tp))
         for k in r:
             if k in t:
