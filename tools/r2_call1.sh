@@ -12,9 +12,13 @@ tail -c 3500 $O/c1_bench.json; tail -5 $O/c1_bench.err
 timeout 300 python bench.py --steps 6 --warmup 3 --no-graph --no-cpu-baseline --no-gpu-baseline --no-vae > $O/c1_bench_nograph.json 2>> $O/c1_bench.err
 VC_LN_FROM_PRODUCER=0 timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-vae > $O/c1_bench_lnpass.json 2>> $O/c1_bench.err
 VC_GN_L2_MB=0 timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-vae > $O/c1_bench_gn1launch.json 2>> $O/c1_bench.err
-for f in nograph lnpass gn1launch; do echo "$f: $(cut -c1-120 $O/c1_bench_$f.json)"; done
+VC_GN_PIPE=0 timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-vae > $O/c1_bench_gnchunked.json 2>> $O/c1_bench.err
+for f in nograph lnpass gn1launch gnchunked; do echo "$f: $(cut -c1-120 $O/c1_bench_$f.json)"; done
 for mb in 0 32 48 64 96; do
-  VC_GN_L2_MB=$mb timeout 200 python tools/ab_micro.py 2>&1 | grep -E "groupnorm" | sed "s/^/[GN_L2_MB=$mb] /" >> $O/c1_ab.txt
+  VC_GN_PIPE=0 VC_GN_L2_MB=$mb timeout 200 python tools/ab_micro.py 2>&1 | grep -E "groupnorm" | sed "s/^/[chunked GN_L2_MB=$mb] /" >> $O/c1_ab.txt
+done
+for mb in 24 48 72; do
+  VC_GN_PIPE=1 VC_GN_L2_MB=$mb timeout 200 python tools/ab_micro.py 2>&1 | grep -E "groupnorm" | sed "s/^/[team pipeline GN_L2_MB=$mb] /" >> $O/c1_ab.txt
 done
 timeout 200 python tools/ab_micro.py 2>&1 | grep -vE "groupnorm" >> $O/c1_ab.txt
 for lib in viewcrafter_b200/libvc_b200_*.so; do

@@ -60,11 +60,10 @@ __device__ __forceinline__ void gn_acc8(const uint4& u, float (&s)[8], float (&s
 }
 
 __device__ __forceinline__ void gn_stats_dev(const __half* __restrict__ x1, const __half* __restrict__ x2, const GnGeom& g,
-                                                        float* __restrict__ partial) {
+                                                        float* __restrict__ partial, const int split, const int sample) {
   extern __shared__ float red[];   // [2*C]
   const int tid = threadIdx.x;
   const int v = tid % g.vecs, pl = tid / g.vecs;
-  const int split = blockIdx.x, sample = blockIdx.y;
   for (int i = tid; i < 2 * g.C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   float s[8], ss[8];
@@ -117,10 +116,10 @@ __device__ __forceinline__ uint4 gn_norm8(const uint4& u, const float (&sc)[8], 
 
 __device__ __forceinline__ void gn_apply_dev(const __half* __restrict__ x1, const __half* __restrict__ x2, const GnGeom& g,
                                                         const float* __restrict__ partial, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
+                                                        const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out,
+                                                        const int split, const int sample) {
   __shared__ float mean_s[32], rstd_s[32];
   const int tid = threadIdx.x;
-  const int sample = blockIdx.y;
   if (tid < 32) {
     double sum = 0.0, sq = 0.0;
     const float* pp = partial + (long long)sample * g.stat_splits * 64;
@@ -146,7 +145,7 @@ __device__ __forceinline__ void gn_apply_dev(const __half* __restrict__ x1, cons
     sc[e] = a;
     sh[e] = beta[c] - mean_s[grp] * a;
   }
-  const GnThread t = gn_thread(x1, x2, g, blockIdx.x, sample, v, pl);
+  const GnThread t = gn_thread(x1, x2, g, split, sample, v, pl);
   const long long ostride = (long long)g.ppi * g.C;
 #if VC_GN_REVERSE
   // Walk the rows BACKWARDS: the statistics pass streamed them forwards, so what the L2 still holds is the tail of every
@@ -180,12 +179,12 @@ __device__ __forceinline__ void gn_apply_dev(const __half* __restrict__ x1, cons
 
 __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
                                                        float* __restrict__ partial) {
-  gn_stats_dev(x1, x2, g, partial);
+  gn_stats_dev(x1, x2, g, partial, blockIdx.x, blockIdx.y);
 }
 __global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
                                                        const float* __restrict__ partial, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
-  gn_apply_dev(x1, x2, g, partial, gamma, beta, eps, silu, out);
+  gn_apply_dev(x1, x2, g, partial, gamma, beta, eps, silu, out, blockIdx.x, blockIdx.y);
 }
 // Fused single launch: statistics pass, a grid-wide rendezvous of the CTAs of one sample (all CTAs are co-resident by
 // construction -- the host checks the occupancy), then the normalise pass, whose re-read of x is served by the 126 MB L2
@@ -194,16 +193,50 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const __half* __restrict_
                                                         float* __restrict__ partial, unsigned int* __restrict__ counters,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                                         __half* __restrict__ out) {
-  gn_stats_dev(x1, x2, g, partial);
+  gn_stats_dev(x1, x2, g, partial, blockIdx.x, blockIdx.y);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     atomicAdd(&counters[blockIdx.y], 1u);
-    while (*reinterpret_cast<volatile unsigned int*>(&counters[blockIdx.y]) < (unsigned)g.splits) __nanosleep(40);
+    unsigned long long spins = 0;
+    while (*reinterpret_cast<volatile unsigned int*>(&counters[blockIdx.y]) < (unsigned)g.splits) {
+      __nanosleep(40);
+      if (++spins > 200000000ull) __trap();      // cannot happen under a cooperative launch; never hang the device
+    }
     __threadfence();
   }
   __syncthreads();
-  gn_apply_dev(x1, x2, g, partial, gamma, beta, eps, silu, out);
+  gn_apply_dev(x1, x2, g, partial, gamma, beta, eps, silu, out, blockIdx.x, blockIdx.y);
+}
+
+// Pipelined form for MANY small samples (the per-frame GroupNorms: 25-50 samples of 0.4-6 MB): the grid is cut into `groups`
+// teams of g.splits CTAs; each team walks its own samples (team, team + groups, ...) through statistics -> team barrier ->
+// normalise.  No grid-wide phases: while one team re-reads its sample from L2 and writes the result, the others stream their
+// statistics pass from HBM, so reads and writes overlap for the whole launch, and the L2 footprint is groups x one sample.
+__global__ void __launch_bounds__(512) gn_pipe_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g, int samples,
+                                                       int groups, float* __restrict__ partial, unsigned int* __restrict__ bars,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                                       __half* __restrict__ out) {
+  const int team = blockIdx.x / g.splits, split = blockIdx.x - team * g.splits;
+  unsigned int target = 0;
+  for (int sample = team; sample < samples; sample += groups) {
+    gn_stats_dev(x1, x2, g, partial, split, sample);
+    __threadfence();
+    __syncthreads();
+    target += (unsigned)g.splits;
+    if (threadIdx.x == 0) {
+      atomicAdd(&bars[team], 1u);
+      unsigned long long spins = 0;
+      while (*reinterpret_cast<volatile unsigned int*>(&bars[team]) < target) {
+        __nanosleep(20);
+        if (++spins > 200000000ull) __trap();
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    gn_apply_dev(x1, x2, g, partial, gamma, beta, eps, silu, out, split, sample);
+    __syncthreads();                               // red[] / mean_s[] are reused by the next sample
+  }
 }
 
 static int gn_geometry(GnGeom& g, const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample) {
@@ -276,12 +309,61 @@ static long long gn_l2_budget_bytes() {
   return v;
 }
 
+// one cooperative launch, teams of CTAs pipelining over the samples; returns VC_OK with *done = false if the shape does not qualify
+static int gn_launch_pipe(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample, const float* gamma,
+                          const float* beta, float eps, int silu, __half* out, float* partial_ws, size_t ws_bytes, long long budget,
+                          cudaStream_t stream, bool* done) {
+  *done = false;
+  GnGeom g;
+  int rc = gn_geometry(g, x1, C1, x2, C2, samples, rows_per_sample);
+  if (rc) return rc;
+  const long long bytes_per_sample = rows_per_sample * g.C * 2;
+  long long groups = budget / (bytes_per_sample > 0 ? bytes_per_sample : 1);
+  if (groups > samples / 2) groups = samples / 2;                      // at least two samples per team, or there is nothing to pipeline
+  while (groups >= 2 && ((samples + groups - 1) / groups) * groups * 10 > (long long)samples * 11) --groups;   // <= 10 % idle team-iterations
+  if (groups < 2) return VC_OK;                                        // caller falls back to the chunked launches
+  const int threads = g.vecs * g.ppi;
+  const size_t smem = 2 * g.C * sizeof(float);
+  int per_sm = 0;
+  VC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_pipe_kernel, threads, smem));
+  const long long capacity = (long long)per_sm * sm_count();
+  long long splits = capacity / groups;
+  const long long max_useful = (rows_per_sample + 4ll * g.ppi - 1) / (4ll * g.ppi);     // >= 4 rows per thread and split
+  if (splits > max_useful) splits = max_useful;
+  if (splits > GN_MAX_SPLITS) splits = GN_MAX_SPLITS;
+  if (splits < 1) return VC_OK;
+  g.splits = (int)splits;
+  g.rows_per_split = (rows_per_sample + g.splits - 1) / g.splits;
+  g.stat_splits = g.splits;
+  const size_t part_bytes = (size_t)samples * g.splits * 64 * sizeof(float);
+  if (ws_bytes < part_bytes + (size_t)groups * sizeof(unsigned int)) return VC_OK;
+  unsigned int* bars = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(partial_ws) + part_bytes);
+  VC_CHECK_CUDA(cudaMemsetAsync(bars, 0, groups * sizeof(unsigned int), stream));
+  int igroups = (int)groups;
+  void* args[] = {(void*)&x1, (void*)&x2, (void*)&g, (void*)&samples, (void*)&igroups, (void*)&partial_ws, (void*)&bars, (void*)&gamma,
+                  (void*)&beta, (void*)&eps, (void*)&silu, (void*)&out};
+  VC_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)gn_pipe_kernel, dim3((unsigned)(groups * g.splits)), dim3(threads), args, smem, stream));
+  *done = true;
+  return VC_OK;
+}
+
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample,
                    const float* gamma, const float* beta, float eps, int silu, __half* out, float* partial_ws,
                    size_t ws_bytes, cudaStream_t stream) {
   VC_REQUIRE(out && gamma && beta && partial_ws && x1, "groupnorm: null pointer");
   const int C = C1 + (x2 ? C2 : 0);
   const long long bytes_per_sample = rows_per_sample * C * 2;
+  {
+    static int pipe = -1;                      // A/B switch VC_GN_PIPE=0: chunked launches instead of the team pipeline
+    if (pipe < 0) { const char* e = getenv("VC_GN_PIPE"); pipe = (e && e[0] == '0') ? 0 : 1; }
+    if (pipe && gn_l2_budget_bytes() > 0) {
+      bool done = false;
+      int rc = gn_launch_pipe(x1, C1, x2, C2, samples, rows_per_sample, gamma, beta, eps, silu, out, partial_ws, ws_bytes, gn_l2_budget_bytes(),
+                              stream, &done);
+      if (rc) return rc;
+      if (done) return VC_OK;
+    }
+  }
   long long chunk = gn_l2_budget_bytes() > 0 ? gn_l2_budget_bytes() / (bytes_per_sample > 0 ? bytes_per_sample : 1) : samples;
   if (chunk < 1) chunk = 1;
   if (chunk > samples) chunk = samples;

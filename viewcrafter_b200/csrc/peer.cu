@@ -74,7 +74,12 @@ __device__ __forceinline__ void peer_finish(const PeerCommDev& pc, int B, bool w
   __syncthreads();
   if (tid < pc.world) {
     st_release_sys(pc.peer_flags[tid] + pc.rank, s);
-    while ((int)(ld_acquire_sys(pc.flags + tid) - s) < 0) __nanosleep(64);
+    // bounded wait (~30 s): a rank that never arrives (crashed peer, mismatched call sequence) must not hang the GPU
+    unsigned long long spins = 0;
+    while ((int)(ld_acquire_sys(pc.flags + tid) - s) < 0) {
+      __nanosleep(spins < 1024 ? 32 : 256);
+      if (++spins > 120000000ull) __trap();
+    }
   }
   __syncthreads();
   if (with_stats) {
