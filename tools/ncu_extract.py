@@ -32,9 +32,13 @@ for key, pat, note in (("roofline", "gemm_tap2_kernel<160>", "3x3 conv 320->320 
                        ("roofline_attention", "flash_attn_d64_kernel", "5 heads N=9216 x 25; algorithmic q+k+v read once 442.4 MB + out 147.5 MB"),
                        ("roofline_groupnorm", "gn_fused_kernel", "C=320 @25x72x128, one op = all launches of its sample chunks; algorithmic read+write once 294.9 MB")):
     sel = [r for r in data if pat in r[col["Kernel Name"]]]
+    if key == "roofline_groupnorm":
+        pipe = [r for r in data if "gn_pipe_kernel" in r[col["Kernel Name"]]]
+        if pipe:                                     # the team-pipelined kernel: one launch per op
+            sel, pat = [pipe[-1]], "gn_pipe_kernel"
     if not sel:
         continue
-    if key == "roofline_groupnorm":
+    if key == "roofline_groupnorm" and pat == "gn_fused_kernel":
         # one GroupNorm op = consecutive chunk launches: sum the launches of the LAST op (ids contiguous, same block size)
         last = sel[-1]
         n_per_op = max(1, len(sel) // 3)             # tools/ncu_target.py runs the op 3 times
