@@ -234,7 +234,17 @@ class CfgComm:
 
 def _make_comm(dist, rank, world, group, device, peer: bool):
     if peer and world > 1 and device is not None and torch.device(device).type == "cuda":
-        return PeerFrameComm(dist, rank, world, group, device)
+        comm, err = None, None
+        try:
+            comm = PeerFrameComm(dist, rank, world, group, device)
+        except Exception as e:                       # e.g. CUDA IPC not permitted in this container
+            err = e
+        ok = torch.tensor([0.0 if comm is None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # all ranks of the group take the same path
+        if float(ok) > 0:
+            return comm
+        import warnings
+        warnings.warn(f"viewcrafter_b200.parallel: NVLink peer-memory exchange unavailable ({err!r}); using the NCCL collectives")
     return FrameComm(dist, rank, world, group)
 
 
