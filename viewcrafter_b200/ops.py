@@ -243,12 +243,17 @@ def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w9: torch.Tensor, bias
     return out
 
 
+UPCONV_FUSED = os.environ.get("VC_UPCONV_FUSED", "1") != "0"     # A/B switch: 0 = materialise the upsampled tensor, then a 9-tap conv
+
+
 def pack_upconv3x3(w: torch.Tensor):
     """Upsample(nearest x2) followed by a 3x3 / pad 1 conv (openaimodel3d.py:80-106) == four 2x2 convolutions on the SMALL image,
     one per output parity (a, b) = (row & 1, col & 1):  out[2i+a, 2j+b] = sum_{r,c in 0..1} Wab[r][c] . x[i + r + a - 1, j + c + b - 1]
     with the 3x3 taps that land on the same source pixel pre-summed (in fp32, then rounded to fp16): rows a=0: {W[0]}, {W[1]+W[2]};
     a=1: {W[0]+W[1]}, {W[2]}; columns alike.  4/9 of the FLOPs, and the 4x larger upsampled tensor is never materialised.
     Returns 4 packed tensors [(4*Cout), Cin] (tap = r*2 + c) for parities (0,0), (0,1), (1,0), (1,1)."""
+    if not UPCONV_FUSED:
+        return pack_conv3x3(w.detach())
     w32 = w.detach().float()
     co, ci = w32.shape[0], w32.shape[1]
     rows = {0: [w32[:, :, 0], w32[:, :, 1] + w32[:, :, 2]], 1: [w32[:, :, 0] + w32[:, :, 1], w32[:, :, 2]]}     # [co, ci, kx] each
@@ -267,6 +272,8 @@ def pack_upconv3x3(w: torch.Tensor):
 def upconv3x3(x: torch.Tensor, frames: int, H: int, W: int, packs, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """conv3x3(upsample2x(x)) on [frames*H*W, Cin] rows -> [frames*2H*2W, Cout]; packs = pack_upconv3x3(weight)."""
     _chk16(x, "upconv3x3.x")
+    if isinstance(packs, torch.Tensor):            # VC_UPCONV_FUSED=0: plain 9-tap weights
+        return conv3x3(upsample2x(x, frames, H, W), frames, 2 * H, 2 * W, packs, bias=bias)
     M, K = x.shape
     assert M == frames * H * W
     N = packs[0].shape[0] // 4
