@@ -152,11 +152,11 @@ typedef struct vc_ddim_scalars {
   int32_t use_cfg;
 } vc_ddim_scalars;
 int vc_ddim_update(const float* x, const float* v_cond, const float* v_uncond, const float* noise, float* x_prev, float* pred_x0,
-                   int64_t n, const vc_ddim_scalars* s, void* ws32bytes, void* stream);
+                   int64_t n, const vc_ddim_scalars* s, void* ws /* 4 * 1025 doubles */, void* stream);
 /* three-way CFG of DDIMSampler (multicond): v = u + cfg_img (v_img - u) + cfg_scale (v_cond - v_img), then the same rescale / update
  * replaces: lvdm/models/samplers/ddim_multiplecond.py:227-236 (+ the shared tail :238-287) */
 int vc_ddim_update3(const float* x, const float* v_cond, const float* v_uncond, const float* v_uncond_img, float cfg_img,
-                    const float* noise, float* x_prev, float* pred_x0, int64_t n, const vc_ddim_scalars* s, void* ws32bytes, void* stream);
+                    const float* noise, float* x_prev, float* pred_x0, int64_t n, const vc_ddim_scalars* s, void* ws /* 4 * 1025 doubles */, void* stream);
 
 /* ---- multi-GPU: frame <-> site layout exchange over NVLink peer memory ------------------------------------------------
  * New functionality (the reference is single-GPU).  The frame-sharded U-Net runs its spatial ops on

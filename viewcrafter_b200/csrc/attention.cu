@@ -78,9 +78,6 @@ __device__ __forceinline__ float ex2_sel(float x, int e) {
 #ifndef VC_ATT_F32X2
 #define VC_ATT_F32X2 1
 #endif
-#ifndef VC_ATT_MERGED
-#define VC_ATT_MERGED 0      // 1: a single role warp issues TMA loads and MMAs (A/B switch)
-#endif
 // two exponentials at once: both on MUFU, or (one pair in every ATT_POLY_PERIOD) both through the polynomial in packed fp32x2
 __device__ __forceinline__ float2 ex2_pair(float2 x, int e) {
   if (ATT_POLY_PERIOD > 0 && (e % (2 * ATT_POLY_PERIOD)) < 2) {
@@ -148,78 +145,6 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tP = tmem_base + 128, tO = tmem_base + 192;
 
-#if VC_ATT_MERGED
-  // ONE role warp issues both the TMA loads and the MMAs.  Every stage hand-back the separate producer warp used to wait for
-  // is implied by an event this warp has already waited on, so no "empty" barriers (and no second spinning warp: ncu round 1
-  // counted 44 M try_wait polls of the producer per launch) are needed:
-  //   K stage j&1 is free once Q K^T(j) retired  <=  s_free(j)  (the softmax warps read S(j) only after s_full(j))
-  //   V stage j&1 is free once P V(j) retired    <=  p_full(j+1) (the softmax warps wait o_done(j) before arriving)
-  if (warp == 0) {
-    // idle: parks at the final barrier
-  } else if (warp == 1) {
-    constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);      // B = V is MN-major
-    const uint32_t aQ = smem_u32(sQ);
-    auto load_k = [&](int j) {
-      if (elect_one()) {
-        uint8_t* sk = sKV + (j & 1) * 2 * ATT_TILE_BYTES;
-        mbar_expect_tx(&kv_full[j & 1], ATT_TILE_BYTES);
-        tma_load_4d(sk, &p.tmap_k, &kv_full[j & 1], 0, head, j * ATT_BN, bk);
-      }
-      __syncwarp();
-    };
-    auto load_v = [&](int j) {
-      if (elect_one()) {
-        uint8_t* sv = sKV + (j & 1) * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES;
-        mbar_expect_tx(&v_full[j & 1], ATT_TILE_BYTES);
-        tma_load_4d(sv, &p.tmap_v, &v_full[j & 1], 0, head, j * ATT_BN, bk);
-      }
-      __syncwarp();
-    };
-    auto issue_qk = [&](int j) {
-      const int s = j & 1;
-      mbar_wait(&kv_full[s], (j >> 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t aK = smem_u32(sKV + s * 2 * ATT_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)
-          umma_ss(tS, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc_qk, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
-      }
-      __syncwarp();
-    };
-    if (elect_one()) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_4d(sQ, &p.tmap_q, q_full, 0, head, q0, b);
-    }
-    __syncwarp();
-    load_k(0);
-    if (ntiles > 1) load_k(1);
-    load_v(0);
-    if (ntiles > 1) load_v(1);
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    for (int j = 0; j < ntiles; ++j) {
-      if (j + 1 < ntiles) {                       // next S as soon as this one has been copied out of TMEM
-        mbar_wait(s_free, j & 1);
-        issue_qk(j + 1);
-        if (j + 2 < ntiles) load_k(j + 2);        // Q K^T(j) retired before s_free(j): its K stage is free
-      }
-      mbar_wait(&v_full[j & 1], (j >> 1) & 1);
-      mbar_wait(p_full, j & 1);
-      if (j >= 1 && j + 1 < ntiles) load_v(j + 1);  // p_full(j) implies P V(j-1) retired: stage (j+1)&1 is free
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t aV = smem_u32(sKV + (j & 1) * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
-#pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k)
-          umma_ts(tO, tP + k * 8, umma_desc_sw128(aV + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(o_done);
-      }
-      __syncwarp();
-    }
-#else
   // warps 0/1 run warp-uniform loops and ONE elected lane issues TMA / MMA (keeps operands in uniform registers)
   if (warp == 0) {
     if (elect_one()) {
@@ -299,7 +224,6 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
       }
       __syncwarp();
     }
-#endif
   } else {
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
@@ -465,7 +389,12 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
 }
 
 int flash_attn_d64(const AttnDesc& d, cudaStream_t stream) {
-  if (flash_attn_bn64_enabled()) return flash_attn_d64_bn64(d, stream);      // opt-in experiment (VC_ATTN_BN64=1), off by default
+  // Short key sequences (text / image cross-attention: 77 / 256 keys; the 18x32 and 9x16 levels: 576 / 144 keys) run on the
+  // 64-key-tile kernel (attention_bn64.cu, three CTAs per SM): measured on B200 (profiles/r02_ab_micro.txt) cross-attention
+  // 179.5 -> 147.1 us (77 keys) and 208.6 -> 186.4 us (256 keys), self-attention at 576 keys 103 -> 87 us; from 2304 keys up the
+  // 128-key tiles of this file win (3.115 vs 3.198 ms at 9216 keys).  VC_ATTN_BN64=1 / 0 forces one kernel.
+  const int bn64 = flash_attn_bn64_mode();
+  if (bn64 == 1 || (bn64 < 0 && d.Nk <= 1024)) return flash_attn_d64_bn64(d, stream);
   VC_REQUIRE(d.q && d.k && d.v && d.out, "flash_attn: null pointer");
   VC_REQUIRE(d.Nq > 0 && d.Nk > 0 && d.B > 0 && d.heads > 0, "flash_attn: empty problem");
   VC_REQUIRE(d.ldq % 8 == 0 && d.ldk % 8 == 0 && d.ldv % 8 == 0 && d.ldo % 8 == 0, "flash_attn: pitches must be multiples of 8");

@@ -1,5 +1,7 @@
-// EXPERIMENTAL, OPT-IN (VC_ATTN_BN64=1), NOT YET RUN ON A GPU: 64-key-tile variant of flash_attn_d64_kernel that fits
-// THREE CTAs per SM instead of two.
+// 64-key-tile variant of flash_attn_d64_kernel that fits THREE CTAs per SM instead of two.  MEASURED on B200 (round 2,
+// profiles/r02_ab_micro.txt): it wins where key sequences are short -- cross-attention with 77 / 256 keys 179.5 -> 147.1 us /
+// 208.6 -> 186.4 us, self-attention with 576 keys 103 -> 87 us -- and ties / loses from 2304 keys up (0.466 vs 0.464 ms; 3.198 vs
+// 3.115 ms at 9216 keys), so flash_attn_d64() dispatches Nk <= 1024 here and keeps the 128-key tiles above.
 //
 // Why (profiles/README.md, ncu --set full of flash_attn_d64_kernel): the shipped kernel is bound by instruction issue
 // of its softmax warps, not by a pipe -- issue slots 65 % busy, MUFU 55 %, tensor 36 %; each softmax warp issues only
@@ -15,7 +17,7 @@
 // 25 % polynomial exp2 share, P back to TMEM as fp16, TS MMA for O += P V, separate K / V TMA rings.
 // Costs to measure: twice as many tiles (barrier round trips per key halve in size), N = 64 MMAs.
 //
-// Selection: flash_attn_d64() forwards here when the environment has VC_ATTN_BN64=1 (tools/ab_micro.py prints both).
+// Selection: flash_attn_d64() forwards here for Nk <= 1024; VC_ATTN_BN64=1 / 0 forces / forbids (tools/ab_micro.py prints both).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -289,10 +291,10 @@ __global__ void __launch_bounds__(192, 3) flash_attn_d64_bn64_kernel(const __gri
   }
 }
 
-bool flash_attn_bn64_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("VC_ATTN_BN64"); on = (e && e[0] == '1') ? 1 : 0; }
-  return on == 1;
+int flash_attn_bn64_mode() {
+  static int mode = -2;
+  if (mode == -2) { const char* e = getenv("VC_ATTN_BN64"); mode = !e ? -1 : (e[0] == '1' ? 1 : 0); }
+  return mode;
 }
 
 int flash_attn_d64_bn64(const AttnDesc& d, cudaStream_t stream) {

@@ -48,8 +48,9 @@ struct AttnDesc {
   int accumulate = 0;              // out += result (second softmax branch of the image cross-attention)
 };
 int flash_attn_d64(const AttnDesc& d, cudaStream_t stream);
-// experimental 64-key-tile / 3-CTAs-per-SM variant (attention_bn64.cu); flash_attn_d64 forwards to it when VC_ATTN_BN64=1
-bool flash_attn_bn64_enabled();
+// 64-key-tile / 3-CTAs-per-SM variant (attention_bn64.cu): flash_attn_d64 forwards short key sequences (Nk <= 1024) to it;
+// env VC_ATTN_BN64 = 1 / 0 forces / forbids it (mode: 1, 0, or -1 = by size)
+int flash_attn_bn64_mode();
 int flash_attn_d64_bn64(const AttnDesc& d, cudaStream_t stream);
 
 // GroupNorm(32) on NHWC fp16; x is the channel concat of (x1: C1 channels) and (x2: C2 channels, may be null).

@@ -222,8 +222,12 @@ __device__ __forceinline__ float cfg_combine(float c, float u, const float* __re
   const float w = vi[i];
   return (u + cfg_img * (w - u)) + cfg * (c - w);
 }
-__global__ void ddim_stats_kernel(const float* __restrict__ vc_, const float* __restrict__ vu, const float* __restrict__ vi, long long n,
+// deterministic: every block leaves its four partial sums in ws[4 + 4 * block] (fixed in-block order); ddim_apply_kernel adds the
+// blocks up in index order -- no floating-point atomics, a seeded sampling run is bit-reproducible
+static constexpr int DDIM_MAX_BLOCKS = 1024;
+__global__ void __launch_bounds__(256) ddim_stats_kernel(const float* __restrict__ vc_, const float* __restrict__ vu, const float* __restrict__ vi, long long n,
                                   float cfg, float cfg_img, double* ws) {
+  __shared__ double red[8][4];
   double s1 = 0, q1 = 0, s2 = 0, q2 = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float c = vc_[i], u = vu[i];
@@ -236,19 +240,31 @@ __global__ void ddim_stats_kernel(const float* __restrict__ vc_, const float* __
     s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
     s2 += __shfl_xor_sync(0xffffffffu, s2, o); q2 += __shfl_xor_sync(0xffffffffu, q2, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(ws + 0, s1); atomicAdd(ws + 1, q1); atomicAdd(ws + 2, s2); atomicAdd(ws + 3, q2);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[w][0] = s1; red[w][1] = q1; red[w][2] = s2; red[w][3] = q2; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double a = 0;
+    for (int i = 0; i < 8; ++i) a += red[i][threadIdx.x];
+    ws[4 + 4 * blockIdx.x + threadIdx.x] = a;
   }
 }
 __global__ void ddim_apply_kernel(const float* __restrict__ x, const float* __restrict__ vc_, const float* __restrict__ vu,
                                   const float* __restrict__ vi, float cfg_img,
                                   const float* __restrict__ noise, float* __restrict__ x_prev, float* __restrict__ pred_x0,
-                                  long long n, DdimStepScalars s, const double* ws) {
+                                  long long n, DdimStepScalars s, const double* ws, int stat_blocks) {
   float factor = 1.f;
   if (s.use_cfg && s.guidance_rescale > 0.f) {
+    __shared__ double tot[4];
+    if (threadIdx.x < 4) {
+      double a = 0;
+      for (int b = 0; b < stat_blocks; ++b) a += ws[4 + 4 * b + threadIdx.x];
+      tot[threadIdx.x] = a;
+    }
+    __syncthreads();
     const double dn = (double)n;
-    const double var_t = (ws[1] - ws[0] * ws[0] / dn) / (dn - 1.0);
-    const double var_c = (ws[3] - ws[2] * ws[2] / dn) / (dn - 1.0);
+    const double var_t = (tot[1] - tot[0] * tot[0] / dn) / (dn - 1.0);
+    const double var_c = (tot[3] - tot[2] * tot[2] / dn) / (dn - 1.0);
     factor = (float)sqrt(var_t > 0 ? var_t : 0.0) / (float)sqrt(var_c > 0 ? var_c : 0.0);
   }
   const float rescale = s.prev_scale_t / s.scale_t;
@@ -275,13 +291,13 @@ int ddim_update(const float* x, const float* v_cond, const float* v_uncond, cons
   VC_REQUIRE(x && v_cond && noise && x_prev && pred_x0 && ws && n > 1, "ddim_update: bad args");
   VC_REQUIRE(!s.use_cfg || v_uncond, "ddim_update: CFG needs the unconditional output");
   VC_REQUIRE(!v_uncond_img || s.use_cfg, "ddim_update: the image-only branch is only defined with CFG on");
-  const int blocks = (int)min((long long)sm_count() * 4, (n + 255) / 256);
-  if (s.use_cfg && s.guidance_rescale > 0.f) {
-    VC_CHECK_CUDA(cudaMemsetAsync(ws, 0, 4 * sizeof(double), stream));
+  int blocks = (int)min((long long)sm_count() * 4, (n + 255) / 256);
+  if (blocks > DDIM_MAX_BLOCKS) blocks = DDIM_MAX_BLOCKS;
+  if (s.use_cfg && s.guidance_rescale > 0.f) {           // ws: 4 * (1 + DDIM_MAX_BLOCKS) doubles
     ddim_stats_kernel<<<blocks, 256, 0, stream>>>(v_cond, v_uncond, v_uncond_img, n, s.cfg_scale, cfg_img, ws);
     VC_CHECK_CUDA(cudaGetLastError());
   }
-  ddim_apply_kernel<<<blocks, 256, 0, stream>>>(x, v_cond, v_uncond, v_uncond_img, cfg_img, noise, x_prev, pred_x0, n, s, ws);
+  ddim_apply_kernel<<<blocks, 256, 0, stream>>>(x, v_cond, v_uncond, v_uncond_img, cfg_img, noise, x_prev, pred_x0, n, s, ws, blocks);
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -104,15 +104,11 @@ __device__ __forceinline__ void acc8(const uint4& u, float (&s)[8], float (&ss)[
 }
 
 __global__ void __launch_bounds__(512) peer_exchange_kernel(const __grid_constant__ ExchangeParams p) {
-  extern __shared__ float red[];   // [2*C] (with_stats)
+  extern __shared__ float red[];   // [ppi][2*C] (with_stats): fixed-order reduction, no float atomics
   __shared__ int is_last;
   const int tid = threadIdx.x;
   const int v = tid % p.vecs, pl = tid / p.vecs;
   const int split = blockIdx.x, b = blockIdx.y;
-  if (p.with_stats) {
-    for (int i = tid; i < 2 * p.C; i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
-  }
   float s[8], ss[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
@@ -157,16 +153,20 @@ __global__ void __launch_bounds__(512) peer_exchange_kernel(const __grid_constan
     if (p.with_stats) acc8(u, s, ss);
   }
   if (p.with_stats) {
+    float* mine = red + (long long)pl * 2 * p.C;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      atomicAdd(&red[v * 8 + e], s[e]);
-      atomicAdd(&red[p.C + v * 8 + e], ss[e]);
+      mine[v * 8 + e] = s[e];
+      mine[p.C + v * 8 + e] = ss[e];
     }
     __syncthreads();
     if (tid < 64) {
       const int grp = tid >> 1, which = tid & 1;
       float acc = 0.f;
-      for (int c = grp * p.cg; c < (grp + 1) * p.cg; ++c) acc += red[which * p.C + c];
+      for (int q = 0; q < p.ppi; ++q) {
+        const float* row = red + (long long)q * 2 * p.C + which * p.C;
+        for (int c = grp * p.cg; c < (grp + 1) * p.cg; ++c) acc += row[c];
+      }
       p.partial[((long long)b * p.splits + split) * 64 + tid] = acc;
     }
   }
@@ -270,7 +270,7 @@ int vc_peer_exchange(const vc_peer_comm* c, const void* src, void* const* dst, i
   p.partial = reinterpret_cast<float*>(ws);
   VC_REQUIRE(!p.with_stats || (ws && ws_bytes >= (size_t)B * splits * 64 * sizeof(float)), "peer_exchange: workspace too small");
   dim3 grid(splits, B);
-  peer_exchange_kernel<<<grid, p.vecs * p.ppi, p.with_stats ? 2 * C * sizeof(float) : 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  peer_exchange_kernel<<<grid, p.vecs * p.ppi, p.with_stats ? (size_t)2 * C * p.ppi * sizeof(float) : 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -535,7 +535,7 @@ def ddim_update(x, v_cond, v_uncond, noise, sc: dict, v_uncond_img=None, cfg_img
     key = (x.device, torch.cuda.current_stream().cuda_stream)
     ws = _ddim_ws.get(key)
     if ws is None:
-        ws = torch.zeros(4, device=x.device, dtype=torch.float64)
+        ws = torch.zeros(4 * 1025, device=x.device, dtype=torch.float64)    # per-block partial sums of the two std reductions
         _ddim_ws[key] = ws
     x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
     if v_uncond_img is not None and use_cfg:
