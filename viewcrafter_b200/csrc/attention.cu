@@ -79,8 +79,11 @@ __device__ __forceinline__ float ex2_sel(float x, int e) {
 #define VC_ATT_F32X2 1
 #endif
 // two exponentials at once: both on MUFU, or (one pair in every ATT_POLY_PERIOD) both through the polynomial in packed fp32x2
+#ifndef VC_ATT_POLY_SEL
+#define VC_ATT_POLY_SEL(e) (ATT_POLY_PERIOD > 0 && ((e) % (2 * ATT_POLY_PERIOD)) < 2)     // which pairs of a 32-score chunk take the polynomial
+#endif
 __device__ __forceinline__ float2 ex2_pair(float2 x, int e) {
-  if (ATT_POLY_PERIOD > 0 && (e % (2 * ATT_POLY_PERIOD)) < 2) {
+  if (VC_ATT_POLY_SEL(e)) {
     x.x = fmaxf(x.x, -125.0f);
     x.y = fmaxf(x.y, -125.0f);
     const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);

@@ -61,6 +61,28 @@ __device__ __forceinline__ float a64_ex2_sel(float x, int e) {
   return a64_ex2(x);
 }
 
+#ifndef VC_ATT_F32X2
+#define VC_ATT_F32X2 1
+#endif
+// two exponentials at once in packed fp32x2 (same arithmetic as attention.cu: ex2_pair)
+__device__ __forceinline__ float2 a64_ex2_pair(float2 x, int e) {
+  if (A64_POLY_PERIOD > 0 && (e % (2 * A64_POLY_PERIOD)) < 2) {
+    x.x = fmaxf(x.x, -125.0f);
+    x.y = fmaxf(x.y, -125.0f);
+    const float2 xf = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
+    const float2 t = __fadd2_rn(xf, make_float2(-12582912.0f, -12582912.0f));
+    const float2 f = __ffma2_rn(t, make_float2(-1.f, -1.f), x);
+    float2 p = __ffma2_rn(f, make_float2(0.05592204f, 0.05592204f), make_float2(0.24264008f, 0.24264008f));
+    p = __ffma2_rn(p, f, make_float2(0.69312102f, 0.69312102f));
+    p = __ffma2_rn(p, f, make_float2(0.99992448f, 0.99992448f));
+    float2 r;
+    r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(xf.x) << 23));
+    r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xf.y) << 23));
+    return r;
+  }
+  return make_float2(a64_ex2(x.x), a64_ex2(x.y));
+}
+
 __global__ void __launch_bounds__(192, 3) flash_attn_d64_bn64_kernel(const __grid_constant__ AttnParams64 p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -212,6 +234,25 @@ __global__ void __launch_bounds__(192, 3) flash_attn_d64_bn64_kernel(const __gri
         m = m_cand;
       }
       const float neg_m = -m;
+#if VC_ATT_F32X2
+      const float2 sl2v = make_float2(sl2, sl2), negm2 = make_float2(neg_m, neg_m);
+      float2 ps0 = make_float2(0.f, 0.f), ps1 = ps0;
+      // probabilities, packed in place: s0[0..15] <- s0, s0[16..31] <- s1 (packed fp32x2 arithmetic, see attention.cu)
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const float2 a = a64_ex2_pair(__ffma2_rn(make_float2(__uint_as_float(s0[e]), __uint_as_float(s0[e + 1])), sl2v, negm2), e);
+        ps0 = __fadd2_rn(ps0, a);
+        s0[e / 2] = pack_half2(a.x, a.y);
+      }
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const float2 a = a64_ex2_pair(__ffma2_rn(make_float2(__uint_as_float(s1[e]), __uint_as_float(s1[e + 1])), sl2v, negm2), e);
+        ps1 = __fadd2_rn(ps1, a);
+        s0[16 + e / 2] = pack_half2(a.x, a.y);
+      }
+      const float2 pst = __fadd2_rn(ps0, ps1);
+      l += pst.x + pst.y;
+#else
       float ps0 = 0.f, ps1 = 0.f;
       // probabilities, packed in place: s0[0..15] <- s0, s0[16..31] <- s1
 #pragma unroll
@@ -227,6 +268,7 @@ __global__ void __launch_bounds__(192, 3) flash_attn_d64_bn64_kernel(const __gri
         s0[16 + e / 2] = pack_half2(a0, a1);
       }
       l += ps0 + ps1;
+#endif
       if (j > 0) {
         mbar_wait(o_done, (j - 1) & 1);                                // P V of the previous tile retired: P and O may be touched
         tc_fence_after();
