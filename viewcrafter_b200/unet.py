@@ -558,7 +558,8 @@ class UNetModel(nn.Module):
             g = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                e["out"] = self._forward_impl(e["x"], e["t"], context, e["fs"], kwargs)
+                # the final frame gather is a NCCL collective: keep it out of the capture (the peer-memory exchanges are plain kernels)
+                e["out"] = self._forward_impl(e["x"], e["t"], context, e["fs"], kwargs, gather=False)
             e["graph"] = g
             e["launches"] = ops.launch_count() - n0     # kernels of this library inside the graph (launched again by every replay)
             e["kv"] = list(self._kv_caches)             # the captured kernels read these K/V projections: keep them alive
@@ -568,9 +569,12 @@ class UNetModel(nn.Module):
             e["fs"].copy_(fs)
         e["graph"].replay()
         self.graph_replayed_launches += e["launches"]
-        return e["out"].clone()
+        out = e["out"]
+        if self._comm:
+            return self._comm.gather_frames(out, x.shape[2]).to(x.dtype)
+        return out.clone()
 
-    def _forward_impl(self, x, timesteps, context, fs, kwargs):
+    def _forward_impl(self, x, timesteps, context, fs, kwargs, gather=True):
         ops.require_cuda(x.device, "viewcrafter_b200.UNetModel")
         P = self._packed or self._pack()
         if P["device"] != x.device:
@@ -648,5 +652,7 @@ class UNetModel(nn.Module):
         y = ops.conv3x3(ops.groupnorm(h, B * T, *P["out_gn"], 1e-5, True), B * T, H, W, P["out_w"], bias=P["out_b"], out_f32=True)
         out = ops.rows_to_ncthw(y, B, self.out_channels, T, H, W)
         if comm:                                   # every rank needs the whole prediction for the (global-std) DDIM update
+            if not gather:
+                return out                            # this rank's frames only (the graph path gathers after the replay)
             out = comm.gather_frames(out, T_all)
         return out.to(x.dtype)
