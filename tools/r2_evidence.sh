@@ -4,6 +4,16 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
+# attention A/B: polynomial-exp2 selection patterns (side-by-side builds), default library first
+for lib in viewcrafter_b200/libvc_b200.so viewcrafter_b200/libvc_b200_*.so; do
+  [ -f "$lib" ] || continue
+  VC_B200_LIB=$PWD/$lib timeout 200 python tools/ab_micro.py 2>&1 | grep -E "attn|rror" >> $O/e_ab_attn.txt
+done
+VC_ATTN_BN64=1 timeout 200 python tools/ab_micro.py 2>&1 | grep -E "attn" | sed "s/^/[force bn64] /" >> $O/e_ab_attn.txt
+VC_ATTN_BN64=0 timeout 200 python tools/ab_micro.py 2>&1 | grep -E "attn" | sed "s/^/[force bn128] /" >> $O/e_ab_attn.txt
+timeout 200 python tools/ab_micro.py 2>&1 | grep -E "groupnorm|ln_stats" >> $O/e_ab_attn.txt
+cat $O/e_ab_attn.txt
+timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-vae > $O/e_bench_default.json 2> $O/e_bench_default.err; echo "bench default: $(cut -c1-130 $O/e_bench_default.json)"
 for wl in ViewCrafter_25_512 ViewCrafter_16; do
   timeout 400 python bench.py --workload $wl --steps 6 --warmup 3 --no-cpu-baseline > $O/e_bench_$wl.json 2> $O/e_bench_$wl.err
   echo "$wl rc=$? $(cut -c1-200 $O/e_bench_$wl.json)"
