@@ -178,6 +178,12 @@ typedef struct vc_peer_comm {
   int32_t Bmax;                      /* batch samples per rank the slots were sized for (1 or 2)                    */
 } vc_peer_comm;
 int vc_enable_peer_access(int32_t peer_device);
+/* IPC-shareable, zero-filled device memory (cudaMalloc) + its 64-byte cudaIpcMemHandle_t; vc_peer_open maps another process's
+ * allocation with the CALLING process's current device as the accessor (lazy peer mapping), vc_peer_close / vc_peer_free undo. */
+int vc_peer_alloc(size_t bytes, void** ptr, void* handle64);
+int vc_peer_open(const void* handle64, void** ptr);
+int vc_peer_close(void* ptr);
+int vc_peer_free(void* ptr);
 /* src: local fp16 rows; dst[p]: rank p's receive buffer as mapped here; f0[world+1]: frame range boundaries of the ranks.
  * to_sites = 1: [(b, t_local, hw), C] -> [(b, t_all, hw_local), C]; 0: the reverse.  ws: >= B * 512 * 64 floats. */
 int vc_peer_exchange(const vc_peer_comm* c, const void* src, void* const* dst, int32_t to_sites, int32_t B, int32_t T, int32_t HW,

@@ -35,14 +35,21 @@ if peer_mode:
     for (Bq, HWq, Cq) in ((2, 256, 64), (1, 64, 320), (2, 16, 1280)):
         gq = torch.Generator().manual_seed(100 + rank)
         hq = (torch.randn(Bq * (f1 - f0) * HWq, Cq, generator=gq) * 1.5 + 0.3).half().cuda()
+        dbg = os.environ.get("VC_DEBUG_SYNC") == "1"
         a = comm.to_sites(hq, Bq, HWq)
+        if dbg:
+            torch.cuda.synchronize(); print(f"[rank {rank}] to_sites ok B={Bq} HW={HWq} C={Cq}", flush=True)
         b = ref_comm.to_sites(hq, Bq, HWq)
         same_sites = torch.equal(a, b)
         gam, bet = torch.rand(Cq, device="cuda") + 0.5, torch.randn(Cq, device="cuda") * 0.1
         n1 = comm.groupnorm5d(a, Bq, gam, bet, 1e-5, True, T * HWq, True)
+        if dbg:
+            torch.cuda.synchronize(); print(f"[rank {rank}] groupnorm (fused stats) ok", flush=True)
         n2 = ref_comm.groupnorm5d(b, Bq, gam, bet, 1e-5, True, T * HWq, True)
         n3 = comm.groupnorm5d(b.clone(), Bq, gam, bet, 1e-5, True, T * HWq, False)      # statistics through vc_peer_groupnorm_stats
         e12, e13 = float((n1.float() - n2.float()).abs().max()), float((n3.float() - n2.float()).abs().max())
+        if dbg:
+            torch.cuda.synchronize(); print(f"[rank {rank}] groupnorm (peer stats) ok", flush=True)
         back = comm.to_frames(a.clone(), Bq, HWq)
         same_back = torch.equal(back, hq)
         torch.cuda.synchronize()

@@ -8,8 +8,8 @@ mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 nvidia-smi topo -m > $O/m${N}_topo.txt 2>&1
 for peer in 1 0; do
-  VC_PEER_COMM=$peer timeout 600 $TR --master-port 29541 tools/parallel_check.py > $O/m${N}_check_peer$peer.log 2>&1
-  echo "parallel_check N=$N peer=$peer rc=$?"; grep -E "world|peer exchange|PARALLEL_CHECK_OK|Error|error" $O/m${N}_check_peer$peer.log | tail -12
+  VC_DEBUG_SYNC=1 VC_PEER_COMM=$peer timeout 600 $TR --master-port 29541 tools/parallel_check.py > $O/m${N}_check_peer$peer.log 2>&1
+  echo "parallel_check N=$N peer=$peer rc=$?"; grep -E "world|peer exchange|rank [0-9]\]|PARALLEL_CHECK_OK|Error|error" $O/m${N}_check_peer$peer.log | tail -12
 done
 run() { # name, env..., args
   local name=$1; shift

@@ -65,6 +65,10 @@ SIGNATURES = {
     "vc_groupnorm_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _f32, _i32, _vp, _vp]),
     "vc_groupnorm_apply_parts": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _i32, _i64, _vp, _vp, _f32, _i32, _vp, _vp]),
     "vc_enable_peer_access": (C.c_int, [_i32]),
+    "vc_peer_alloc": (C.c_int, [_sz, C.POINTER(C.c_void_p), _vp]),
+    "vc_peer_open": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
+    "vc_peer_close": (C.c_int, [_vp]),
+    "vc_peer_free": (C.c_int, [_vp]),
     "vc_peer_exchange": (C.c_int, [C.POINTER(PeerComm), _vp, C.POINTER(C.c_void_p), _i32, _i32, _i32, _i32, _i32, C.POINTER(C.c_int32), _i32,
                                    _vp, _sz, _vp]),
     "vc_peer_groupnorm_stats": (C.c_int, [C.POINTER(PeerComm), _vp, _i32, _i32, _i64, _vp, _sz, _vp]),

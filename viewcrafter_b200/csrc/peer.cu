@@ -241,6 +241,43 @@ int vc_enable_peer_access(int32_t peer_device) {
   return VC_OK;
 }
 
+/* IPC-shareable device memory: plain cudaMalloc (the handle then refers to exactly this allocation), zero-filled.  The importing
+ * rank opens the handle with ITS OWN compute device current, so that the lazy peer mapping is created for the device whose
+ * kernels will dereference the pointer. */
+int vc_peer_alloc(size_t bytes, void** ptr, void* handle64) {
+  if (!ptr || !handle64 || bytes == 0) { vc::set_error("vc_peer_alloc: bad args"); return VC_ERR_ARG; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* p = nullptr;
+  VC_CHECK_CUDA(cudaMalloc(&p, bytes));
+  VC_CHECK_CUDA(cudaMemset(p, 0, bytes));
+  VC_CHECK_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    vc::set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return VC_ERR_CUDA;
+  }
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return VC_OK;
+}
+int vc_peer_open(const void* handle64, void** ptr) {
+  if (!ptr || !handle64) { vc::set_error("vc_peer_open: bad args"); return VC_ERR_ARG; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  VC_CHECK_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return VC_OK;
+}
+int vc_peer_close(void* ptr) {
+  VC_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return VC_OK;
+}
+int vc_peer_free(void* ptr) {
+  VC_CHECK_CUDA(cudaFree(ptr));
+  return VC_OK;
+}
+
 int vc_peer_exchange(const vc_peer_comm* c, const void* src, void* const* dst, int32_t to_sites, int32_t B, int32_t T, int32_t HW,
                      int32_t C, const int32_t* f0, int32_t with_stats, void* ws, size_t ws_bytes, void* stream) {
   using namespace vc;

@@ -99,7 +99,8 @@ class FrameComm:
 class PeerFrameComm(FrameComm):
     """FrameComm whose layout switches and GroupNorm statistics run as this library's own kernels over NVLink peer memory
     (csrc/peer.cu) instead of NCCL collectives: every rank maps the receive buffers, flag words and statistics slots of the
-    other ranks of its group (CUDA IPC through torch's shared-storage handles, exchanged once over the process group) and
+    other ranks of its group (CUDA IPC: cudaMalloc'd buffers, handles exchanged once over the process group, opened with the
+    importing rank's compute device current) and
       * to_sites / to_frames are ONE kernel each (rows stored straight into the owning rank's buffer; no pack / unpack copy),
       * the statistics of the 5-D GroupNorm that follows every to_sites ride along with it (no statistics pass, no all-reduce),
       * the GroupNorms in the middle of a temporal block exchange 2 x 32 floats per sample through the same flag protocol.
@@ -112,60 +113,69 @@ class PeerFrameComm(FrameComm):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.bmax = bmax
-        self._bufs = {}            # name -> (local tensor, [remote views], nbytes)
-        self._keep = []            # remote storages must stay alive
-        self._ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+        self._bufs = {}            # name -> (own tensor, [device pointer of rank q's buffer as mapped here], capacity in elements)
+        self._own_ptrs, self._peer_ptrs = [], []
         with torch.cuda.device(self.device):
-            flags = torch.zeros(world, dtype=torch.int32, device=self.device)
-            slots = torch.zeros((2, bmax, world, 64), dtype=torch.float32, device=self.device)
             self.seq = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.done = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.cur_stats = torch.zeros((bmax, world, 32, 2), dtype=torch.float32, device=self.device)
             self.ws = torch.empty(bmax * 512 * 64, dtype=torch.float32, device=self.device)
             torch.cuda.synchronize()
-        self.flags, self.peer_flags = self._share(flags)
-        self.slots, self.peer_slots = self._share(slots)
+            self.flags, flag_ptrs = self._shared(world * 4, torch.int32)
+            self.slots, slot_ptrs = self._shared(2 * bmax * world * 64 * 4, torch.float32)
         c = _lib.PeerComm()
         c.world, c.rank, c.Bmax = world, rank, bmax
         c.flags, c.seq, c.done, c.cur_stats = self.flags.data_ptr(), self.seq.data_ptr(), self.done.data_ptr(), self.cur_stats.data_ptr()
         for q in range(world):
-            c.peer_flags[q] = self.peer_flags[q].data_ptr()
-            c.stats_slots[q] = self.peer_slots[q].data_ptr()
+            c.peer_flags[q] = flag_ptrs[q]
+            c.stats_slots[q] = slot_ptrs[q]
         self.c = c
         self._stats_of = None      # data_ptr of the tensor whose statistics cur_stats holds
 
     # -- CUDA IPC plumbing (setup only) -------------------------------------------------------------
-    def _share(self, t: torch.Tensor):
-        """Map `t` of every rank of the group into this process; returns (own tensor, [view of rank q's tensor])."""
+    class _Raw:
+        """__cuda_array_interface__ over a raw device allocation, so torch can alias it."""
+
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+    def _shared(self, nbytes: int, dtype):
+        """A zero-filled IPC-shareable allocation of `nbytes` on EVERY rank of the group (collective).  Returns (own tensor of
+        `dtype`, [device pointer of rank q's allocation as mapped into this process]); the mapping is opened with this rank's
+        compute device current, which is what gives its kernels access over NVLink."""
         import ctypes as C
         from . import _lib
-        handle = (t.untyped_storage()._share_cuda_(), t.storage_offset(), tuple(t.shape), t.dtype)
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        ptr, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        _lib.check(self.lib.vc_peer_alloc(nbytes, C.byref(ptr), handle), "vc_peer_alloc")
+        self._own_ptrs.append(ptr.value)
         handles = [None] * self.world
-        self.dist.all_gather_object(handles, handle, group=self.group)
-        views = []
-        for q, (h, off, shape, dtype) in enumerate(handles):
+        self.dist.all_gather_object(handles, (bytes(handle), torch.cuda.current_device()), group=self.group)
+        ptrs = []
+        for q, (hb, dev_q) in enumerate(handles):
             if q == self.rank:
-                views.append(t)
+                ptrs.append(ptr.value)
                 continue
-            _lib.check(self.lib.vc_enable_peer_access(int(h[0])), "vc_enable_peer_access")
-            st = torch.UntypedStorage._new_shared_cuda(*h)
-            v = torch.empty(0, dtype=dtype, device=st.device).set_(st, off, shape)
-            self._keep.append(st)
-            views.append(v)
+            _lib.check(self.lib.vc_enable_peer_access(int(dev_q)), "vc_enable_peer_access")
+            rp = C.c_void_p()
+            _lib.check(self.lib.vc_peer_open((C.c_uint8 * 64).from_buffer_copy(hb), C.byref(rp)), "vc_peer_open")
+            self._peer_ptrs.append(rp.value)
+            ptrs.append(rp.value)
+        own = torch.as_tensor(self._Raw(ptr.value, nbytes), device=self.device).view(dtype)
         self.dist.barrier(group=self.group)
-        return t, views
+        return own, ptrs
 
-    def _buffer(self, name: str, numel: int, dtype=torch.float16):
-        """Receive buffer `name` with room for `numel` elements on EVERY rank (collective: all ranks grow it together)."""
+    def _buffer(self, name: str, numel: int):
+        """fp16 receive buffer `name` with room for `numel` elements on EVERY rank (collective: all ranks grow it together)."""
         ent = self._bufs.get(name)
-        if ent is None or ent[0].numel() < numel:
+        if ent is None or ent[2] < numel:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("PeerFrameComm: a receive buffer must grow during CUDA-graph capture; run one eager forward first")
             torch.cuda.synchronize()
             self.dist.barrier(group=self.group)          # nobody still writes into the old mapping
             with torch.cuda.device(self.device):
-                t = torch.empty(numel, dtype=dtype, device=self.device)
-            ent = self._share(t)
+                own, ptrs = self._shared(numel * 2, torch.float16)
+            ent = (own, ptrs, numel)
             self._bufs[name] = ent
         return ent
 
@@ -180,8 +190,8 @@ class PeerFrameComm(FrameComm):
         tmax = max(f1 - f0 for f0, f1 in self.ranges)
         out_rows = B * self.T * HWl if to_sites else B * Tl * HW
         cap = B * (self.T * HWl if to_sites else tmax * HW) * Cc        # same on every rank
-        own, views, = self._buffer("sites" if to_sites else "frames", cap)
-        dst = (C.c_void_p * P)(*[v.data_ptr() for v in views])
+        own, ptrs, _ = self._buffer("sites" if to_sites else "frames", cap)
+        dst = (C.c_void_p * P)(*ptrs)
         f0 = (C.c_int32 * (P + 1))(*([r[0] for r in self.ranges] + [self.T]))
         _lib.check(self.lib.vc_peer_exchange(C.byref(self.c), h.data_ptr(), dst, int(to_sites), B, self.T, HW, Cc, f0, int(to_sites),
                                              self.ws.data_ptr(), self.ws.numel() * 4, torch.cuda.current_stream().cuda_stream), "vc_peer_exchange")
@@ -216,6 +226,14 @@ class PeerFrameComm(FrameComm):
         """True if `t` is a view of one of the reusable receive buffers."""
         p = t.data_ptr()
         return any(ent[0].data_ptr() <= p < ent[0].data_ptr() + ent[0].numel() * 2 for ent in self._bufs.values())
+
+    def close(self):
+        """Unmap the peers' buffers and free the own ones (call on every rank after a barrier; optional at process exit)."""
+        for p in self._peer_ptrs:
+            self.lib.vc_peer_close(p)
+        for p in self._own_ptrs:
+            self.lib.vc_peer_free(p)
+        self._peer_ptrs, self._own_ptrs, self._bufs = [], [], {}
 
 
 class CfgComm:
