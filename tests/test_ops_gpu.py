@@ -420,3 +420,17 @@ def test_upsample_conv_fused(ops, frames, H, W, Ci, Co):
     ref = F.conv2d(F.interpolate(xi, scale_factor=2, mode="nearest"), w.cuda(), b, padding=1)
     ref = ref.permute(0, 2, 3, 1).reshape(-1, Co)
     close(y, ref, atol=6e-3, what="upconv3x3")
+
+
+@pytest.mark.parametrize("env", [{"VC_ATTN_PP": "1", "VC_ATTN_BN64": "0"}, {"VC_ATTN_PP": "0", "VC_ATTN_BN64": "0"}, {"VC_ATTN_BN64": "1"}])
+def test_attention_kernel_variants(env):
+    """Every attention kernel (ping-pong / two-CTA 128-key tiles / 64-key tiles), forced for ALL shapes through the environment in a
+    fresh process (the choice is cached per process), against the fp32 reference: tools/attn_check.py."""
+    import os, subprocess, sys
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "attn_check.py")], capture_output=True, text=True, timeout=280,
+                       env=dict(os.environ, **env))
+    print(r.stdout[-1500:], r.stderr[-1500:])
+    assert r.returncode == 0 and "ATTN_CHECK_OK" in r.stdout
