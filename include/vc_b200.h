@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VC_B200_ABI_VERSION 4
+#define VC_B200_ABI_VERSION 5
 
 int vc_abi_version(void);
 const char* vc_last_error(void);
@@ -63,6 +63,11 @@ typedef struct vc_gemm_desc {
    * with N % 32 == 0 and no residual.  Upsample (F.interpolate nearest x2, openaimodel3d.py:80-106) + 3x3 conv runs as four
    * parity sub-convolutions with 2x2 pre-summed taps on the SMALL image, each writing every second pixel of the large one. */
   int64_t ldo_y, ldo_z;
+  /* optional by-product for the NEXT GroupNorm (basics.py:76-87, openaimodel3d.py:256-265): partial (sum, sumsq) of the fp16-rounded
+   * output per 32-row block rb = m_tile * 4 + quadrant (m-tiles in x, y, z order, count padded to an even number), 32-column chunk and
+   * piece: gn_part[((rb * (N/32) + chunk) * 4 + piece) * 2]; a chunk is cut into 4 pieces at multiples of gn_sub (10 or 8) channels.
+   * vc_groupnorm_from_parts consumes them.  fp16 outputs with N % 32 == 0 and N % gn_sub == 0 only. */
+  float* gn_part; int32_t gn_sub;
 } vc_gemm_desc;
 int vc_gemm_tap(const vc_gemm_desc* d, void* stream);
 /* N-tile width the kernel will use for (N, geglu): needed to interleave GEGLU weights on the host */
@@ -109,6 +114,18 @@ int vc_groupnorm_apply(const void* x1, int32_t C1, const void* x2, int32_t C2, i
 /* pass 2 with UN-reduced statistics: parts = [samples][n_parts][32][2] partial (sum, sumsq), summed in index order */
 int vc_groupnorm_apply_parts(const void* x1, int32_t C1, int32_t samples, int64_t rows_per_sample, const float* parts, int32_t n_parts,
                              int64_t stat_rows, const float* gamma, const float* beta, float eps, int32_t silu, void* out, void* stream);
+/* GroupNorm(32) (+SiLU) of concat(x1, x2) whose statistics come from the gn_part records the producing vc_gemm_tap calls left
+ * (one descriptor per source): the activation is read once and written once, there is no statistics pass.
+ * Sample s of the consumer covers the 32-row blocks [base, base + rb_per_sample) of the producer with
+ * base = (s / samples_per_z) * rb_per_z + (s % samples_per_z) * rb_per_sample.  Every group boundary of the consumer must be a
+ * multiple of `sub` channels inside each source.  ws: vc_groupnorm_parts_ws_bytes(samples) bytes. */
+typedef struct vc_gn_part_geom {
+  const float* part; int32_t n_chunks; int32_t sub; int64_t rb_per_z; int32_t samples_per_z; int64_t rb_per_sample;
+} vc_gn_part_geom;
+size_t vc_groupnorm_parts_ws_bytes(int32_t samples);
+int vc_groupnorm_from_parts(const void* x1, int32_t C1, const vc_gn_part_geom* g1, const void* x2, int32_t C2, const vc_gn_part_geom* g2,
+                            int32_t samples, int64_t rows_per_sample, const float* gamma, const float* beta, float eps, int32_t silu,
+                            void* out, void* ws, size_t ws_bytes, void* stream);
 /* statistics half of nn.LayerNorm: stats[row] = (mean, 1/sqrt(var + eps)) in fp32; the normalisation is applied by the
  * consuming vc_gemm_tap (ln_stats / ln_colsum), so the normalised activation is never written to memory */
 int vc_layernorm_stats(const void* x, int64_t rows, int32_t C, float eps, float* stats, void* stream);

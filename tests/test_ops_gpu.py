@@ -434,3 +434,101 @@ def test_attention_kernel_variants(env):
                        env=dict(os.environ, **env))
     print(r.stdout[-1500:], r.stderr[-1500:])
     assert r.returncode == 0 and "ATTN_CHECK_OK" in r.stdout
+
+
+# ------------------------------------------------------------------ GroupNorm statistics from the producing GEMM's epilogue
+def _gn_ref(y, samples, g, b, eps, silu):
+    rows, C = y.shape[0] // samples, y.shape[1]
+    xr = y.float().reshape(samples, rows, C).permute(0, 2, 1)
+    ref = F.group_norm(xr, 32, g, b, eps)
+    if silu:
+        ref = F.silu(ref)
+    return ref.permute(0, 2, 1).reshape(samples * rows, C)
+
+
+def _force_gn_parts(ops, monkeypatch, mode=2):
+    monkeypatch.setattr(ops, "GN_FROM_PRODUCER", mode)
+
+
+@pytest.mark.parametrize("frames,H,W,Ci,Co", [(3, 9, 16, 64, 320), (2, 18, 32, 320, 640), (2, 36, 64, 128, 320), (3, 72, 128, 64, 320),
+                                               (5, 9, 16, 320, 1280)])
+def test_groupnorm_from_conv3x3_partial_sums(ops, monkeypatch, frames, H, W, Ci, Co):
+    """conv3x3(gn_out=True) leaves per-(32-row block, chunk, piece) sums; groupnorm() on that tensor (4-D: one sample per frame, and
+    5-D: one sample over all frames) skips its statistics pass and must equal the GroupNorm of the stored output."""
+    _force_gn_parts(ops, monkeypatch)
+    x = rnd(frames * H * W, Ci, seed=61)
+    w = ops.pack_conv3x3(torch.randn(Co, Ci, 3, 3, generator=torch.Generator().manual_seed(62)) * (2.0 / math.sqrt(9 * Ci))).cuda()
+    bias = torch.randn(Co, generator=torch.Generator().manual_seed(63)).cuda()
+    r = rnd(frames * H * W, Co, seed=64)
+    y_ref = ops.conv3x3(x, frames, H, W, w, bias=bias, res=r)
+    y = ops.conv3x3(x, frames, H, W, w, bias=bias, res=r, gn_out=True)
+    assert torch.equal(y, y_ref) and ops.gn_part_of(y) is not None
+    g, b = rnd(Co, seed=65, dtype=torch.float32), rnd(Co, seed=66, dtype=torch.float32)
+    n0 = ops.gn_from_parts_calls
+    out4 = ops.groupnorm(y, frames, g, b, 1e-5, True)
+    assert ops.gn_from_parts_calls - n0 == 1, "expected finalize + apply (the partial-sum path), not the statistics-pass kernel"
+    close(out4, _gn_ref(y_ref, frames, g, b, 1e-5, True), 3e-3, what="4-D from parts")
+    assert torch.equal(out4, ops.groupnorm(y, frames, g, b, 1e-5, True)), "not deterministic"
+    out5 = ops.groupnorm(y, 1, g, b, 1e-6, False)
+    close(out5, _gn_ref(y_ref, 1, g, b, 1e-6, False), 3e-3, what="5-D from parts")
+    # the path without the producer's sums gives the same result up to fp32 summation order
+    assert float((out4.float() - ops.groupnorm(y_ref, frames, g, b, 1e-5, True).float()).abs().max()) < 4e-3
+
+
+@pytest.mark.parametrize("B,T,HW,C", [(2, 5, 576, 320), (1, 7, 144, 640), (2, 4, 2304, 320), (1, 3, 96, 1280)])
+def test_groupnorm_from_temporal_conv_and_linear_partial_sums(ops, monkeypatch, B, T, HW, C):
+    """Producers in the linear row geometry (temporal conv: Z = B slabs of T*HW rows; 1x1 linear: one slab): consumers are the 5-D
+    GroupNorm (sample = batch element) and the 4-D GroupNorm (sample = frame, HW % 32 == 0; otherwise the statistics-pass path)."""
+    _force_gn_parts(ops, monkeypatch)
+    M = B * T * HW
+    x = rnd(M, C, seed=71)
+    w3 = ops.pack_conv_temporal(torch.randn(C, C, 3, 1, 1, generator=torch.Generator().manual_seed(72)) * (2.0 / math.sqrt(3 * C))).cuda()
+    y = ops.conv_temporal(x, B, T, HW, w3, bias=None, res=x, gn_out=True)
+    y_ref = ops.conv_temporal(x, B, T, HW, w3, bias=None, res=x)
+    assert torch.equal(y, y_ref)
+    g, b = rnd(C, seed=73, dtype=torch.float32), rnd(C, seed=74, dtype=torch.float32)
+    close(ops.groupnorm(y, B, g, b, 1e-5, True), _gn_ref(y_ref, B, g, b, 1e-5, True), 3e-3, what="5-D after temporal conv")
+    n0 = ops.gn_from_parts_calls
+    out = ops.groupnorm(y, B * T, g, b, 1e-6, False)
+    assert (ops.gn_from_parts_calls - n0 == 1) == (HW % 32 == 0)
+    close(out, _gn_ref(y_ref, B * T, g, b, 1e-6, False), 3e-3, what="4-D after temporal conv")
+    wl = rnd(C, C, seed=75, scale=2.0 * C ** -0.5)
+    z = ops.linear(x, wl, res=y_ref, gn_out=True)
+    z_ref = ops.linear(x, wl, res=y_ref)
+    assert torch.equal(z, z_ref) and ops.gn_part_of(z) is not None
+    close(ops.groupnorm(z, B, g, b, 1e-5, True), _gn_ref(z_ref, B, g, b, 1e-5, True), 3e-3, what="5-D after linear")
+    close(ops.groupnorm(z, B * T, g, b, 1e-5, True), _gn_ref(z_ref, B * T, g, b, 1e-5, True), 3e-3, what="4-D after linear")
+
+
+@pytest.mark.parametrize("C1,C2", [(320, 320), (640, 320), (640, 640), (1280, 640), (1280, 1280)])
+def test_groupnorm_concat_from_partial_sums(ops, monkeypatch, C1, C2):
+    """The skip-concat GroupNorm of the output blocks: both sources carry their producers' sums; groups of (C1 + C2) / 32 = 20 / 30 / 40 /
+    60 / 80 channels are assembled from the 10-channel sub-groups of the two sources (a group may straddle the concat boundary)."""
+    _force_gn_parts(ops, monkeypatch)
+    frames, H, W = 3, 18, 32
+    M = frames * H * W
+    xa, xb = rnd(M, 64, seed=81), rnd(M, 64, seed=82)
+    wa = rnd(C1, 64, seed=83, scale=0.3)
+    wb = ops.pack_conv3x3(torch.randn(C2, 64, 3, 3, generator=torch.Generator().manual_seed(84)) * 0.1).cuda()
+    a = ops.linear(xa, wa, gn_out=True)
+    s = ops.conv3x3(xb, frames, H, W, wb, gn_out=True)
+    C = C1 + C2
+    g, b = rnd(C, seed=85, dtype=torch.float32), rnd(C, seed=86, dtype=torch.float32)
+    n0 = ops.gn_from_parts_calls
+    out = ops.groupnorm(a, frames, g, b, 1e-5, True, x2=s)
+    assert ops.gn_from_parts_calls - n0 == 1
+    ref = _gn_ref(torch.cat([a, s], 1), frames, g, b, 1e-5, True)
+    close(out, ref, 3e-3, what="concat from parts")
+    a2 = a.clone()                                          # a source without sums -> the statistics-pass kernel
+    close(ops.groupnorm(a2, frames, g, b, 1e-5, True, x2=s), ref, 3e-3, what="concat fallback")
+
+
+def test_gemm_output_unchanged_by_gn_out_cta_pair_and_single(ops, monkeypatch):
+    """Large problems run on CTA pairs (m-tile count padded to even), small ones on single CTAs: records of both kernels are consumed."""
+    _force_gn_parts(ops, monkeypatch)
+    for M, K, N in ((128 * 301, 320, 320), (128 * 3 + 40, 640, 640), (40000, 1280, 320)):
+        x, w = rnd(M, K, seed=91), rnd(N, K, seed=92, scale=2.0 * K ** -0.5)
+        y = ops.linear(x, w, gn_out=True)
+        assert torch.equal(y, ops.linear(x, w))
+        g, b = rnd(N, seed=93, dtype=torch.float32), rnd(N, seed=94, dtype=torch.float32)
+        close(ops.groupnorm(y, 1, g, b, 1e-5, False), _gn_ref(y, 1, g, b, 1e-5, False), 3e-3, what=f"M={M}")

@@ -22,6 +22,15 @@ if which in ("norm", "all"):
     for _ in range(3):
         ops.groupnorm(x, T, g, be, 1e-5, True)
         ops.layernorm_stats(x)
+if which in ("gnparts", "all"):
+    # GroupNorm whose statistics come from the producing conv's epilogue: conv with gn_out, then finalize + one-pass normalise
+    ops.GN_FROM_PRODUCER = 2
+    w9 = (torch.randn(9 * C, C, device="cuda") * 0.02).half()
+    g, be = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    for _ in range(3):
+        y = ops.conv3x3(x, T, H, W, w9, gn_out=True)
+        ops.groupnorm(y, T, g, be, 1e-5, True)
+        ops.groupnorm(y, 1, g, be, 1e-5, True)
 if which in ("lin", "all"):
     # level-0 transformer linears with the LayerNorm folded into the epilogue: qkv (320->960) and GEGLU (320->2560)
     g32, b32 = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VC_B200_LIB") or os.path.join(_HERE, "libvc_b200.so")   # override: A/B builds of the kernels
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class VcError(RuntimeError):
@@ -25,7 +25,12 @@ class GemmDesc(C.Structure):
                 ("out", C.c_void_p), ("out_f32", C.c_void_p), ("ldo", C.c_int32),
                 ("bias", C.c_void_p), ("bias_z_div", C.c_int32), ("res", C.c_void_p), ("ldr", C.c_int32),
                 ("geglu", C.c_int32), ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_part", C.c_void_p),
-                ("ldo_y", C.c_int64), ("ldo_z", C.c_int64)]
+                ("ldo_y", C.c_int64), ("ldo_z", C.c_int64), ("gn_part", C.c_void_p), ("gn_sub", C.c_int32)]
+
+
+class GnPartGeom(C.Structure):
+    _fields_ = [("part", C.c_void_p), ("n_chunks", C.c_int32), ("sub", C.c_int32), ("rb_per_z", C.c_int64),
+                ("samples_per_z", C.c_int32), ("rb_per_sample", C.c_int64)]
 
 
 class AttnDesc(C.Structure):
@@ -63,6 +68,9 @@ SIGNATURES = {
     "vc_groupnorm_nhwc": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp, _vp, _f32, _i32, _vp, _vp, _sz, _vp]),
     "vc_groupnorm_stats": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp, _vp, _sz, _vp]),
     "vc_groupnorm_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _f32, _i32, _vp, _vp]),
+    "vc_groupnorm_parts_ws_bytes": (_sz, [_i32]),
+    "vc_groupnorm_from_parts": (C.c_int, [_vp, _i32, C.POINTER(GnPartGeom), _vp, _i32, C.POINTER(GnPartGeom), _i32, _i64, _vp, _vp, _f32, _i32,
+                                          _vp, _vp, _sz, _vp]),
     "vc_groupnorm_apply_parts": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _i32, _i64, _vp, _vp, _f32, _i32, _vp, _vp]),
     "vc_enable_peer_access": (C.c_int, [_i32]),
     "vc_peer_alloc": (C.c_int, [_sz, C.POINTER(C.c_void_p), _vp]),

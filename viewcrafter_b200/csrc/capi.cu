@@ -33,7 +33,7 @@ int vc_gemm_tap(const vc_gemm_desc* c, void* stream) {
   for (int i = 0; i < 9; ++i) { d.tap_dx[i] = c->tap_dx[i]; d.tap_dy[i] = c->tap_dy[i]; }
   d.out = HM(c->out); d.out_f32 = reinterpret_cast<float*>(c->out_f32); d.ldo = c->ldo;
   d.bias = c->bias; d.bias_z_div = c->bias_z_div; d.res = H(c->res); d.ldr = c->ldr; d.geglu = c->geglu;
-  d.ln_stats = c->ln_stats; d.ln_colsum = c->ln_colsum; d.ln_part = c->ln_part;
+  d.ln_stats = c->ln_stats; d.ln_colsum = c->ln_colsum; d.ln_part = c->ln_part; d.gn_part = c->gn_part; d.gn_sub = c->gn_sub;
   d.ldo_y = c->ldo_y; d.ldo_z = c->ldo_z;
   COUNT(1);
   return gemm_tap(d, ST(stream));
@@ -74,6 +74,20 @@ int vc_groupnorm_apply(const void* x1, int32_t C1, const void* x2, int32_t C2, i
                        void* stream) {
   COUNT(1);
   return groupnorm_apply(H(x1), C1, H(x2), C2, samples, rows_per_sample, stats, stat_rows, gamma, beta, eps, silu, HM(out), ST(stream));
+}
+size_t vc_groupnorm_parts_ws_bytes(int32_t samples) { return groupnorm_parts_ws_bytes(samples); }
+int vc_groupnorm_from_parts(const void* x1, int32_t C1, const vc_gn_part_geom* g1, const void* x2, int32_t C2, const vc_gn_part_geom* g2,
+                            int32_t samples, int64_t rows_per_sample, const float* gamma, const float* beta, float eps, int32_t silu,
+                            void* out, void* ws, size_t ws_bytes, void* stream) {
+  if (!g1 || (x2 && !g2)) { set_error("vc_groupnorm_from_parts: null geometry"); return VC_ERR_ARG; }
+  auto conv = [](const vc_gn_part_geom* c) {
+    GnPartGeom g;
+    if (c) { g.part = c->part; g.n_chunks = c->n_chunks; g.sub = c->sub; g.rb_per_z = c->rb_per_z; g.samples_per_z = c->samples_per_z; g.rb_per_sample = c->rb_per_sample; }
+    return g;
+  };
+  COUNT(x2 ? 3 : 2);
+  return groupnorm_from_parts(H(x1), C1, conv(g1), H(x2), C2, conv(g2), samples, rows_per_sample, gamma, beta, eps, silu, HM(out),
+                              reinterpret_cast<float*>(ws), ws_bytes, ST(stream));
 }
 int vc_groupnorm_apply_parts(const void* x1, int32_t C1, int32_t samples, int64_t rows_per_sample, const float* parts, int32_t n_parts,
                              int64_t stat_rows, const float* gamma, const float* beta, float eps, int32_t silu, void* out, void* stream) {

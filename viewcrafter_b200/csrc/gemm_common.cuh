@@ -77,6 +77,9 @@ struct GemmParams {
   const float* ln_colsum;  // folded LayerNorm: per-column sum of the (gamma-scaled) weights
   float2* ln_part;         // optional: per (32-column chunk, row) partial (sum, sumsq) of the fp16-rounded outputs, [N/32][ln_rows]:
   long long ln_rows;       //   the LayerNorm statistics of the tensor this GEMM writes, gathered while it is still in registers
+  float2* gn_part;         // optional: GroupNorm partial (sum, sumsq) of the fp16-rounded outputs per (32-row block, 32-column chunk, piece):
+  int gn_hp;               //   [m_tile * 4 + quadrant][N / 32][4]; a chunk is cut at the boundaries of gn_sub = 2 * gn_hp channel sub-groups
+  int gn_nchunks;          //   (4 pieces: first partial, two whole, last partial / whole) -- see gn_part_accumulate and norm.cu: gn_part_finalize_kernel
   int out_tma;           // fp16 output written by TMA stores from per-warp staging tiles (full-line, LSU-free)
   int vec_ok;            // rows are 32-byte aligned: the 256-bit epilogue path may be used
   int debug;             // profiling aid, only honoured by builds with -DVC_GEMM_DEBUG_BUILD=1 (env VC_GEMM_DEBUG): 1 = skip the MMAs
@@ -177,6 +180,7 @@ struct EpiTile {
   long long orow;        // output row index of this thread
   const float* bias;     // bias row for this tile's z (or nullptr)
   int n_tile;
+  int m_tile;            // linear m-tile index (x fastest, then y, then z)
   int c_first;           // this warp's first chunk in the tile
   int wx, wy, wz;        // (x, y, z) of the warp's first row: TMA store coordinates
   bool row_ok;
@@ -187,7 +191,8 @@ __device__ __forceinline__ EpiTile epi_tile(const GemmParams& p, int tile, int l
   EpiTile t;
   const int mq = fast_div(p.div_n_tiles, tile);
   t.n_tile = tile - mq * p.n_tiles;
-  const TileCoord tc = tile_coord_m(p, mq * m_mul + m_add);
+  t.m_tile = mq * m_mul + m_add;
+  const TileCoord tc = tile_coord_m(p, t.m_tile);
   const int R = (warp & 3) * 32 + lane;          // accumulator row owned by this thread (TMEM lane)
   const int R0 = (warp & 3) * 32;
   t.wx = tc.x0 + (R0 & (p.bx - 1)); t.wy = tc.y0 + (R0 >> p.bx_shift); t.wz = tc.z;
@@ -256,6 +261,82 @@ __device__ __forceinline__ void epi_store32(const GemmParams& p, const EpiTile& 
         else p.out[t.orow * p.ldo + col0 + e] = __float2half_rn(v);
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm statistics of the tensor a GEMM is writing (GemmParams::gn_part), so that the consuming GroupNorm is ONE pass over
+// the activation (read + write once) instead of statistics pass + normalise pass.  GroupNorm(32) groups are C/32 channels wide
+// (10 / 20 / 40 in the U-Net, 30 / 60 / 80 for the skip concats) and do not line up with the 32-column chunks a thread owns,
+// so each chunk is cut into 4 pieces at the boundaries of `sub`-channel sub-groups (sub = 10: every group boundary of every
+// consumer is a multiple of 10; sub = 8 for power-of-two widths): with o = (first column) mod sub, the pieces are
+// [0, sub-o), [sub-o, 2 sub-o), [2 sub-o, 3 sub-o), [3 sub-o, 32) -- always exactly four for sub in {8, 10}.  A thread owns one
+// row: it sums its fp16-rounded values (what the consumer will read) per piece, the warp reduces the 8 numbers over its 32 rows
+// with a recursive-halving exchange (9 shuffles; fixed order -> bit-reproducible) and 8 lanes store them.
+// B1 = pairs in the first piece, HP = pairs per sub-group.
+template <int B1, int HP>
+__device__ __forceinline__ void gn_piece_sums(const float (&f)[32], bool row_ok, float (&v)[8]) {
+  float2 s[4], q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s[i] = q[i] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int piece = e < B1 ? 0 : e < B1 + HP ? 1 : e < B1 + 2 * HP ? 2 : 3;
+    const float2 r = __half22float2(__floats2half2_rn(f[2 * e], f[2 * e + 1]));
+    s[piece] = __fadd2_rn(s[piece], r);
+    q[piece] = __ffma2_rn(r, r, q[piece]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = row_ok ? s[i].x + s[i].y : 0.f;
+    v[4 + i] = row_ok ? q[i].x + q[i].y : 0.f;
+  }
+}
+__device__ __forceinline__ void gn_part_accumulate(const GemmParams& p, const EpiTile& t, int nb, const float (&f)[32], int warp, int lane) {
+  float v[8];
+  const int sub = 2 * p.gn_hp;
+  const int o = nb % sub;                               // even: nb is a multiple of 32, sub is even
+  if (p.gn_hp == 5) {
+    switch (o) {
+      case 0: gn_piece_sums<5, 5>(f, t.row_ok, v); break;
+      case 2: gn_piece_sums<4, 5>(f, t.row_ok, v); break;
+      case 4: gn_piece_sums<3, 5>(f, t.row_ok, v); break;
+      case 6: gn_piece_sums<2, 5>(f, t.row_ok, v); break;
+      default: gn_piece_sums<1, 5>(f, t.row_ok, v); break;
+    }
+  } else {
+    gn_piece_sums<4, 4>(f, t.row_ok, v);                // sub = 8 divides 32: o == 0 always
+  }
+  // recursive halving over the 32 lanes (rows): 8 -> 4 -> 2 -> 1 values per lane, then a two-step butterfly
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    const float send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  // lane bits (4, 3, 2) select which of the 8 numbers this lane ended up with: idx = 4*b4 + 2*b3 + b2  (0..3 sums, 4..7 sums of squares)
+  if ((lane & 3) == 0) {
+    const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const long long rb = (long long)t.m_tile * 4 + (warp & 3);
+    float* dst = reinterpret_cast<float*>(p.gn_part + (rb * p.gn_nchunks + (nb >> 5)) * 4);
+    dst[(idx & 3) * 2 + (idx >> 2)] = v[0];
   }
 }
 
@@ -381,6 +462,7 @@ __device__ __forceinline__ void gemm_epilogue_loop(const GemmParams& p, int tile
             }
             if (cur.row_ok) p.ln_part[(long long)(nb >> 5) * p.ln_rows + cur.orow] = make_float2(s2.x + s2.y, q2.x + q2.y);
           }
+          if (p.gn_part) gn_part_accumulate(p, cur, nb, f, warp, lane);
           epi_store32(p, cur, nb, p.N, f, p.res != nullptr && !vec, stage, lane);
         }
       }

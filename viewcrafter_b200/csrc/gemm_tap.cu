@@ -337,6 +337,10 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
                             (reinterpret_cast<uintptr_t>(d.ln_part) & 7) == 0),
              "gemm_tap: LayerNorm partial sums need a plain fp16 [M,N] output with N %% 32 == 0");
   p.ln_part = reinterpret_cast<float2*>(d.ln_part); p.ln_rows = d.X;
+  VC_REQUIRE(!d.gn_part || ((d.gn_sub == 10 || d.gn_sub == 8) && d.N % 32 == 0 && d.N % d.gn_sub == 0 && !d.geglu && d.out && !d.out_f32 &&
+                            (reinterpret_cast<uintptr_t>(d.gn_part) & 7) == 0),
+             "gemm_tap: GroupNorm partial sums need an fp16 output with N %% 32 == 0 and N %% gn_sub == 0 (gn_sub 10 or 8)");
+  p.gn_part = reinterpret_cast<float2*>(d.gn_part); p.gn_hp = d.gn_sub / 2; p.gn_nchunks = d.N / 32;
   // 256-bit epilogue accesses need 32-byte aligned rows (true for every activation on the U-Net / VAE path); anything
   // else (odd pitches, the 4- and 3-channel output convs) takes the predicated scalar path inside the kernel
   const bool o_al = ((reinterpret_cast<uintptr_t>(optr) & 31) == 0) && ((long long)d.ldo * esz) % 32 == 0;

@@ -33,6 +33,12 @@ struct GemmDesc {
   // LayerNorm statistics of the OUTPUT, gathered in the epilogue: ln_part[(n / 32) * X + row] = (sum, sumsq) over the 32 output
   // columns [n, n + 32) of the row, of the fp16-rounded values; layernorm_stats_from_parts turns them into (mean, rstd)
   float* ln_part = nullptr;
+  // GroupNorm statistics of the OUTPUT, gathered in the epilogue (gemm_common.cuh: gn_part_accumulate): per 32-row block
+  // rb = m_tile * 4 + quadrant (m-tiles in x, y, z order; CTA pairs pad the m-tile count to an even number), 32-column chunk and piece,
+  // gn_part[((rb * (N / 32) + chunk) * 4 + piece) * 2] = (sum, sumsq) of the fp16-rounded outputs; chunks are cut at multiples of
+  // gn_sub channels (10 or 8).  groupnorm_from_parts() turns them into per-group statistics and normalises in ONE pass.
+  float* gn_part = nullptr;
+  int gn_sub = 0;
 };
 int gemm_tap(const GemmDesc& d, cudaStream_t stream);
 
@@ -64,6 +70,20 @@ int groupnorm_stats(const __half* x1, int C1, const __half* x2, int C2, int samp
 int groupnorm_apply(const __half* x1, int C1, const __half* x2, int C2, int samples, long long rows_per_sample,
                     const float* stats, long long stat_rows, const float* gamma, const float* beta, float eps, int silu, __half* out,
                     cudaStream_t stream, int stat_parts = 1);
+
+// GroupNorm(32) (+SiLU) whose statistics come from the gn_part records of the GEMM(s) that produced x1 (and x2): no statistics pass.
+struct GnPartGeom {
+  const float* part = nullptr;   // [n_rb][n_chunks][4][2]
+  int n_chunks = 0;              // producer N / 32
+  int sub = 10;                  // sub-group width the producer cut its chunks at
+  long long rb_per_z = 0;        // 32-row blocks per producer slab; sample s starts at block (s / samples_per_z) * rb_per_z + (s % samples_per_z) * rb_per_sample
+  int samples_per_z = 1;
+  long long rb_per_sample = 0;
+};
+size_t groupnorm_parts_ws_bytes(int samples);
+int groupnorm_from_parts(const __half* x1, int C1, const GnPartGeom& g1, const __half* x2, int C2, const GnPartGeom& g2, int samples,
+                         long long rows_per_sample, const float* gamma, const float* beta, float eps, int silu, __half* out, float* ws,
+                         size_t ws_bytes, cudaStream_t stream);
 
 int layernorm_stats(const __half* x, long long rows, int C, float eps, float* stats, cudaStream_t stream);
 int layernorm_stats_from_parts(const float* parts, long long rows, int C, float eps, float* stats, cudaStream_t stream);

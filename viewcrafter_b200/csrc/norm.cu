@@ -334,6 +334,117 @@ int groupnorm_apply(const __half* x1, int C1, const __half* x2, int C2, int samp
 }
 
 // ------------------------------------------------------------------------------------------------
+// GroupNorm from the partial sums the producing GEMM left behind (GemmDesc::gn_part, gemm_common.cuh: gn_part_accumulate):
+// the statistics pass over the activation disappears -- a small kernel folds the per-(32-row block, chunk, piece) records
+// (1.6 % of the activation's bytes) into per-(sample, split, group) sums in a fixed order, and gn_apply_kernel normalises in
+// one read + one write.  Reference semantics as above (basics.py:76-87, openaimodel3d.py:256-265).
+struct GnFin {
+  const float2* part;
+  int cols;               // n_chunks * 4 records per 32-row block
+  int sub;
+  long long rb_per_z, rb_per_sample;
+  int spz;
+  int cg, c_off, C_src;   // consumer group width, channel offset of this source in the concat, channels of this source
+  int lanes;              // row-block lanes per CTA (blockDim.x == cols * lanes)
+  int nsplit, split_off, total_splits;
+};
+__global__ void __launch_bounds__(1024) gn_part_finalize_kernel(GnFin f, float* __restrict__ records) {
+  __shared__ float2 red[1024];
+  const int tid = threadIdx.x, split = blockIdx.x, s = blockIdx.y;
+  const int col = tid % f.cols, ln = tid / f.cols;
+  const long long per = (f.rb_per_sample + f.nsplit - 1) / f.nsplit;
+  const long long r0 = (long long)split * per, r1 = min(f.rb_per_sample, r0 + per);
+  const long long base = (long long)(s / f.spz) * f.rb_per_z + (long long)(s % f.spz) * f.rb_per_sample;
+  float sum = 0.f, sq = 0.f;
+  const float2* p = f.part + (base + r0 + ln) * f.cols + col;
+  const long long step = (long long)f.lanes * f.cols;
+  long long rb = r0 + ln;
+  for (; rb + 3 * f.lanes < r1; rb += 4 * f.lanes, p += 4 * step) {      // 4 independent loads in flight
+    const float2 a = __ldg(p), b = __ldg(p + step), c = __ldg(p + 2 * step), d = __ldg(p + 3 * step);
+    sum += a.x; sq += a.y; sum += b.x; sq += b.y; sum += c.x; sq += c.y; sum += d.x; sq += d.y;
+  }
+  for (; rb < r1; rb += f.lanes, p += step) {
+    const float2 a = __ldg(p);
+    sum += a.x; sq += a.y;
+  }
+  red[tid] = make_float2(sum, sq);
+  __syncthreads();
+  if (tid < f.cols) {
+    float2 acc = red[tid];
+    for (int l = 1; l < f.lanes; ++l) { const float2 o = red[l * f.cols + tid]; acc.x += o.x; acc.y += o.y; }
+    red[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int grp = tid >> 1, which = tid & 1;
+    float acc = 0.f;
+    for (int c = 0; c < f.cols; ++c) {
+      const int ch = (((c >> 2) * 32) / f.sub + (c & 3)) * f.sub;      // first channel of the sub-group this record belongs to
+      if (ch < f.C_src && (f.c_off + ch) / f.cg == grp) acc += which ? red[c].y : red[c].x;
+    }
+    records[((long long)s * f.total_splits + f.split_off + split) * 64 + tid] = acc;
+  }
+}
+
+static constexpr int GN_PART_MAX_SPLITS = 64;          // per source
+size_t groupnorm_parts_ws_bytes(int samples) { return (size_t)samples * 2 * GN_PART_MAX_SPLITS * 64 * sizeof(float); }
+
+static int gn_part_plan(const GnPartGeom& g, int C_src, int samples, GnFin& f) {
+  VC_REQUIRE(g.part && g.n_chunks * 32 == C_src && (g.sub == 10 || g.sub == 8) && g.rb_per_sample >= 1 && g.samples_per_z >= 1 &&
+             g.rb_per_z >= (long long)g.samples_per_z * g.rb_per_sample, "groupnorm_from_parts: bad partial-sum geometry");
+  f.part = reinterpret_cast<const float2*>(g.part);
+  f.cols = g.n_chunks * 4; f.sub = g.sub;
+  f.rb_per_z = g.rb_per_z; f.rb_per_sample = g.rb_per_sample; f.spz = g.samples_per_z;
+  f.C_src = C_src;
+  VC_REQUIRE(f.cols <= 1024, "groupnorm_from_parts: too many channels");
+  f.lanes = 256 / f.cols > 0 ? 256 / f.cols : 1;
+  int nsplit = (2 * sm_count() + samples - 1) / samples;
+  const long long max_useful = (g.rb_per_sample + 4 * f.lanes - 1) / (4 * f.lanes);
+  if (nsplit > max_useful) nsplit = (int)max_useful;
+  if (nsplit > GN_PART_MAX_SPLITS) nsplit = GN_PART_MAX_SPLITS;
+  if (nsplit < 1) nsplit = 1;
+  f.nsplit = nsplit;
+  return VC_OK;
+}
+
+int groupnorm_from_parts(const __half* x1, int C1, const GnPartGeom& g1, const __half* x2, int C2, const GnPartGeom& g2, int samples,
+                         long long rows_per_sample, const float* gamma, const float* beta, float eps, int silu, __half* out, float* ws,
+                         size_t ws_bytes, cudaStream_t stream) {
+  VC_REQUIRE(out && gamma && beta && ws, "groupnorm_from_parts: null pointer");
+  GnGeom g;
+  int rc = gn_geometry(g, x1, C1, x2, C2, samples, rows_per_sample);
+  if (rc) return rc;
+  VC_REQUIRE(ws_bytes >= groupnorm_parts_ws_bytes(samples), "groupnorm_from_parts: workspace too small");
+  GnFin f1, f2;
+  rc = gn_part_plan(g1, C1, samples, f1);
+  if (rc) return rc;
+  f1.cg = g.cg; f1.c_off = 0; f1.split_off = 0;
+  VC_REQUIRE(g.cg % g1.sub == 0, "groupnorm_from_parts: group width %d is not a multiple of the sub-group width %d", g.cg, g1.sub);
+  int total = f1.nsplit;
+  if (x2) {
+    rc = gn_part_plan(g2, C2, samples, f2);
+    if (rc) return rc;
+    VC_REQUIRE(g.cg % g2.sub == 0 && C1 % g2.sub == 0, "groupnorm_from_parts: concat boundary %d / group width %d vs sub-group width %d", C1, g.cg, g2.sub);
+    f2.cg = g.cg; f2.c_off = C1; f2.split_off = f1.nsplit;
+    total += f2.nsplit;
+  }
+  f1.total_splits = total;
+  gn_part_finalize_kernel<<<dim3(f1.nsplit, samples), f1.cols * f1.lanes, 0, stream>>>(f1, ws);
+  VC_CHECK_CUDA(cudaGetLastError());
+  if (x2) {
+    f2.total_splits = total;
+    gn_part_finalize_kernel<<<dim3(f2.nsplit, samples), f2.cols * f2.lanes, 0, stream>>>(f2, ws);
+    VC_CHECK_CUDA(cudaGetLastError());
+  }
+  g.stat_splits = total;
+  g.stat_rows = rows_per_sample;
+  dim3 grid(g.splits, samples);
+  gn_apply_kernel<<<grid, g.vecs * g.ppi, 0, stream>>>(x1, x2, g, ws, gamma, beta, eps, silu, out);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Persistent warps: each warp walks rows with a grid stride and keeps TWO rows in flight (all their 16-byte loads are
 // issued before the first reduction) so the DRAM latency is covered by memory-level parallelism, not by block churn.
 template <int MAXV>

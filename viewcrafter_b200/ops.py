@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import AttnDesc, DdimScalars, GemmDesc, check
+from ._lib import AttnDesc, DdimScalars, GemmDesc, GnPartGeom, check
 
 
 def _stream() -> int:
@@ -145,15 +145,71 @@ def _gemm(desc: GemmDesc):
 
 
 LN_FROM_PRODUCER = os.environ.get("VC_LN_FROM_PRODUCER", "1") != "0"   # A/B switch: LayerNorm statistics from the producing GEMM's epilogue
+# GroupNorm statistics from the producing GEMM's epilogue (GemmDesc.gn_part): 0 = off (statistics pass inside the GroupNorm kernel),
+# 1 = producers with a long reduction only (3x3 / temporal / stride-2 convs: the extra epilogue work hides under the MMAs), 2 = every producer
+GN_FROM_PRODUCER = int(os.environ.get("VC_GN_FROM_PRODUCER", "1"))
+GN_SUB = 10          # sub-group width the U-Net producers cut their chunks at: every GroupNorm(32) boundary of 320 / 640 / 1280 channels
+                     # and of their skip concats (640 / 960 / 1280 / 1920 / 2560) is a multiple of 10
+
+
+class GnPart:
+    """The (sum, sumsq) records a GEMM left for the GroupNorm that reads its output: [n_rb, C/32, 4, 2] fp32 over 32-row blocks in
+    m-tile order.  `rb_per_z` blocks per producer slab (frame for the 3x3 convs, batch element for the temporal convs, everything
+    for a linear); `rows_per_z` valid rows per slab; `row_blocks_linear`: block b of a slab holds the rows [32 b, 32 b + 32) of it."""
+    __slots__ = ("part", "n_chunks", "sub", "rb_per_z", "rows_per_z", "slabs", "linear")
+
+    def __init__(self, part, n_chunks, sub, rb_per_z, rows_per_z, slabs, linear):
+        self.part, self.n_chunks, self.sub, self.rb_per_z, self.rows_per_z, self.slabs, self.linear = part, n_chunks, sub, rb_per_z, rows_per_z, slabs, linear
+
+    def geom(self, samples: int, rows_per_sample: int):
+        """ctypes geometry for a consumer with `samples` x `rows_per_sample` rows, or None if its samples do not fall on block boundaries."""
+        g = GnPartGeom()
+        g.part, g.n_chunks, g.sub = self.part.data_ptr(), self.n_chunks, self.sub
+        total = self.slabs * self.rows_per_z
+        if samples * rows_per_sample != total:
+            return None
+        if rows_per_sample % self.rows_per_z == 0:               # a sample = k whole slabs (k = 1: 4-D GroupNorm after a conv; k = T: 5-D)
+            k = rows_per_sample // self.rows_per_z
+            g.rb_per_z, g.samples_per_z, g.rb_per_sample = k * self.rb_per_z, 1, k * self.rb_per_z
+            return g
+        if self.linear and self.rows_per_z % rows_per_sample == 0 and rows_per_sample % 32 == 0:   # several samples per slab
+            g.rb_per_z, g.samples_per_z, g.rb_per_sample = self.rb_per_z, self.rows_per_z // rows_per_sample, rows_per_sample // 32
+            return g
+        return None
+
+
+def _gn_part_alloc(d: GemmDesc, device):
+    """Allocate the record buffer for the GEMM described by d and hook it up; returns the GnPart (or None if N does not qualify)."""
+    N = d.N
+    if N % 32 != 0 or N % GN_SUB != 0 or d.geglu or not d.out:
+        return None
+    tx, ty = -(-d.X // d.bx), -(-d.Y // d.by)
+    m_tiles = tx * ty * d.Z
+    n_rb = (m_tiles + 1) // 2 * 2 * 4                           # CTA pairs touch an even number of m-tiles
+    part = torch.empty((n_rb, N // 32, 4, 2), device=device, dtype=torch.float32)
+    d.gn_part, d.gn_sub = part.data_ptr(), GN_SUB
+    return GnPart(part, N // 32, GN_SUB, tx * ty * 4, d.X * d.Y, d.Z, linear=(d.by == 1 and d.bx == 128 and (d.Y == 1 or d.X % 128 == 0)))
+
+
+def _want_gn(gn_out: bool, k_iters: int) -> bool:
+    return bool(gn_out) and (GN_FROM_PRODUCER >= 2 or (GN_FROM_PRODUCER == 1 and k_iters >= 12))
+
+
+def gn_part_of(t):
+    return getattr(t, "_vc_gn", None)
+
+
+gn_from_parts_calls = 0      # GroupNorms that took their statistics from a producer's partial sums (introspection / tests)
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
            geglu: bool = False, out: Optional[torch.Tensor] = None, out_f32: bool = False,
-           x2: Optional[torch.Tensor] = None, ln=None, ln_out: bool = False):
+           x2: Optional[torch.Tensor] = None, ln=None, ln_out: bool = False, gn_out: bool = False):
     """y = [x|x2] @ w.T (+bias) (GEGLU) (+res).  x: [M,K1] fp16 (row pitch = x.stride(0)), w: [N,K] fp16.
     ln = (stats [M,2] fp32 from layernorm_stats(x), colsum [N] fp32): LayerNorm folded into the epilogue (fold_layernorm).
     ln_out: also return the LayerNorm statistics [M,2] (mean, rstd) of y -- y feeds a LayerNorm next (attention.py:283-292); the
-    epilogue leaves per-32-column partial sums of the rows it is writing and a tiny kernel finishes them, so y is not re-read."""
+    epilogue leaves per-32-column partial sums of the rows it is writing and a tiny kernel finishes them, so y is not re-read.
+    gn_out: y feeds a GroupNorm next: leave its partial sums (GnPart, attached to y as ``y._vc_gn``; see groupnorm())."""
     _chk16(x, "linear.x"); _chk16(w, "linear.w")
     M, K1 = x.shape
     N, K = w.shape
@@ -184,6 +240,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         assert stats.shape == (M, 2) and stats.dtype == torch.float32 and stats.is_contiguous()
         assert colsum.shape == (N,) and colsum.dtype == torch.float32 and colsum.is_contiguous()
         d.ln_stats, d.ln_colsum = stats.data_ptr(), colsum.data_ptr()
+    out._vc_gn = _gn_part_alloc(d, x.device) if (_want_gn(gn_out, -(-K // 64)) and not out_f32 and not geglu and out.is_contiguous()) else None
     if not ln_out:
         _gemm(d)
         return out
@@ -209,8 +266,8 @@ def _conv_box(H: int, W: int):
 
 def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w9: torch.Tensor, bias: Optional[torch.Tensor] = None,
             res: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None, bias_z_div: int = 0,
-            out_f32: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """3x3 / stride 1 / pad 1 convolution on [frames*H*W, Cin] rows; w9 = pack_conv3x3(weight)."""
+            out_f32: bool = False, out: Optional[torch.Tensor] = None, gn_out: bool = False) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution on [frames*H*W, Cin] rows; w9 = pack_conv3x3(weight).  gn_out: see linear()."""
     _chk16(x, "conv3x3.x"); _chk16(w9, "conv3x3.w")
     M, K1 = x.shape
     assert M == frames * H * W, (M, frames, H, W)
@@ -239,6 +296,7 @@ def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w9: torch.Tensor, bias
     d.bias, d.bias_z_div = _ptr(bias), bias_z_div
     if res is not None:
         d.res, d.ldr = res.data_ptr(), res.stride(0)
+    out._vc_gn = _gn_part_alloc(d, x.device) if (_want_gn(gn_out, 9 * -(-K // 64)) and not out_f32 and out.is_contiguous()) else None
     _gemm(d)
     return out
 
@@ -299,8 +357,8 @@ def upconv3x3(x: torch.Tensor, frames: int, H: int, W: int, packs, bias: Optiona
 
 
 def conv_temporal(x: torch.Tensor, B: int, T: int, HW: int, w3: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                  res: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Conv3d (3,1,1) pad (1,0,0) on [(B T) HW, C] rows: three row-shifted GEMM taps; batches never mix (Z = B)."""
+                  res: Optional[torch.Tensor] = None, gn_out: bool = False) -> torch.Tensor:
+    """Conv3d (3,1,1) pad (1,0,0) on [(B T) HW, C] rows: three row-shifted GEMM taps; batches never mix (Z = B).  gn_out: see linear()."""
     _chk16(x, "conv_temporal.x")
     M, K = x.shape
     assert M == B * T * HW
@@ -317,6 +375,7 @@ def conv_temporal(x: torch.Tensor, B: int, T: int, HW: int, w3: torch.Tensor, bi
     d.bias = _ptr(bias)
     if res is not None:
         d.res, d.ldr = res.data_ptr(), res.stride(0)
+    out._vc_gn = _gn_part_alloc(d, x.device) if _want_gn(gn_out, 3 * -(-K // 64)) else None
     _gemm(d)
     return out
 
@@ -372,12 +431,32 @@ def _gn_workspace(device, samples: int) -> torch.Tensor:
 
 def groupnorm(x: torch.Tensor, samples: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
               x2: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm(32) (+SiLU) over ``samples`` groups of rows; [x|x2] concatenated along channels."""
+    """GroupNorm(32) (+SiLU) over ``samples`` groups of rows; [x|x2] concatenated along channels.  When the GEMMs that produced x
+    (and x2) left their partial sums (``_vc_gn``, see linear(gn_out=True)) the statistics pass is skipped: one read + one write."""
     _chk16(x, "groupnorm.x")
     rows, C1 = x.shape
     C2 = 0 if x2 is None else x2.shape[1]
     assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
     out = torch.empty((rows, C1 + C2), device=x.device, dtype=torch.float16)
+    p1, p2 = gn_part_of(x), (gn_part_of(x2) if x2 is not None else None)
+    if p1 is not None and (x2 is None or p2 is not None):
+        cg = (C1 + C2) // 32
+        g1 = p1.geom(samples, rows // samples)
+        g2 = p2.geom(samples, rows // samples) if x2 is not None else None
+        if g1 is not None and (x2 is None or g2 is not None) and cg % p1.sub == 0 and (x2 is None or (cg % p2.sub == 0 and C1 % p2.sub == 0)):
+            lib = _lib.load()
+            need = lib.vc_groupnorm_parts_ws_bytes(samples)
+            key = (x.device, torch.cuda.current_stream().cuda_stream, "parts")
+            ws = _gn_ws.get(key)
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(max(need, 1 << 20), device=x.device, dtype=torch.uint8)
+                _gn_ws[key] = ws
+            global gn_from_parts_calls
+            gn_from_parts_calls += 1
+            check(lib.vc_groupnorm_from_parts(x.data_ptr(), C1, C.byref(g1), _ptr(x2), C2, C.byref(g2) if g2 is not None else None, samples,
+                                              rows // samples, gamma.data_ptr(), beta.data_ptr(), eps, int(silu), out.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _stream()), "vc_groupnorm_from_parts")
+            return out
     ws = _gn_workspace(x.device, samples)
     check(_lib.load().vc_groupnorm_nhwc(x.data_ptr(), C1, _ptr(x2), C2, samples, rows // samples, gamma.data_ptr(), beta.data_ptr(),
                                         eps, int(silu), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "vc_groupnorm_nhwc")

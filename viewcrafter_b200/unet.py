@@ -364,20 +364,20 @@ class UNetModel(nn.Module):
         BT, HW = B * T, H * W
         a = ops.groupnorm(h, BT, *P["gn1"], 1e-5, True, x2=skip)
         bias1 = ops.small_linear(emb, P["emb_w"], P["emb_b"], silu_in=True)            # [B, Cout] = emb_layers + conv1 bias
-        h1 = ops.conv3x3(a, BT, H, W, P["w1"], bias=bias1, bias_z_div=T)
+        h1 = ops.conv3x3(a, BT, H, W, P["w1"], bias=bias1, bias_z_div=T, gn_out=True)      # gn_out: the epilogue leaves the GroupNorm sums of its output
         b = ops.groupnorm(h1, BT, *P["gn2"], 1e-5, True)
         if "skip_w" in P:
             xs = ops.linear(h, P["skip_w"], bias=P["skip_b"], x2=skip)
         else:
             xs = h
-        h2 = ops.conv3x3(b, BT, H, W, P["w2"], bias=P["b2"], res=xs)
+        h2 = ops.conv3x3(b, BT, H, W, P["w2"], bias=P["b2"], res=xs, gn_out=True)
         if "tconv" in P:
             # TemporalConvBlock: needs every frame of a pixel -> (optionally) transpose frames<->sites across GPUs
             t = ident = comm.to_sites(h2, B, HW) if comm else h2
             Tg, HWl = (comm.T, HW // comm.world) if comm else (T, HW)
             for i, (g, be, w3, b3) in enumerate(P["tconv"]):
                 t = UNetModel._gn5d(t, B, g, be, 1e-5, True, comm, Tg * HW, fresh=(i == 0))   # statistics over (C/32, T, H, W)
-                t = ops.conv_temporal(t, B, Tg, HWl, w3, bias=b3, res=ident if i == 3 else None)
+                t = ops.conv_temporal(t, B, Tg, HWl, w3, bias=b3, res=ident if i == 3 else None, gn_out=comm is None)
             h2 = comm.to_frames(t, B, HW) if comm else t
         return h2
 
@@ -427,7 +427,7 @@ class UNetModel(nn.Module):
             last = Q is P["blocks"][-1]
             x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x, ln_out=fold and not last)
             x, st = x if (fold and not last) else (x, None)
-        return ops.linear(x, P["out_w"], bias=P["out_b"], res=h)
+        return ops.linear(x, P["out_w"], bias=P["out_b"], res=h, gn_out=True)
 
     @staticmethod
     def _temporal_tf(P, h, B, T, H, W, comm=None):
@@ -451,7 +451,7 @@ class UNetModel(nn.Module):
             last = Q is P["blocks"][-1]
             x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x, ln_out=fold and not last)
             x, st = x if (fold and not last) else (x, None)
-        out = ops.linear(x, P["out_w"], bias=P["out_b"], res=t_in)
+        out = ops.linear(x, P["out_w"], bias=P["out_b"], res=t_in, gn_out=comm is None)
         return comm.to_frames(out, B, HW) if comm else out
 
     def _run_stage(self, stage, h, skip, emb, ctx, B, T, H, W):
@@ -466,12 +466,12 @@ class UNetModel(nn.Module):
                 h = self._temporal_tf(P, h, B, T, H, W, self._comm)
             elif k == "D":
                 cols, H, W = ops.im2col_s2(h, B * T, H, W)
-                h = ops.linear(cols, P["w"], bias=P["b"])
+                h = ops.linear(cols, P["w"], bias=P["b"], gn_out=True)
             elif k == "U":
                 h = ops.upconv3x3(h, B * T, H, W, P["w"], bias=P["b"])      # upsample folded into four parity sub-convolutions
                 H, W = 2 * H, 2 * W
             elif k == "C":
-                h = ops.conv3x3(h, B * T, H, W, P["w"], bias=P["b"])
+                h = ops.conv3x3(h, B * T, H, W, P["w"], bias=P["b"], gn_out=True)
         return h, H, W
 
     def _canonical_context(self, context: torch.Tensor) -> torch.Tensor:
