@@ -408,6 +408,18 @@ def main():
         comm.bytes_moved = 0
         y_sh = unet_m(xc, t499, context=dev["ctx_c"], fs=fs)
         comm.bytes_per_forward = comm.bytes_moved
+        # exposed communication: the exchanges run in-stream, so their device time (transfer + waiting for the slowest peer) is not
+        # overlapped with compute; measured over one more eager forward with CUDA events around every exchange / statistics call
+        torch.cuda.synchronize(); dist.barrier()
+        comm.profile(True)
+        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fe0.record()
+        unet_m(xc, t499, context=dev["ctx_c"], fs=fs)
+        fe1.record()
+        comm.exposed_ms = comm.profile_ms()
+        comm.forward_ms = fe0.elapsed_time(fe1)
+        comm.n_exchanges = len(comm._prof)
+        comm.profile(False)
         unet_m._comm = None
         y_1 = unet_m(xc, t499, context=dev["ctx_c"], fs=fs)
         unet_m._comm = comm
@@ -470,6 +482,11 @@ def main():
                      "impl": ("NVLink peer-memory exchange kernels (csrc/peer.cu), GroupNorm statistics fused into the frames->sites switch"
                               if isinstance(comm, _par.PeerFrameComm) else ("NCCL all_to_all_single + all_reduce" if comm is not None else "none (CFG split only)")),
                      "bytes_sent_per_forward_rank0": None if comm is None else int(getattr(comm, "bytes_per_forward", 0)),
+                     "bytes_per_step": None if comm is None else int(getattr(comm, "bytes_per_forward", 0)) + int(dev["x_T"].numel() * 4),
+                     "exposed_ms": None if comm is None else {"per_forward_rank0": getattr(comm, "exposed_ms", None), "eager_forward_ms": getattr(comm, "forward_ms", None),
+                                                               "exchanges": getattr(comm, "n_exchanges", None),
+                                                               "what": "device time of the in-stream exchange / statistics kernels of ONE eager forward on rank 0 "
+                                                                       "(transfer + waiting for the slowest peer): not overlapped with compute"},
                      "cfg_exchange_bytes_per_step": int(dev["x_T"].numel() * 4) if world % 2 == 0 else 0}
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)

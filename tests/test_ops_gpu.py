@@ -448,6 +448,7 @@ def _gn_ref(y, samples, g, b, eps, silu):
 
 def _force_gn_parts(ops, monkeypatch, mode=2):
     monkeypatch.setattr(ops, "GN_FROM_PRODUCER", mode)
+    monkeypatch.setattr(ops, "GN_PARTS_MIN_MB", 0.0)
 
 
 @pytest.mark.parametrize("frames,H,W,Ci,Co", [(3, 9, 16, 64, 320), (2, 18, 32, 320, 640), (2, 36, 64, 128, 320), (3, 72, 128, 64, 320),

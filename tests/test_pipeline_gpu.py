@@ -186,3 +186,63 @@ def test_resampler_matches_reference_golden_and_oracle(golden_dir):
     err = (y.cpu() - ref).abs()
     print(f"resampler full: max err {float(err.max()):.4g} mean {float(err.mean()):.4g} ref std {float(ref.std()):.3g}")
     assert y.shape == (1, 256, 1024) and float(err.max()) <= 0.04 and float(err.mean()) <= 0.004
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_image_guided_synthesis_on_gpu_vs_oracle(multi):
+    """The caller of the hot path on the GPU: viewcrafter_b200.synthesis.image_guided_synthesis
+    (utils/diffusion_utils.py:117-201) with the CUDA VAE encode -> CFG DDIM loop (graph replay on) -> VAE decode, 2-way and 3-way CFG,
+    n_samples = 2, against the fp32 CPU oracle fed the same draws (posterior noise on the CPU generator per frame, x_T and the
+    per-step noise on the CUDA generator, in the reference's order).  Bound: mean |err| <= 5 % of the image std (two CFG steps
+    amplify the fp16 U-Net error ~16x each, then the decoder maps it to pixels)."""
+    _need_gpu()
+    from oracle import lvdm_oracle as O
+    from oracle import synth
+    from viewcrafter_b200.configs import UNET_PARAMS, VAE_DDCONFIG
+    from viewcrafter_b200.diffusion import LatentDiffusion
+    from viewcrafter_b200.synthesis import image_guided_synthesis
+    model = LatentDiffusion(dict(UNET_PARAMS, model_channels=64), dict(ddconfig=dict(VAE_DDCONFIG, ch=32), embed_dim=4), base_scale=0.7).eval()
+    sd = synth.synth_state_dict(synth.module_shapes(model.model.diffusion_model), seed=71)
+    model.model.diffusion_model.load_state_dict(sd, strict=True)
+    sdv = synth.synth_state_dict(synth.module_shapes(model.first_stage_model), seed=72)
+    model.first_stage_model.load_state_dict(sdv, strict=True)
+    model = model.cuda()
+    g = torch.Generator().manual_seed(73)
+    W_img, txt, txt_empty = torch.randn(3 * 4 * 4, 256 * 8, generator=g) * 0.1, torch.randn(1, 77, 1024, generator=g), torch.randn(1, 77, 1024, generator=g)
+    W_d, txt_d, txt_empty_d = W_img.cuda(), txt.cuda(), txt_empty.cuda()
+    model.embedder = lambda img: torch.nn.functional.adaptive_avg_pool2d(img, 4).reshape(img.shape[0], 1, -1)
+    model.image_proj_model = lambda e: (e @ (W_d if e.is_cuda else W_img)).reshape(e.shape[0], 256, 8).repeat(1, 1, 128)
+    model.get_learned_conditioning = lambda prompts: torch.cat([txt_empty_d if p == "" else txt_d for p in prompts], 0)
+    model.uncond_type = "empty_seq"
+    T, H, W, S, n_samples = 3, 8, 8, 2, 2
+    videos = torch.rand(1, 3, T, 8 * H, 8 * W, generator=g) * 2 - 1
+    shape = (1, 4, T, H, W)
+    torch.manual_seed(74)
+    out = image_guided_synthesis(model, ["a photo"], videos.cuda(), list(shape), n_samples=n_samples, ddim_steps=S, ddim_eta=1.0,
+                                 unconditional_guidance_scale=7.5, cfg_img=(2.0 if multi else None), fs=10, text_input=True,
+                                 multiple_cond_cfg=multi, timestep_spacing="uniform_trailing", guidance_rescale=0.7, condition_index=[0])
+    assert out.shape == (1, n_samples, 3, T, 8 * H, 8 * W) and out.is_cuda
+    torch.manual_seed(74)
+    enc_noise = [torch.randn(1, 4, H, W) for _ in range(T)]
+    img = videos[:, :, 0]
+    ctx = lambda t, im: torch.cat([t, model.image_proj_model(model.embedder(im))], 1)
+    ctx_c, ctx_u, ctx_i = ctx(txt, img), ctx(txt_empty, torch.zeros_like(img)), ctx(txt_empty, img)
+    fs = torch.tensor([10])
+    with torch.no_grad():
+        cc = O.encode_first_stage(sdv, videos, enc_noise)
+    sched = O.model_schedule(base_scale=0.7)
+
+    def model_fn(x, t, cond):
+        with torch.no_grad():
+            return O.unet_forward(sd, torch.cat([x, cc], 1), t, cond, fs)
+
+    for k in range(n_samples):
+        x_T = torch.randn(shape, device="cuda").cpu()
+        noises = [torch.randn(shape, device="cuda").cpu() for _ in range(S)]
+        extra = dict(fixed_prev_scale=False, uncond_img=ctx_i, cfg_img=2.0) if multi else {}
+        ref, _ = O.ddim_sample(model_fn, sched, shape, S, ctx_c, ctx_u, x_T, noises, **extra)
+        with torch.no_grad():
+            ref_img = O.decode_first_stage(sdv, ref)
+        err = (out[:, k].cpu() - ref_img).abs()
+        print(f"synthesis multi={multi} sample {k}: mean err {float(err.mean()):.4g} max {float(err.max()):.4g} ref std {float(ref_img.std()):.3g}")
+        assert float(err.mean()) < 0.05 * max(1.0, float(ref_img.std())), (k, float(err.mean()), float(ref_img.std()))

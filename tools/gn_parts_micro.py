@@ -7,6 +7,7 @@ import torch
 from viewcrafter_b200 import ops
 
 ops.GN_FROM_PRODUCER = 2
+ops.GN_PARTS_MIN_MB = 0.0
 
 
 def t(fn, reps=5):

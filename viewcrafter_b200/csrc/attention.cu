@@ -405,7 +405,10 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
 // two groups are half a tile apart BY CONSTRUCTION: while one is in its exponentials the other loads, reduces and stores.
 // K and V tiles are loaded once (4-stage TMA rings each) instead of once per co-resident CTA.  At the end the two partial
 // results of a row are merged like split-KV attention: O = (2^(m0-m) O0 + 2^(m1-m) O1) / (2^(m0-m) l0 + 2^(m1-m) l1).
-// Warp roles (320 threads): warp0 TMA, warp1 TMEM alloc + MMA issue, warps 2-5 softmax group 0, warps 6-9 softmax group 1.
+// Warp roles (384 threads = 3 warpgroups): warpgroup 0 = warp0 TMA, warp1 TMEM alloc + MMA issue, warps 2-3 idle; warpgroup 1 (warps 4-7)
+// softmax group 0, warpgroup 2 (warps 8-11) softmax group 1.  Registers are allocated per warpgroup: 384 threads get 168 each at
+// launch (a 320-thread CTA is charged for 12 warps too: 192 registers x 10 warps was refused as "too many resources"); the role
+// warpgroup gives its share back (setmaxnreg.dec 40) and the two softmax warpgroups grow to 224 (128 x 40 + 256 x 224 = 62464 <= 64 K).
 // ---------------------------------------------------------------------------------------------------------------------
 #ifndef VC_PP_ORDERED
 #define VC_PP_ORDERED 1      // the two groups take turns in the exponential section (named-barrier hand-over); 0 = free-running (A/B)
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
 static constexpr int PP_KS = 4, PP_VS = 4;
 static constexpr int PP_SMEM = ATT_TILE_BYTES * (1 + PP_KS + PP_VS) + 1024 + 512 + 2 * 2 * 128 * 4;
 
-__global__ void __maxnreg__(200) flash_attn_d64_pp_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(384, 1) flash_attn_d64_pp_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -456,7 +459,9 @@ __global__ void __maxnreg__(200) flash_attn_d64_pp_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(q_full, ATT_TILE_BYTES);
       tma_load_4d(sQ, &p.tmap_q, q_full, 0, head, q0, b);
@@ -519,8 +524,10 @@ __global__ void __maxnreg__(200) flash_attn_d64_pp_kernel(const __grid_constant_
       }
       __syncwarp();
     }
+   }
   } else {
-    const int wg = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+    const int wg = (warp - 4) >> 2;
     const int qd = warp & 3;
     const int r = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
@@ -730,7 +737,7 @@ int flash_attn_d64(const AttnDesc& d, cudaStream_t stream) {
   static int pp = -1;                         // VC_ATTN_PP=1: the ping-pong kernel (one CTA per SM, two softmax warpgroups on alternate key tiles)
   if (pp < 0) { const char* e = getenv("VC_ATTN_PP"); pp = (e && e[0] == '1') ? 1 : 0; }
   if (pp) {
-    flash_attn_d64_pp_kernel<<<grid, 320, PP_SMEM, stream>>>(p);
+    flash_attn_d64_pp_kernel<<<grid, 384, PP_SMEM, stream>>>(p);
     VC_CHECK_CUDA(cudaGetLastError());
     return VC_OK;
   }

@@ -100,6 +100,24 @@ __device__ __forceinline__ void gn_stats_dev(const __half* __restrict__ x1, cons
   __syncthreads();                                  // red[] may be rewritten by the caller's next use
 }
 
+#ifndef VC_SILU_TANH
+#define VC_SILU_TANH 1       // A/B switch: SiLU through ONE MUFU op (tanh.approx) instead of ex2 + rcp
+#endif
+// x * sigmoid(x) = h + h * tanh(h) with h = x / 2: one MUFU.TANH + 2 FP ops per element instead of MUFU.EX2 + MUFU.RCP + 3.  The
+// normalise pass issues 2 MUFU per element otherwise and is then bound by the 16-per-clock MUFU pipe (41 us for the 74 M elements of
+// a 25x72x128x320 tensor) rather than by HBM.  tanh.approx.f32 has a relative error of 2^-11 on tanh, i.e. an absolute error of
+// <= 2.4e-4 |x| on the result -- the size of the fp16 rounding the output gets anyway.
+__device__ __forceinline__ float gn_silu(float x) {
+#if VC_SILU_TANH
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+#else
+  return silu_f(x);
+#endif
+}
+
 __device__ __forceinline__ uint4 gn_norm8(const uint4& u, const float (&sc)[8], const float (&sh)[8], int silu) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
   float f[8];
@@ -111,7 +129,7 @@ __device__ __forceinline__ uint4 gn_norm8(const uint4& u, const float (&sc)[8], 
   }
   if (silu) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+    for (int e = 0; e < 8; ++e) f[e] = gn_silu(f[e]);
   }
   uint4 o;
   o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
@@ -152,41 +170,43 @@ __device__ __forceinline__ void gn_apply_dev(const __half* __restrict__ x1, cons
   }
   const GnThread t = gn_thread(x1, x2, g, split, sample, v, pl);
   const long long ostride = (long long)g.ppi * g.C;
-#if VC_GN_REVERSE
-  // Walk the rows BACKWARDS: the statistics pass streamed them forwards, so what the L2 still holds is the tail of every
-  // CTA's slice.  A second forward sweep is the worst case for an LRU-like cache (ncu, C=320 @25x72x128: L2 hit 0.4 %,
-  // 294 MB read from DRAM for a 147 MB tensor); the reverse sweep meets the resident lines first.
-  const __half* p = t.src + (t.n - 1) * t.sstride;
-  __half* o = out + ((long long)sample * g.rows + t.orow0) * g.C + v * 8 + (t.n - 1) * ostride;
-  long long k = t.n;
-  for (; k >= 4; k -= 4, p -= 4 * t.sstride, o -= 4 * ostride) {
-    uint4 u[4];
+  // Walk the rows BACKWARDS (VC_GN_REVERSE): in the fused kernel the statistics pass streamed them forwards, so what the L2 still
+  // holds is the tail of every CTA's slice; a second forward sweep is the worst case for an LRU-like cache (ncu, C=320 @25x72x128:
+  // L2 hit 0.4 %, 294 MB read from DRAM for a 147 MB tensor), the reverse sweep meets the resident lines first.
+  // Software pipeline: the loads of the NEXT four rows are issued before the current four are normalised and stored, so up to eight
+  // 16-byte loads per thread are in flight and the DRAM latency is covered when this pass is the only one (statistics from the
+  // producing GEMM: no L2-resident tail to meet).
+  const long long ds = VC_GN_REVERSE ? -t.sstride : t.sstride, dd = VC_GN_REVERSE ? -ostride : ostride;
+  const __half* p = VC_GN_REVERSE ? t.src + (t.n - 1) * t.sstride : t.src;
+  __half* o = out + ((long long)sample * g.rows + t.orow0) * g.C + v * 8 + (VC_GN_REVERSE ? (t.n - 1) * ostride : 0);
+  long long left = t.n;
+  uint4 cur[4], nxt[4];
+  int ncur = left < 4 ? (int)left : 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) u[i] = *reinterpret_cast<const uint4*>(p - i * t.sstride);
+  for (int i = 0; i < 4; ++i)
+    if (i < ncur) cur[i] = *reinterpret_cast<const uint4*>(p + i * ds);
+  left -= ncur; p += ncur * ds;
+  while (ncur > 0) {
+    const int nn = left < 4 ? (int)left : 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(o - i * ostride) = gn_norm8(u[i], sc, sh, silu);
+    for (int i = 0; i < 4; ++i)
+      if (i < nn) nxt[i] = *reinterpret_cast<const uint4*>(p + i * ds);
+    left -= nn; p += nn * ds;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < ncur) *reinterpret_cast<uint4*>(o + i * dd) = gn_norm8(cur[i], sc, sh, silu);
+    o += ncur * dd;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+    ncur = nn;
   }
-  for (; k > 0; --k, p -= t.sstride, o -= ostride) *reinterpret_cast<uint4*>(o) = gn_norm8(*reinterpret_cast<const uint4*>(p), sc, sh, silu);
-#else
-  const __half* p = t.src;
-  __half* o = out + ((long long)sample * g.rows + t.orow0) * g.C + v * 8;
-  long long k = 0;
-  for (; k + 4 <= t.n; k += 4, p += 4 * t.sstride, o += 4 * ostride) {
-    uint4 u[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) u[i] = *reinterpret_cast<const uint4*>(p + i * t.sstride);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(o + i * ostride) = gn_norm8(u[i], sc, sh, silu);
-  }
-  for (; k < t.n; ++k, p += t.sstride, o += ostride) *reinterpret_cast<uint4*>(o) = gn_norm8(*reinterpret_cast<const uint4*>(p), sc, sh, silu);
-#endif
 }
 
 __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
                                                        float* __restrict__ partial) {
   gn_stats_dev(x1, x2, g, partial, blockIdx.x, blockIdx.y);
 }
-__global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+__global__ void __launch_bounds__(512, 2) gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
                                                        const float* __restrict__ partial, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
   gn_apply_dev(x1, x2, g, partial, gamma, beta, eps, silu, out, blockIdx.x, blockIdx.y);
@@ -194,7 +214,7 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict_
 // Fused single launch: statistics pass, a grid-wide rendezvous of the CTAs of one sample (all CTAs are co-resident by
 // construction -- the host checks the occupancy), then the normalise pass, whose re-read of x is served by the 126 MB L2
 // for everything but the largest 5-D tensors: HBM traffic drops from 3 passes to ~2.
-__global__ void __launch_bounds__(512) gn_fused_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
+__global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, GnGeom g,
                                                         float* __restrict__ partial, unsigned int* __restrict__ counters,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                                         __half* __restrict__ out) {
@@ -376,11 +396,20 @@ __global__ void __launch_bounds__(1024) gn_part_finalize_kernel(GnFin f, float* 
   }
   __syncthreads();
   if (tid < 64) {
+    // group `grp` of the consumer = the sub-groups [sg_lo, sg_hi) of this source; sub-group sg has one record in every chunk it touches
+    // (at most two): chunk c holds it as piece sg - (32 c) / sub
     const int grp = tid >> 1, which = tid & 1;
+    const int ch_lo = max(grp * f.cg - f.c_off, 0), ch_hi = min((grp + 1) * f.cg - f.c_off, f.C_src);
     float acc = 0.f;
-    for (int c = 0; c < f.cols; ++c) {
-      const int ch = (((c >> 2) * 32) / f.sub + (c & 3)) * f.sub;      // first channel of the sub-group this record belongs to
-      if (ch < f.C_src && (f.c_off + ch) / f.cg == grp) acc += which ? red[c].y : red[c].x;
+    if (ch_hi > ch_lo) {
+      const int sg_lo = ch_lo / f.sub, sg_hi = ch_hi / f.sub;
+      for (int sg = sg_lo; sg < sg_hi; ++sg) {
+        const int c_lo = (sg * f.sub) >> 5, c_hi = (sg * f.sub + f.sub - 1) >> 5;
+        for (int c = c_lo; c <= c_hi; ++c) {
+          const int k = sg - (c * 32) / f.sub;
+          if (k >= 0 && k < 4) acc += which ? red[c * 4 + k].y : red[c * 4 + k].x;
+        }
+      }
     }
     records[((long long)s * f.total_splits + f.split_off + split) * 64 + tid] = acc;
   }
@@ -399,7 +428,7 @@ static int gn_part_plan(const GnPartGeom& g, int C_src, int samples, GnFin& f) {
   VC_REQUIRE(f.cols <= 1024, "groupnorm_from_parts: too many channels");
   f.lanes = 256 / f.cols > 0 ? 256 / f.cols : 1;
   int nsplit = (2 * sm_count() + samples - 1) / samples;
-  const long long max_useful = (g.rb_per_sample + 4 * f.lanes - 1) / (4 * f.lanes);
+  const long long max_useful = (g.rb_per_sample + 16 * f.lanes - 1) / (16 * f.lanes);     // >= 16 records per thread
   if (nsplit > max_useful) nsplit = (int)max_useful;
   if (nsplit > GN_PART_MAX_SPLITS) nsplit = GN_PART_MAX_SPLITS;
   if (nsplit < 1) nsplit = 1;

@@ -32,6 +32,7 @@ class FrameComm:
         self.T = None
         self.ranges = None
         self.bytes_moved = 0            # all-to-all payload sent by this rank (for the bench report)
+        self._prof = None               # list of (start, end) CUDA events around every exchange when profiling (bench.py: exposed comm time)
 
     def __bool__(self):
         return self.world > 1
@@ -41,8 +42,41 @@ class FrameComm:
         self.ranges = frame_ranges(T, self.world)
         return self.ranges[self.rank]
 
+    # -- exposed-communication profile: the exchanges run in-stream, so their device time (incl. waiting for the peers) is exposed --
+    def profile(self, on: bool):
+        self._prof = [] if on else None
+
+    def profile_ms(self) -> float:
+        torch.cuda.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in (self._prof or [])))
+
+    def _mark(self):
+        if self._prof is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _done(self, e0):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self._prof.append((e0, e1))
+
     # -- layout transposes -----------------------------------------------------------------------
     def to_sites(self, h: torch.Tensor, B: int, HW: int) -> torch.Tensor:
+        e0 = self._mark()
+        out = self._to_sites(h, B, HW)
+        self._done(e0)
+        return out
+
+    def to_frames(self, t: torch.Tensor, B: int, HW: int) -> torch.Tensor:
+        e0 = self._mark()
+        out = self._to_frames(t, B, HW)
+        self._done(e0)
+        return out
+
+    def _to_sites(self, h: torch.Tensor, B: int, HW: int) -> torch.Tensor:
         """[(b, t_local, hw), C] -> [(b, t_all, hw_local), C]."""
         P, C = self.world, h.shape[1]
         assert HW % P == 0, f"H*W={HW} must be divisible by the world size {P}"
@@ -58,7 +92,7 @@ class FrameComm:
         parts = [c.view(B, -1, HWl, C) for c in torch.split(recv, out_rows, 0)]
         return torch.cat(parts, dim=1).reshape(B * self.T * HWl, C)
 
-    def to_frames(self, t: torch.Tensor, B: int, HW: int) -> torch.Tensor:
+    def _to_frames(self, t: torch.Tensor, B: int, HW: int) -> torch.Tensor:
         """[(b, t_all, hw_local), C] -> [(b, t_local, hw), C]."""
         P, C = self.world, t.shape[1]
         HWl = HW // P
@@ -82,7 +116,9 @@ class FrameComm:
         last to_sites() returned (the peer-memory path already holds its statistics)."""
         from . import ops
         st = ops.groupnorm_stats(x, B)
+        e0 = self._mark()
         self.all_reduce(st)
+        self._done(e0)
         return ops.groupnorm_apply(x, B, st, stat_rows, gamma, beta, eps, silu)
 
     def gather_frames(self, y_local: torch.Tensor, T: int) -> torch.Tensor:
@@ -201,10 +237,10 @@ class PeerFrameComm(FrameComm):
         self._stats_of = out.data_ptr() if to_sites else None
         return out
 
-    def to_sites(self, h: torch.Tensor, B: int, HW: int) -> torch.Tensor:
+    def _to_sites(self, h: torch.Tensor, B: int, HW: int) -> torch.Tensor:
         return self._exchange(h, B, HW, True)
 
-    def to_frames(self, t: torch.Tensor, B: int, HW: int) -> torch.Tensor:
+    def _to_frames(self, t: torch.Tensor, B: int, HW: int) -> torch.Tensor:
         return self._exchange(t, B, HW, False)
 
     def groupnorm5d(self, x, B, gamma, beta, eps, silu, stat_rows, fresh: bool):
@@ -213,8 +249,10 @@ class PeerFrameComm(FrameComm):
         stream = torch.cuda.current_stream().cuda_stream
         rows, Cc = x.shape
         if not (fresh and self._stats_of == x.data_ptr()):
+            e0 = self._mark()
             _lib.check(self.lib.vc_peer_groupnorm_stats(C.byref(self.c), x.data_ptr(), Cc, B, rows // B, self.ws.data_ptr(), self.ws.numel() * 4,
                                                         stream), "vc_peer_groupnorm_stats")
+            self._done(e0)
         self._stats_of = None
         out = torch.empty_like(x)
         _lib.check(self.lib.vc_groupnorm_apply_parts(x.data_ptr(), Cc, B, rows // B, self.cur_stats.data_ptr(), self.world, stat_rows,
