@@ -422,9 +422,9 @@ def test_upsample_conv_fused(ops, frames, H, W, Ci, Co):
     close(y, ref, atol=6e-3, what="upconv3x3")
 
 
-@pytest.mark.parametrize("env", [{"VC_ATTN_PP": "1", "VC_ATTN_BN64": "0"}, {"VC_ATTN_PP": "0", "VC_ATTN_BN64": "0"}, {"VC_ATTN_BN64": "1"}])
+@pytest.mark.parametrize("env", [{"VC_ATTN_BN64": "0"}, {"VC_ATTN_BN64": "1"}])
 def test_attention_kernel_variants(env):
-    """Every attention kernel (ping-pong / two-CTA 128-key tiles / 64-key tiles), forced for ALL shapes through the environment in a
+    """Both attention kernels (128-key tiles, two CTAs per SM / 64-key tiles, three CTAs per SM), forced for ALL shapes through the environment in a
     fresh process (the choice is cached per process), against the fp32 reference: tools/attn_check.py."""
     import os, subprocess, sys
     if not torch.cuda.is_available():

@@ -1,4 +1,4 @@
-"""Correctness of the attention kernel selected by the environment (VC_ATTN_PP / VC_ATTN_BN64) against an fp32 torch reference,
+"""Correctness of the attention kernel selected by the environment (VC_ATTN_BN64) against an fp32 torch reference,
 over tile counts that exercise every code path: 1 tile (one softmax group idle), odd / even counts, a masked tail, shared K/V,
 the accumulate epilogue.  Prints one line per case and ATTN_CHECK_OK.  Used by tests/test_ops_gpu.py::test_attention_kernel_variants."""
 import os, sys

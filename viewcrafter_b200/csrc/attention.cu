@@ -393,307 +393,6 @@ __global__ void __launch_bounds__(192, 2) flash_attn_d64_kernel(const __grid_con
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Ping-pong variant for LONG key sequences (spatial self-attention, 2304 / 9216 keys): ONE CTA per SM, TWO softmax warpgroups
-// that take ALTERNATE key tiles of the same 128 query rows.
-//
-// Why (round-2 measurements, profiles/README.md): with two independent CTAs per SM the softmax warps of both CTAs run in
-// lockstep -- both in their MUFU-bound exponential section (the 16 ex2/clk/SM pipe saturated), then both in their MUFU-free
-// section (TMEM load of S, row maximum, barriers, P store): 1067-1210 clocks per tile and SM against a MUFU floor of 768.
-// Here warpgroup 0 owns tiles 0, 2, 4, ... and warpgroup 1 tiles 1, 3, 5, ...; each has its own S, P and O in TMEM (2 x 128 +
-// 2 x 64 + 2 x 64 = 512 columns) and its own running (max, sum), so the MMA warp alternates S0 = Q K0^T, S1 = Q K1^T, ... and the
-// two groups are half a tile apart BY CONSTRUCTION: while one is in its exponentials the other loads, reduces and stores.
-// K and V tiles are loaded once (4-stage TMA rings each) instead of once per co-resident CTA.  At the end the two partial
-// results of a row are merged like split-KV attention: O = (2^(m0-m) O0 + 2^(m1-m) O1) / (2^(m0-m) l0 + 2^(m1-m) l1).
-// Warp roles (384 threads = 3 warpgroups): warpgroup 0 = warp0 TMA, warp1 TMEM alloc + MMA issue, warps 2-3 idle; warpgroup 1 (warps 4-7)
-// softmax group 0, warpgroup 2 (warps 8-11) softmax group 1.  Registers are allocated per warpgroup: 384 threads get 168 each at
-// launch (a 320-thread CTA is charged for 12 warps too: 192 registers x 10 warps was refused as "too many resources"); the role
-// warpgroup gives its share back (setmaxnreg.dec 40) and the two softmax warpgroups grow to 224 (128 x 40 + 256 x 224 = 62464 <= 64 K).
-// ---------------------------------------------------------------------------------------------------------------------
-#ifndef VC_PP_ORDERED
-#define VC_PP_ORDERED 1      // the two groups take turns in the exponential section (named-barrier hand-over); 0 = free-running (A/B)
-#endif
-static constexpr int PP_KS = 4, PP_VS = 4;
-static constexpr int PP_SMEM = ATT_TILE_BYTES * (1 + PP_KS + PP_VS) + 1024 + 512 + 2 * 2 * 128 * 4;
-
-__global__ void __launch_bounds__(384, 1) flash_attn_d64_pp_kernel(const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + ATT_TILE_BYTES;
-  uint8_t* sV = sK + PP_KS * ATT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + PP_VS * ATT_TILE_BYTES);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;               // [PP_KS]
-  uint64_t* k_empty = k_full + PP_KS;        // [PP_KS]  Q K^T of the stage retired
-  uint64_t* v_full = k_empty + PP_KS;        // [PP_VS]
-  uint64_t* v_empty = v_full + PP_VS;        // [PP_VS]  P V of the stage retired
-  uint64_t* s_full = v_empty + PP_VS;        // [2] MMA -> group: S ready
-  uint64_t* s_free = s_full + 2;             // [2] group -> MMA: S copied to registers (4 warp arrivals)
-  uint64_t* p_full = s_free + 2;             // [2] group -> MMA: P written, O corrected (4 warp arrivals)
-  uint64_t* o_done = p_full + 2;             // [2] MMA -> group: P V retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
-  float* mrg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);      // [2][2][128]: (m, l) of each group's rows
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ATT_BM, head = blockIdx.y, b = blockIdx.z;
-  const int bk = p.kv_shared ? 0 : b;
-  const int ntiles = (p.Nk + ATT_BN - 1) / ATT_BN;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmap_q);
-    tma_prefetch_desc(&p.tmap_k);
-    tma_prefetch_desc(&p.tmap_v);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < PP_KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-    for (int i = 0; i < PP_VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_full[i], 4); mbar_init(&o_done[i], 1); }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
-   if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_4d(sQ, &p.tmap_q, q_full, 0, head, q0, b);
-    }
-    __syncwarp();
-    for (int j = 0; j < ntiles; ++j) {
-      const int ks = j % PP_KS, vs = j % PP_VS;
-      if (j >= PP_KS) mbar_wait(&k_empty[ks], ((j / PP_KS) - 1) & 1);
-      if (elect_one()) {
-        mbar_expect_tx(&k_full[ks], ATT_TILE_BYTES);
-        tma_load_4d(sK + ks * ATT_TILE_BYTES, &p.tmap_k, &k_full[ks], 0, head, j * ATT_BN, bk);
-      }
-      __syncwarp();
-      if (j >= PP_VS) mbar_wait(&v_empty[vs], ((j / PP_VS) - 1) & 1);
-      if (elect_one()) {
-        mbar_expect_tx(&v_full[vs], ATT_TILE_BYTES);
-        tma_load_4d(sV + vs * ATT_TILE_BYTES, &p.tmap_v, &v_full[vs], 0, head, j * ATT_BN, bk);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);      // B = V is MN-major
-    const uint32_t aQ = smem_u32(sQ);
-    auto issue_qk = [&](int j) {
-      const int w = j & 1, ks = j % PP_KS;
-      mbar_wait(&k_full[ks], (j / PP_KS) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t aK = smem_u32(sK + ks * ATT_TILE_BYTES);
-        const uint32_t tS = tmem_base + w * 128;
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)
-          umma_ss(tS, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc_qk, k > 0 ? 1u : 0u);
-        umma_commit(&s_full[w]);
-        umma_commit(&k_empty[ks]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    if (ntiles > 1) issue_qk(1);
-    for (int j = 0; j < ntiles; ++j) {
-      const int w = j & 1, it = j >> 1, vs = j % PP_VS;
-      if (j + 2 < ntiles) {                         // S(j) sits in its group's registers: the S buffer takes tile j + 2
-        mbar_wait(&s_free[w], it & 1);
-        issue_qk(j + 2);
-      }
-      mbar_wait(&v_full[vs], (j / PP_VS) & 1);
-      mbar_wait(&p_full[w], it & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t aV = smem_u32(sV + vs * ATT_TILE_BYTES);
-        const uint32_t tP = tmem_base + 256 + w * 64, tO = tmem_base + 384 + w * 64;
-#pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k)
-          umma_ts(tO, tP + k * 8, umma_desc_sw128(aV + k * 2048), idesc_pv, (j >= 2 || k > 0) ? 1u : 0u);
-        umma_commit(&v_empty[vs]);
-        umma_commit(&o_done[w]);
-      }
-      __syncwarp();
-    }
-   }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
-    const int wg = (warp - 4) >> 2;
-    const int qd = warp & 3;
-    const int r = qd * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    const uint32_t tS = tmem_base + wg * 128, tP = tmem_base + 256 + wg * 64, tO = tmem_base + 384 + wg * 64;
-    const float sl2 = p.scale_log2;
-    float m = -INFINITY, l = 0.f;
-    int it = 0;
-#if VC_PP_ORDERED
-    // Turn-taking in the MUFU-bound section: group g enters it after `bar.sync 2+g` (128 own + 128 arrivals of the other group)
-    // and hands over with `bar.arrive 2+(1-g)` when the other group still has a tile to process.  Group 1 gives group 0 the first turn.
-    if (wg == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");
-#endif
-    for (int j = wg; j < ntiles; j += 2, ++it) {
-      const int valid = min(ATT_BN, p.Nk - j * ATT_BN);
-      mbar_wait(&s_full[wg], it & 1);
-      tc_fence_after();
-      uint32_t s0[32], s1[32], s2[32], s3[32];
-      tmem_ld32(tS + lane_off, s0);
-      tmem_ld32(tS + lane_off + 32, s1);
-      tmem_ld32(tS + lane_off + 64, s2);
-      tmem_ld32(tS + lane_off + 96, s3);
-      tc_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(&s_free[wg]);
-
-      float mx = -INFINITY;
-      if (valid == ATT_BN) {
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          m0 = fmaxf(m0, fmaxf(__uint_as_float(s0[e]), __uint_as_float(s0[e + 1])));
-          m1 = fmaxf(m1, fmaxf(__uint_as_float(s1[e]), __uint_as_float(s1[e + 1])));
-          m2 = fmaxf(m2, fmaxf(__uint_as_float(s2[e]), __uint_as_float(s2[e + 1])));
-          m3 = fmaxf(m3, fmaxf(__uint_as_float(s3[e]), __uint_as_float(s3[e + 1])));
-        }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          if (e >= valid) s0[e] = 0xff800000u;            // -inf: masked keys get probability 0
-          if (32 + e >= valid) s1[e] = 0xff800000u;
-          if (64 + e >= valid) s2[e] = 0xff800000u;
-          if (96 + e >= valid) s3[e] = 0xff800000u;
-          mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(s0[e]), __uint_as_float(s1[e])), fmaxf(__uint_as_float(s2[e]), __uint_as_float(s3[e]))));
-        }
-      }
-      const float m_cand = fmaxf(m, mx * sl2);
-      const bool need = (m_cand - m) > ATT_LAZY;          // first own tile: m = -inf -> true
-      float alpha = 1.f;
-      if (need) {
-        alpha = ex2f(m - m_cand);                         // 0 at the first own tile
-        l *= alpha;
-        m = m_cand;
-      }
-      const float2 sl2v = make_float2(sl2, sl2), negm2 = make_float2(-m, -m);
-      float2 ps0 = make_float2(0.f, 0.f), ps1 = ps0, ps2 = ps0, ps3 = ps0;
-#if VC_PP_ORDERED
-      if (wg == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
-      else asm volatile("bar.sync 3, 256;" ::: "memory");
-#endif
-#define VC_PP_CHUNK(SRC, DST, OFF, PS)                                                                        \
-  _Pragma("unroll") for (int e = 0; e < 32; e += 2) {                                                         \
-    const float2 x = __ffma2_rn(make_float2(__uint_as_float(SRC[e]), __uint_as_float(SRC[e + 1])), sl2v, negm2); \
-    const float2 a = ex2_pair(x, e);                                                                          \
-    PS = __fadd2_rn(PS, a);                                                                                   \
-    DST[OFF + e / 2] = pack_half2(a.x, a.y);                                                                  \
-  }
-      VC_PP_CHUNK(s0, s0, 0, ps0)
-      VC_PP_CHUNK(s1, s0, 16, ps1)
-      VC_PP_CHUNK(s2, s2, 0, ps2)
-      VC_PP_CHUNK(s3, s2, 16, ps3)
-#undef VC_PP_CHUNK
-      const float2 pst = __fadd2_rn(__fadd2_rn(ps0, ps1), __fadd2_rn(ps2, ps3));
-      l += pst.x + pst.y;
-#if VC_PP_ORDERED
-      if (j + 1 < ntiles) {                                // the other group has tile j + 1: its turn
-        if (wg == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
-        else asm volatile("bar.arrive 2, 256;" ::: "memory");
-      }
-#endif
-      if (it > 0) {
-        mbar_wait(&o_done[wg], (it - 1) & 1);              // P V of this group's previous tile retired: P and O may be touched
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {               // warp-uniform: tcgen05.ld/st are warp-collective
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tO + lane_off + c * 32, v);
-            tc_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-            tmem_st32(tO + lane_off + c * 32, v);
-          }
-        }
-      }
-      tmem_st32(tP + lane_off, s0);
-      tmem_st32(tP + lane_off + 32, s2);
-      tc_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(&p_full[wg]);
-    }
-    // ---- merge the two groups' partial results and write the output ----
-    const int my_tiles = it;                                  // tiles this group processed
-    const int oth_tiles = ntiles - my_tiles;
-    if (my_tiles > 0) {
-      mbar_wait(&o_done[wg], (my_tiles - 1) & 1);
-      tc_fence_after();
-    }
-    mrg[(wg * 2 + 0) * 128 + r] = m;
-    mrg[(wg * 2 + 1) * 128 + r] = l;
-    tc_fence_before();
-    asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 softmax warps: both accumulators final, (m, l) published
-    if (oth_tiles > 0) mbar_wait(&o_done[1 - wg], (oth_tiles - 1) & 1);   // observe the other accumulator's last P V directly as well
-    tc_fence_after();
-    const float m_o = mrg[((1 - wg) * 2 + 0) * 128 + r], l_o = mrg[((1 - wg) * 2 + 1) * 128 + r];
-    const float M = fmaxf(my_tiles > 0 ? m : -INFINITY, oth_tiles > 0 ? m_o : -INFINITY);
-    const float a_s = my_tiles > 0 ? ex2f(m - M) : 0.f, a_o = oth_tiles > 0 ? ex2f(m_o - M) : 0.f;
-    const float inv = 1.f / (a_s * l + a_o * l_o);
-    const float w_s = a_s * inv, w_o = a_o * inv;
-    // group g writes output columns [32 g, 32 g + 32) of its rows from BOTH accumulators
-    const uint32_t tO_s = tO + lane_off + wg * 32, tO_o = tmem_base + 384 + (1 - wg) * 64 + lane_off + wg * 32;
-    uint32_t vs_[32], vo_[32];
-    if (my_tiles > 0) tmem_ld32(tO_s, vs_);
-    if (oth_tiles > 0) tmem_ld32(tO_o, vo_);
-    tc_wait_ld();
-    const int row = q0 + r;
-    if (row < p.Nq) {
-      __half* op = p.out + ((long long)b * p.Nq + row) * p.ldo + head * ATT_D + wg * 32;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float acc = 0.f;
-          if (my_tiles > 0) acc = __uint_as_float(vs_[g * 8 + e]) * w_s;
-          if (oth_tiles > 0) acc = fmaf(__uint_as_float(vo_[g * 8 + e]), w_o, acc);
-          f[e] = acc;
-        }
-        uint4* dst = reinterpret_cast<uint4*>(op + g * 8);
-        if (p.accumulate) {
-          const uint4 u = *dst;
-          const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 t = __half22float2(h[e]);
-            f[2 * e] += t.x; f[2 * e + 1] += t.y;
-          }
-        }
-        uint4 o;
-        o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
-        o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
-        *dst = o;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 int flash_attn_d64(const AttnDesc& d, cudaStream_t stream) {
   // Short key sequences (text / image cross-attention: 77 / 256 keys; the 18x32 and 9x16 levels: 576 / 144 keys) run on the
   // 64-key-tile kernel (attention_bn64.cu, three CTAs per SM): measured on B200 (profiles/r02_ab_micro.txt) cross-attention
@@ -730,17 +429,9 @@ int flash_attn_d64(const AttnDesc& d, cudaStream_t stream) {
   static DeviceOnce configured;
   if (device_once_needed(configured)) {
     VC_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    VC_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_d64_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM));
     device_once_mark(configured);
   }
   dim3 grid((d.Nq + ATT_BM - 1) / ATT_BM, d.heads, d.B);
-  static int pp = -1;                         // VC_ATTN_PP=1: the ping-pong kernel (one CTA per SM, two softmax warpgroups on alternate key tiles)
-  if (pp < 0) { const char* e = getenv("VC_ATTN_PP"); pp = (e && e[0] == '1') ? 1 : 0; }
-  if (pp) {
-    flash_attn_d64_pp_kernel<<<grid, 384, PP_SMEM, stream>>>(p);
-    VC_CHECK_CUDA(cudaGetLastError());
-    return VC_OK;
-  }
   flash_attn_d64_kernel<<<grid, 192, ATT_SMEM, stream>>>(p);
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;

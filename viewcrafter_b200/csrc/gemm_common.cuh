@@ -80,7 +80,6 @@ struct GemmParams {
   float2* gn_part;         // optional: GroupNorm partial (sum, sumsq) of the fp16-rounded outputs per (32-row block, 32-column chunk, piece):
   int gn_hp;               //   [m_tile * 4 + quadrant][N / 32][4]; a chunk is cut at the boundaries of gn_sub = 2 * gn_hp channel sub-groups
   int gn_nchunks;          //   (4 pieces: first partial, two whole, last partial / whole) -- see gn_part_accumulate and norm.cu: gn_part_finalize_kernel
-  int l2_prefetch;       // producer warps prefetch the NEXT tile's own A rows into L2 while the current tile is being multiplied
   int out_tma;           // fp16 output written by TMA stores from per-warp staging tiles (full-line, LSU-free)
   int vec_ok;            // rows are 32-byte aligned: the 256-bit epilogue path may be used
   int debug;             // profiling aid, only honoured by builds with -DVC_GEMM_DEBUG_BUILD=1 (env VC_GEMM_DEBUG): 1 = skip the MMAs
@@ -106,19 +105,6 @@ __device__ __forceinline__ TileCoord tile_coord_m(const GemmParams& p, int m) {
 #endif
 
 #ifdef __CUDACC__
-// A persistent CTA is at most a ring (3-5 k-blocks, ~1 us of tensor work) ahead of its MMAs, less than a DRAM round trip under
-// load: the first touch of a tile's own activation rows (cold: nobody has read them yet; the rows a 3x3 / temporal tap reaches
-// beyond them are other tiles' own rows) stalled the pipeline once per tile -- the fixed ~2-3 us per tile visible as 1239 vs 1446
-// TFLOP/s between the 45- and the 135-k-block 3x3 convs of the same M and N (profiles/r02_gemm_micro.txt).  So the producer asks the
-// L2 for the next tile's own rows (centre tap, every k-block) a whole tile period before it loads them.
-__device__ __forceinline__ void prefetch_tile_rows(const GemmParams& p, const TileCoord& tc, int kblocks) {
-  for (int kb = 0; kb < kblocks; ++kb) {
-    const int k = kb * BK;
-    if (k < p.K1) tma_prefetch_l2_4d(&p.tmap_a, k, tc.x0, tc.y0, tc.z);
-    else tma_prefetch_l2_4d(&p.tmap_a2, k - p.K1, tc.x0, tc.y0, tc.z);
-  }
-}
-
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one instruction moves a full 32-byte sector per thread
 __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),

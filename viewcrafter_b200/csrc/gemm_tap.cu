@@ -95,11 +95,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tap_kernel(const __grid_
       const int m_tile = fast_div(p.div_n_tiles, tile);
       const TileCoord tc = tile_coord_m(p, m_tile);
       const int n0 = (tile - m_tile * p.n_tiles) * BN;
-      if (p.l2_prefetch && tile + (int)gridDim.x < p.total_tiles) {
-        const int m_next = fast_div(p.div_n_tiles, tile + (int)gridDim.x);
-        if (m_next != m_tile && elect_one()) prefetch_tile_rows(p, tile_coord_m(p, m_next), kblocks);
-        __syncwarp();
-      }
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
         const int brow = tap * p.N + n0;
@@ -377,9 +372,6 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
       dbg = e ? atoi(e) : 0;
     }
     p.debug = dbg;
-    static int pf = -1;                        // tuning switch VC_GEMM_L2PF=0: no L2 prefetch of the next tile's rows
-    if (pf < 0) { const char* e = getenv("VC_GEMM_L2PF"); pf = (e && e[0] == '0') ? 0 : 1; }
-    p.l2_prefetch = pf;
   }
   const long long total = (use_pair ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;
   VC_REQUIRE(total > 0 && total < (1ll << 31), "gemm_tap: tile count %lld out of range", total);

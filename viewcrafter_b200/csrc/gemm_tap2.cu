@@ -133,11 +133,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
       const int n_tile = tile - m_pair * p.n_tiles;
       const TileCoord tc = tile_coord_m(p, m_pair * 2 + (int)rank);
       const int n0 = n_tile * BN + (int)rank * (BN / 2);
-      if (p.l2_prefetch && tile + nclusters < pair_tiles) {
-        const int m_next = fast_div(p.div_n_tiles, tile + nclusters);
-        if (m_next != m_pair && elect_one()) prefetch_tile_rows(p, tile_coord_m(p, m_next * 2 + (int)rank), kblocks);
-        __syncwarp();
-      }
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const int cx = tc.x0 + p.tap_dx[tap], cy = tc.y0 + p.tap_dy[tap];
         const int brow = tap * p.N + n0;

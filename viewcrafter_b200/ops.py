@@ -148,8 +148,10 @@ LN_FROM_PRODUCER = os.environ.get("VC_LN_FROM_PRODUCER", "1") != "0"   # A/B swi
 # GroupNorm statistics from the producing GEMM's epilogue (GemmDesc.gn_part): 0 = off (statistics pass inside the GroupNorm kernel),
 # 1 = producers with a long reduction only (3x3 / temporal / stride-2 convs: the extra epilogue work hides under the MMAs), 2 = every producer
 GN_FROM_PRODUCER = int(os.environ.get("VC_GN_FROM_PRODUCER", "1"))
-# ... and only for tensors of at least this many MB: smaller ones are re-read from the 126 MB L2 by the one-launch fused kernel, which then
-# beats finalize + normalise (measured on B200, profiles/README.md round 2)
+# ... taken for every GroupNorm with <= 4 samples (the 5-D ones: one sample = a whole batch element, so the fused kernel's statistics and
+# normalise phases cannot overlap across samples) and for per-frame GroupNorms of at least this many MB; smaller per-frame tensors are re-read
+# from the 126 MB L2 by the one-launch fused kernel, which then beats finalize + normalise (measured on B200, profiles/README.md round 2:
+# 5-D 75 vs 97 us at level 0, 46 vs 59 at level 1, 33 vs 42 at level 2; 4-D 139 vs 161 us at level 0 B=2, but 51 vs 47 at level 1)
 GN_PARTS_MIN_MB = float(os.environ.get("VC_GN_PARTS_MIN_MB", "100"))
 GN_SUB = 10          # sub-group width the U-Net producers cut their chunks at: every GroupNorm(32) boundary of 320 / 640 / 1280 channels
                      # and of their skip concats (640 / 960 / 1280 / 1920 / 2560) is a multiple of 10
@@ -442,7 +444,7 @@ def groupnorm(x: torch.Tensor, samples: int, gamma: torch.Tensor, beta: torch.Te
     assert x.is_contiguous() and (x2 is None or x2.is_contiguous())
     out = torch.empty((rows, C1 + C2), device=x.device, dtype=torch.float16)
     p1, p2 = gn_part_of(x), (gn_part_of(x2) if x2 is not None else None)
-    if p1 is not None and (x2 is None or p2 is not None) and rows * (C1 + C2) * 2 >= GN_PARTS_MIN_MB * 1e6:
+    if p1 is not None and (x2 is None or p2 is not None) and (samples <= 4 or rows * (C1 + C2) * 2 >= GN_PARTS_MIN_MB * 1e6):
         cg = (C1 + C2) // 32
         g1 = p1.geom(samples, rows // samples)
         g2 = p2.geom(samples, rows // samples) if x2 is not None else None
