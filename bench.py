@@ -144,7 +144,12 @@ def kernel_rooflines(wl, device, peaks):
     t_att = time_kernel(lambda: ops.flash_attn(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], T, H * W, H * W, heads))
     fl_att = 4.0 * T * heads * (H * W) ** 2 * 64
     gam, bet = torch.ones(C, device=device), torch.zeros(C, device=device)
-    t_gn = time_kernel(lambda: ops.groupnorm(x, T, gam, bet, 1e-5, True))
+    # the shipped GroupNorm path for this tensor: the producing conv's epilogue leaves the partial sums (gn_out), GroupNorm = finalize + ONE pass
+    y = ops.conv3x3(x, T, H, W, w9, gn_out=True)
+    gn_parts = ops.gn_part_of(y) is not None
+    n_gn0 = ops.gn_from_parts_calls
+    t_gn = time_kernel(lambda: ops.groupnorm(y, T, gam, bet, 1e-5, True))
+    gn_parts = gn_parts and ops.gn_from_parts_calls > n_gn0
     by_gn = 2.0 * M * C * 2                                     # algorithmic: read once + write once, fp16
     r = {
         "roofline": {"kernel": "gemm_tap2_kernel<160> (tcgen05 cta_group::2 tap-GEMM, 3x3 conv 320->320 @%dx%dx%d)" % (T, H, W), "bound": "tensor",
@@ -156,7 +161,8 @@ def kernel_rooflines(wl, device, peaks):
                                "achieved": fl_att / t_att / 1e12, "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
                                "frac": fl_att / t_att / 1e12 / peaks["tflops_burst"], "traffic": None, "ms": t_att * 1e3,
                                "algorithmic_flop": fl_att, "algorithmic_bytes": 4.0 * M * C * 2},
-        "roofline_groupnorm": {"kernel": "gn_fused_kernel (GroupNorm32+SiLU, C=320, one launch)", "bound": "hbm",
+        "roofline_groupnorm": {"kernel": ("gn_part_finalize_kernel + gn_apply_kernel (GroupNorm32+SiLU, C=320; statistics from the producing conv's epilogue, one pass)"
+                                          if gn_parts else "gn_fused_kernel (GroupNorm32+SiLU, C=320, statistics pass + normalise pass in one launch)"), "bound": "hbm",
                                "achieved": by_gn / t_gn / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                "frac": by_gn / t_gn / 1e9 / peaks["hbm_gbs"], "traffic": None, "ms": t_gn * 1e3, "algorithmic_bytes": by_gn},
     }
@@ -167,6 +173,8 @@ def kernel_rooflines(wl, device, peaks):
     tp = cands[-1] if cands else ""                                       # the newest committed capture
     if tp and (T, H, W) == (25, 72, 128):                                  # the capture is of the headline shapes only
         t = json.load(open(tp))
+        if not gn_parts and "groupnorm_fused_statistics_pass" in t:
+            t["roofline_groupnorm"] = t["groupnorm_fused_statistics_pass"]
         for k in r:
             if k in t:
                 r[k]["traffic"] = t[k]["traffic_bytes"]
@@ -492,8 +500,7 @@ def main():
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dist)
         return
 
     value = args.steps / float(t_dev)
@@ -528,8 +535,21 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample, "estimated": True}
             line["cpu_baseline_config1"] = cpu_config1_measured(sd_cpu)
     print(json.dumps(line))
+    _finish(world, dist)
+
+
+def _finish(world, dist):
+    """End of a multi-rank run: every rank has its result; leave without tearing the process group down.  destroy_process_group() after
+    NCCL collectives were captured into CUDA graphs hung at exit on the 4-GPU box (round 2, call C: the line was printed, the ranks never
+    left), so the ranks meet at a barrier and exit hard."""
+    sys.stdout.flush(); sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            torch.cuda.synchronize()
+            dist.barrier()
+        except Exception:
+            pass
+        os._exit(0)
 
 
 if __name__ == "__main__":
