@@ -329,6 +329,7 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the parity block and the eager-PyTorch GPU baseline")
     ap.add_argument("--no-vae", action="store_true")
     ap.add_argument("--no-batch-cfg", action="store_true")
+    ap.add_argument("--no-cfg-split", action="store_true", help="N > 1: pure frame sharding (every rank runs the B=2 cond+uncond forward on its frames) instead of 2-way CFG split x N/2-way frames")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured forward")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -380,7 +381,7 @@ def main():
     model = build_model(wl, device)
     if world > 1:
         from viewcrafter_b200 import parallel
-        parallel.shard_model(model, dist, rank, world)
+        parallel.shard_model(model, dist, rank, world, cfg_split=not args.no_cfg_split)
     if not args.no_graph:
         model.model.diffusion_model.enable_cuda_graph()
     config["host"] = ("eager launches" if args.no_graph else
@@ -414,8 +415,11 @@ def main():
         xc = torch.cat([dev["x_T"], dev["c_concat"]], 1)
         t499 = torch.full((1,), 499, device=device, dtype=torch.long)
         comm.bytes_moved = 0
+        if hasattr(comm, "fused_switches"):
+            comm.fused_switches = 0
         y_sh = unet_m(xc, t499, context=dev["ctx_c"], fs=fs)
         comm.bytes_per_forward = comm.bytes_moved
+        comm.fused_per_forward = getattr(comm, "fused_switches", 0)
         # exposed communication: the exchanges run in-stream, so their device time (transfer + waiting for the slowest peer) is not
         # overlapped with compute; measured over one more eager forward with CUDA events around every exchange / statistics call
         torch.cuda.synchronize(); dist.barrier()
@@ -486,7 +490,9 @@ def main():
     comm_info = None
     if world > 1:
         from viewcrafter_b200 import parallel as _par
-        comm_info = {"layout": "2-way CFG split x %d-way frame sharding" % (world // 2) if world % 2 == 0 else "%d-way frame sharding" % world,
+        cfg_split = world % 2 == 0 and not args.no_cfg_split
+        comm_info = {"layout": "2-way CFG split x %d-way frame sharding" % (world // 2) if cfg_split else "%d-way frame sharding" % world,
+                     "fused_switches_per_forward": None if comm is None else getattr(comm, "fused_per_forward", None),
                      "impl": ("NVLink peer-memory exchange kernels (csrc/peer.cu), GroupNorm statistics fused into the frames->sites switch"
                               if isinstance(comm, _par.PeerFrameComm) else ("NCCL all_to_all_single + all_reduce" if comm is not None else "none (CFG split only)")),
                      "bytes_sent_per_forward_rank0": None if comm is None else int(getattr(comm, "bytes_per_forward", 0)),
@@ -495,7 +501,7 @@ def main():
                                                                "exchanges": getattr(comm, "n_exchanges", None),
                                                                "what": "device time of the in-stream exchange / statistics kernels of ONE eager forward on rank 0 "
                                                                        "(transfer + waiting for the slowest peer): not overlapped with compute"},
-                     "cfg_exchange_bytes_per_step": int(dev["x_T"].numel() * 4) if world % 2 == 0 else 0}
+                     "cfg_exchange_bytes_per_step": int(dev["x_T"].numel() * 4) if cfg_split else 0}
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define VC_B200_ABI_VERSION 5
+#define VC_B200_ABI_VERSION 6
 
 int vc_abi_version(void);
 const char* vc_last_error(void);
@@ -68,7 +68,18 @@ typedef struct vc_gemm_desc {
    * piece: gn_part[((rb * (N/32) + chunk) * 4 + piece) * 2]; a chunk is cut into 4 pieces at multiples of gn_sub (10 or 8) channels.
    * vc_groupnorm_from_parts consumes them.  fp16 outputs with N % 32 == 0 and N % gn_sub == 0 only. */
   float* gn_part; int32_t gn_sub;
+  /* optional: multi-GPU layout switch fused into the epilogue (see vc_gemm_peer below); NULL = write `out` locally */
+  const struct vc_gemm_peer* peer;
 } vc_gemm_desc;
+/* Output rows of the GEMM are stored tile by tile (TMA stores through the NVLink peer mapping) into the receive buffers of the ranks
+ * that own them in the OTHER layout of the frame-sharded U-Net (new functionality): mode 1 = this rank's rows are
+ * [(b, t_local, hw), N] and go to [(b, t, hw_local), N] on rank hw / (HW / world); mode 2 the reverse.  `out` is not written.
+ * Complete the switch with vc_peer_finish_scatter (rendezvous + GroupNorm sums).  2..4 ranks, fp16 output with N % 32 == 0. */
+typedef struct vc_gemm_peer {
+  int32_t mode, world, rank, B, T, HW;
+  int32_t f0[9];          /* rank q owns frames [f0[q], f0[q+1]) */
+  void* dst[8];           /* rank q's receive buffer of the destination layout as mapped into this process */
+} vc_gemm_peer;
 int vc_gemm_tap(const vc_gemm_desc* d, void* stream);
 /* N-tile width the kernel will use for (N, geglu): needed to interleave GEGLU weights on the host */
 int vc_gemm_tile_n(int32_t N, int32_t geglu);
@@ -207,6 +218,7 @@ int vc_peer_exchange(const vc_peer_comm* c, const void* src, void* const* dst, i
                      int32_t C, const int32_t* f0, int32_t with_stats, void* ws, size_t ws_bytes, void* stream);
 /* GroupNorm statistics of this rank's rows + exchange with all peers -> cur_stats (the site-sharded 5-D GroupNorms in the
  * middle of a temporal block, openaimodel3d.py:256-265) */
+int vc_peer_finish_scatter(const vc_peer_comm* c, const vc_gn_part_geom* geom, int32_t C, int32_t samples, void* ws, size_t ws_bytes, void* stream);
 int vc_peer_groupnorm_stats(const vc_peer_comm* c, const void* x, int32_t C, int32_t samples, int64_t rows_per_sample, void* ws,
                             size_t ws_bytes, void* stream);
 

@@ -72,7 +72,7 @@ def _h(t):
     return t.to(torch.float16)
 
 
-def linear(x, w, bias=None, res=None, geglu=False, out=None, out_f32=False, x2=None, ln=None, ln_out=False, gn_out=False):
+def linear(x, w, bias=None, res=None, geglu=False, out=None, out_f32=False, x2=None, ln=None, ln_out=False, gn_out=False, peer=None):
     # the kernel's host-side contract (gemm_tap.cu: TMA strides are 16-byte multiples)
     # (the double's own norm ops may hand back permuted views; only row-major operands carry a meaningful pitch)
     assert w.shape[1] % 8 == 0, w.shape
@@ -122,7 +122,7 @@ def upconv3x3(x, frames, H, W, packs, bias=None):
     return _h(_nchw_to_rows(out))
 
 
-def conv3x3(x, frames, H, W, w9, bias=None, res=None, x2=None, bias_z_div=0, out_f32=False, out=None, gn_out=False):
+def conv3x3(x, frames, H, W, w9, bias=None, res=None, x2=None, bias_z_div=0, out_f32=False, out=None, gn_out=False, peer=None):
     a = x if x2 is None else torch.cat([x, x2], 1)
     N, K = w9.shape[0] // 9, w9.shape[1]
     w = w9.float().reshape(3, 3, N, K).permute(2, 3, 0, 1)
@@ -138,7 +138,7 @@ def conv3x3(x, frames, H, W, w9, bias=None, res=None, x2=None, bias_z_div=0, out
     return y
 
 
-def conv_temporal(x, B, T, HW, w3, bias=None, res=None, gn_out=False):
+def conv_temporal(x, B, T, HW, w3, bias=None, res=None, gn_out=False, peer=None):
     N, K = w3.shape[0] // 3, w3.shape[1]
     w = w3.float().reshape(3, N, K).permute(1, 2, 0).reshape(N, K, 3, 1, 1)
     x5 = x.float().reshape(B, T, HW, K).permute(0, 3, 1, 2).unsqueeze(-1)

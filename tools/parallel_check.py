@@ -57,6 +57,38 @@ if peer_mode:
         ok_unit = ok_unit and good
         if rank == 0:
             print(f"peer exchange B={Bq} HW={HWq} C={Cq}: to_sites==nccl {same_sites}, round trip {same_back}, GN(fused stats) err {e12:.2e}, GN(peer stats) err {e13:.2e}")
+        # ---- layout switches performed by the producing GEMM's epilogue (scatter_plan) vs GEMM + separate exchange kernel ----
+        Hq = {256: 16, 64: 8, 16: 4}[HWq]
+        Tl, HWl = f1 - f0, HWq // world
+        fused = {}
+        plan = comm.scatter_plan(True, Bq, HWq, Cq)
+        if plan is not None and Tl > 0:
+            xq = (torch.randn(Bq * Tl * HWq, 64, generator=gq) * 0.8).half().cuda()
+            rq = (torch.randn(Bq * Tl * HWq, Cq, generator=gq) * 0.5).half().cuda()
+            w9 = ops.pack_conv3x3(torch.randn(Cq, 64, 3, 3, generator=gq) * 0.06).cuda()
+            bq = torch.randn(Cq, generator=gq).cuda() * 0.1
+            ref = comm.to_sites(ops.conv3x3(xq, Bq * Tl, Hq, Hq, w9, bias=bq, res=rq), Bq, HWq).clone()
+            got = ops.conv3x3(xq, Bq * Tl, Hq, Hq, w9, bias=bq, res=rq, peer=comm.scatter_plan(True, Bq, HWq, Cq))
+            fused["conv3x3->sites"] = torch.equal(got, ref)
+            n_f = comm.groupnorm5d(got, Bq, gam, bet, 1e-5, True, T * HWq, True)            # statistics from the GEMM's partial sums
+            n_r = ref_comm.groupnorm5d(ref, Bq, gam, bet, 1e-5, True, T * HWq, True)
+            fused["GN after fused switch"] = float((n_f.float() - n_r.float()).abs().max()) < 4e-3
+            wl = (torch.randn(Cq, 64, generator=gq) * 0.1).half().cuda()
+            ref = comm.to_sites(ops.linear(xq, wl, bias=bq, res=rq), Bq, HWq).clone()
+            got = ops.linear(xq, wl, bias=bq, res=rq, peer=comm.scatter_plan(True, Bq, HWq, Cq))
+            fused["linear->sites"] = torch.equal(got, ref)
+            a_s = ref.clone()                                                                    # a site-layout tensor [(b, t, hw_local), C]
+            w3 = ops.pack_conv_temporal(torch.randn(Cq, Cq, 3, 1, 1, generator=gq) * (1.0 / (3 * Cq) ** 0.5)).cuda()
+            ref = comm.to_frames(ops.conv_temporal(a_s, Bq, T, HWl, w3, bias=bq, res=a_s), Bq, HWq).clone()
+            got = ops.conv_temporal(a_s, Bq, T, HWl, w3, bias=bq, res=a_s, peer=comm.scatter_plan(False, Bq, HWq, Cq))
+            fused["tconv->frames"] = torch.equal(got, ref)
+            wl2 = (torch.randn(Cq, Cq, generator=gq) * (1.0 / Cq ** 0.5)).half().cuda()
+            ref = comm.to_frames(ops.linear(a_s, wl2, bias=bq, res=a_s), Bq, HWq).clone()
+            got = ops.linear(a_s, wl2, bias=bq, res=a_s, peer=comm.scatter_plan(False, Bq, HWq, Cq))
+            fused["linear->frames"] = torch.equal(got, ref)
+            torch.cuda.synchronize()
+            ok_unit = ok_unit and all(fused.values())
+        print(f"[rank {rank}] fused switches B={Bq} HW={HWq} C={Cq}: {fused if fused else 'no plan (shape not supported / VC_PEER_FUSED=0)'}", flush=True)
 y_sharded = m(x.cuda(), t.cuda(), context=ctx.cuda())
 torch.cuda.synchronize()
 # CUDA-graph replay of the sharded forward (call 1 eager, call 2 capture, call 3 replay)
@@ -83,7 +115,8 @@ if rank == 0:
         ref = O.unet_forward(sd, x, t, ctx, None, default_fs=10)
     d_ref = float((y_sharded.cpu() - ref).abs().max())
     ok = ok and d_ref < 0.02
-    print(f"world {world}: |sharded - single| {d_single:.4g}, |sharded - oracle| {d_ref:.4g}, all-to-all bytes sent by rank 0: {comm.bytes_moved}")
+    print(f"world {world}: |sharded - single| {d_single:.4g}, |sharded - oracle| {d_ref:.4g}, all-to-all bytes sent by rank 0: {comm.bytes_moved}, "
+          f"switches fused into GEMM epilogues: {getattr(comm, 'fused_switches', 0)}")
 m._comm = None
 
 # ---- one guided DDIM step with the 2-way CFG split x (world/2)-way frame sharding (what bench.py --gpus N runs) ----

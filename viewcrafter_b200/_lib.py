@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VC_B200_LIB") or os.path.join(_HERE, "libvc_b200.so")   # override: A/B builds of the kernels
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class VcError(RuntimeError):
@@ -25,7 +25,13 @@ class GemmDesc(C.Structure):
                 ("out", C.c_void_p), ("out_f32", C.c_void_p), ("ldo", C.c_int32),
                 ("bias", C.c_void_p), ("bias_z_div", C.c_int32), ("res", C.c_void_p), ("ldr", C.c_int32),
                 ("geglu", C.c_int32), ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_part", C.c_void_p),
-                ("ldo_y", C.c_int64), ("ldo_z", C.c_int64), ("gn_part", C.c_void_p), ("gn_sub", C.c_int32)]
+                ("ldo_y", C.c_int64), ("ldo_z", C.c_int64), ("gn_part", C.c_void_p), ("gn_sub", C.c_int32),
+                ("peer", C.c_void_p)]
+
+
+class GemmPeer(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("B", C.c_int32), ("T", C.c_int32), ("HW", C.c_int32),
+                ("f0", C.c_int32 * 9), ("dst", C.c_void_p * 8)]
 
 
 class GnPartGeom(C.Structure):
@@ -79,6 +85,7 @@ SIGNATURES = {
     "vc_peer_free": (C.c_int, [_vp]),
     "vc_peer_exchange": (C.c_int, [C.POINTER(PeerComm), _vp, C.POINTER(C.c_void_p), _i32, _i32, _i32, _i32, _i32, C.POINTER(C.c_int32), _i32,
                                    _vp, _sz, _vp]),
+    "vc_peer_finish_scatter": (C.c_int, [C.POINTER(PeerComm), _vp, _i32, _i32, _vp, _sz, _vp]),
     "vc_peer_groupnorm_stats": (C.c_int, [C.POINTER(PeerComm), _vp, _i32, _i32, _i64, _vp, _sz, _vp]),
     "vc_layernorm_stats": (C.c_int, [_vp, _i64, _i32, _f32, _vp, _vp]),
     "vc_layernorm_stats_from_parts": (C.c_int, [_vp, _i64, _i32, _f32, _vp, _vp]),

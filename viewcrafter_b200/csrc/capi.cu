@@ -35,6 +35,15 @@ int vc_gemm_tap(const vc_gemm_desc* c, void* stream) {
   d.bias = c->bias; d.bias_z_div = c->bias_z_div; d.res = H(c->res); d.ldr = c->ldr; d.geglu = c->geglu;
   d.ln_stats = c->ln_stats; d.ln_colsum = c->ln_colsum; d.ln_part = c->ln_part; d.gn_part = c->gn_part; d.gn_sub = c->gn_sub;
   d.ldo_y = c->ldo_y; d.ldo_z = c->ldo_z;
+  GemmPeerDesc pd;
+  if (c->peer && c->peer->mode) {
+    const vc_gemm_peer* q = c->peer;
+    pd.mode = q->mode; pd.world = q->world; pd.rank = q->rank; pd.B = q->B; pd.T = q->T; pd.HW = q->HW;
+    if (q->world < 1 || q->world > 8) { set_error("vc_gemm_tap: peer world %d out of range", q->world); return VC_ERR_ARG; }
+    for (int i = 0; i <= q->world; ++i) pd.f0[i] = q->f0[i];
+    for (int i = 0; i < q->world; ++i) pd.dst[i] = q->dst[i];
+    d.peer = &pd;
+  }
   COUNT(1);
   return gemm_tap(d, ST(stream));
 }

@@ -49,6 +49,25 @@ __device__ __forceinline__ int fast_div(const FastDiv& f, int n) { return f.d ==
 #define VC_GEMM_DBG(p, bit) 0
 #endif
 
+// Multi-GPU layout switch fused into the epilogue (frame-sharded U-Net, parallel.py): instead of writing its output locally and
+// handing it to a separate exchange kernel, the GEMM that PRODUCES a tensor stores every 32-row x 32-column tile straight into the
+// receive buffer of the rank that owns those rows in the other layout -- TMA stores through the NVLink peer mapping, issued tile by
+// tile while the MMAs of the following tiles run.  mode 1: this rank's rows are (b, t_local, hw) ["frames"], destination
+// (b, t_all, hw_local) on rank hw / HWl ["sites"]; mode 2 the reverse.  Destination tensor maps are 3-D (C, HWl, b*t) with a
+// (32, 32, 1) box: a 32-row patch that runs past the end of a rank's hw range (or of a frame) is written as one clipped store per
+// segment -- every segment starts or ends on a range boundary, so the rows outside it fall outside the map and are dropped.
+static constexpr int GEMM_PEER_MAX = 4;
+struct GemmPeer {
+  int mode;              // 0: off
+  int P, me;
+  int wrap;              // producer rows form ONE slab-major matrix (Y == 1, Z == 1): the slab index is row / rps
+  int HW, HWl, T, Tl_me;
+  int rps;               // producer rows per slab (mode 1: HW, slab = b * Tl_me + t_local; mode 2: T * HWl, slab = b)
+  FastDiv div_hwl, div_rps, div_tl;
+  int f0[GEMM_PEER_MAX + 1];
+  CUtensorMap map[GEMM_PEER_MAX];
+};
+
 struct GemmParams {
   CUtensorMap tmap_a;
   CUtensorMap tmap_a2;
@@ -82,6 +101,7 @@ struct GemmParams {
   int gn_nchunks;          //   (4 pieces: first partial, two whole, last partial / whole) -- see gn_part_accumulate and norm.cu: gn_part_finalize_kernel
   int out_tma;           // fp16 output written by TMA stores from per-warp staging tiles (full-line, LSU-free)
   int vec_ok;            // rows are 32-byte aligned: the 256-bit epilogue path may be used
+  GemmPeer peer;         // output scattered to the ranks of the frame group (mode != 0: `out` itself is not written)
   int debug;             // profiling aid, only honoured by builds with -DVC_GEMM_DEBUG_BUILD=1 (env VC_GEMM_DEBUG): 1 = skip the MMAs
                          // (feed rate only), 2 = skip TMA (MMA rate only), 4 = skip the epilogue body; results are garbage then
 };
@@ -204,6 +224,35 @@ __device__ __forceinline__ EpiTile epi_tile(const GemmParams& p, int tile, int l
   return t;
 }
 
+// peer mode: the warp's staged 32 x 32 tile goes to the rank(s) owning its rows in the other layout (executed by one lane)
+__device__ __forceinline__ void peer_scatter32(const GemmParams& p, const EpiTile& t, int col0, const uint8_t* stage) {
+  const GemmPeer& g = p.peer;
+  int lin = t.wy * p.X + t.wx;                 // first row of the warp's patch inside its z-slab (patches are row-contiguous: host check)
+  int slab = t.wz;
+  if (g.wrap) { slab = fast_div(g.div_rps, lin); lin -= slab * g.rps; }
+  int rem = 32, i0 = 0;
+  while (rem > 0) {
+    if (lin >= g.rps) {
+      if (!g.wrap) break;                      // rows past the slab are tile padding
+      lin -= g.rps; ++slab;
+    }
+    int q, s, c2;
+    if (g.mode == 1) {
+      q = fast_div(g.div_hwl, lin); s = lin - q * g.HWl;
+      const int b = fast_div(g.div_tl, slab);
+      c2 = b * g.T + g.f0[g.me] + (slab - b * g.Tl_me);
+    } else {
+      const int tt = fast_div(g.div_hwl, lin); s = lin - tt * g.HWl;
+      q = 0;
+      while (q + 1 < g.P && tt >= g.f0[q + 1]) ++q;
+      c2 = slab * (g.f0[q + 1] - g.f0[q]) + tt - g.f0[q];
+    }
+    const int len = min(rem, g.HWl - s);
+    if (q < g.P) tma_store_3d(&g.map[q], stage, col0, s - i0, c2);
+    i0 += len; lin += len; rem -= len;
+  }
+}
+
 // store 32 consecutive output columns of this thread's row (fp16 or fp32), vector path or predicated scalar path
 __device__ __forceinline__ void epi_store32(const GemmParams& p, const EpiTile& t, int col0, int n_out, float (&f)[32], bool res_scalar,
                                             uint8_t* stage, int lane) {
@@ -224,7 +273,8 @@ __device__ __forceinline__ void epi_store32(const GemmParams& p, const EpiTile& 
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_4d(&p.tmap_out, stage, col0, t.wx, t.wy, t.wz);
+      if (p.peer.mode) peer_scatter32(p, t, col0, stage);
+      else tma_store_4d(&p.tmap_out, stage, col0, t.wx, t.wy, t.wz);
       tma_store_commit();
     }
     return;

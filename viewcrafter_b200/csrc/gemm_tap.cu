@@ -365,6 +365,39 @@ int gemm_tap(const GemmDesc& d, cudaStream_t stream) {
     VC_REQUIRE((d.ldo_y == 0 && d.ldo_z == 0) || (p.out_tma && !d.res && !d.ln_part),
                "gemm_tap: strided (ldo_y / ldo_z) outputs need the TMA-store epilogue (fp16, N %% 32 == 0) and no residual");
   }
+  if (d.peer && d.peer->mode) {
+    // layout switch fused into the epilogue: per-rank destination maps (gemm_common.cuh: GemmPeer)
+    const GemmPeerDesc& q = *d.peer;
+    VC_REQUIRE(q.mode == 1 || q.mode == 2, "gemm_tap: peer mode %d", q.mode);
+    VC_REQUIRE(q.world >= 2 && q.world <= GEMM_PEER_MAX && q.rank >= 0 && q.rank < q.world, "gemm_tap: peer scatter supports 2..%d ranks", GEMM_PEER_MAX);
+    VC_REQUIRE(p.out_tma && !d.geglu && !d.ln_part && d.ldo_y == 0 && d.ldo_z == 0, "gemm_tap: peer scatter needs the fp16 TMA-store epilogue");
+    VC_REQUIRE(q.HW % q.world == 0 && q.f0[0] == 0 && q.f0[q.world] == q.T && q.B >= 1, "gemm_tap: peer scatter: bad frame / site split");
+    GemmPeer& g = p.peer;
+    g.mode = q.mode; g.P = q.world; g.me = q.rank;
+    g.HW = q.HW; g.HWl = q.HW / q.world; g.T = q.T;
+    g.Tl_me = q.f0[q.rank + 1] - q.f0[q.rank];
+    for (int r = 0; r <= q.world; ++r) g.f0[r] = q.f0[r];
+    const long long rows = (long long)d.X * d.Y * d.Z;
+    g.rps = q.mode == 1 ? q.HW : q.T * g.HWl;
+    VC_REQUIRE(rows == (q.mode == 1 ? (long long)q.B * g.Tl_me * q.HW : (long long)q.B * q.T * g.HWl), "gemm_tap: peer scatter: %lld rows do not match the layout", rows);
+    // every 32-row patch of the epilogue must be a run of consecutive rows of its slab
+    const bool row_major_patches = d.Y == 1 || d.bx == d.X || (d.by == 1 && d.X % 32 == 0);
+    VC_REQUIRE(row_major_patches && (d.bx >= 32 || 32 % d.bx == 0), "gemm_tap: peer scatter: tile box %dx%d of a %dx%d image is not row-contiguous", d.bx, d.by, d.X, d.Y);
+    if (d.Y == 1 && d.Z == 1) { g.wrap = 1; }
+    else { g.wrap = 0; VC_REQUIRE((long long)d.X * d.Y == g.rps, "gemm_tap: peer scatter: slab of %d rows expected, tile geometry has %lld", g.rps, (long long)d.X * d.Y); }
+    g.div_hwl = make_fastdiv(g.HWl); g.div_rps = make_fastdiv(g.rps); g.div_tl = make_fastdiv(g.Tl_me > 0 ? g.Tl_me : 1);
+    for (int r = 0; r < q.world; ++r) {
+      VC_REQUIRE(q.dst[r] && (reinterpret_cast<uintptr_t>(q.dst[r]) & 15) == 0, "gemm_tap: peer scatter: destination %d missing / misaligned", r);
+      const int tl_r = q.f0[r + 1] - q.f0[r];
+      const __half* base = reinterpret_cast<const __half*>(q.dst[r]) + (q.mode == 2 ? (long long)q.rank * g.HWl * d.N : 0);
+      uint64_t dims[3] = {(uint64_t)d.N, (uint64_t)g.HWl, (uint64_t)(q.mode == 1 ? (long long)q.B * q.T : (long long)q.B * tl_r)};
+      if (dims[2] == 0) dims[2] = 1;              // a rank without frames: nothing is ever routed to it
+      uint64_t str[2] = {(uint64_t)d.N * 2, (uint64_t)(q.mode == 1 ? g.HWl : q.HW) * d.N * 2};
+      uint32_t box[3] = {32, 32, 1};
+      int rc = encode_tmap_f16(&g.map[r], base, 3, dims, str, box, 64);
+      if (rc) return rc;
+    }
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {

@@ -6,6 +6,15 @@
 
 namespace vc {
 
+// Output of a GEMM scattered to the receive buffers of the ranks of a frame group (layout switch fused into the epilogue, gemm_common.cuh)
+struct GemmPeerDesc {
+  int mode = 0;                 // 1: frames -> sites, 2: sites -> frames
+  int world = 1, rank = 0;
+  int B = 1, T = 1, HW = 1;     // batch elements on this rank, frames of the clip, pixels per frame
+  int f0[9] = {0};              // frame ranges of the ranks: rank q owns [f0[q], f0[q + 1])
+  void* dst[8] = {nullptr};     // rank q's receive buffer of the destination layout, as mapped into this process
+};
+
 struct GemmDesc {
   // A operand: fp16, logical (K channels, X, Y, Z) with row pitch lda elements; optional second K-slab a2.
   const __half* a = nullptr; int lda = 0;
@@ -39,6 +48,7 @@ struct GemmDesc {
   // gn_sub channels (10 or 8).  groupnorm_from_parts() turns them into per-group statistics and normalises in ONE pass.
   float* gn_part = nullptr;
   int gn_sub = 0;
+  const GemmPeerDesc* peer = nullptr;
 };
 int gemm_tap(const GemmDesc& d, cudaStream_t stream);
 
@@ -81,6 +91,8 @@ struct GnPartGeom {
   long long rb_per_sample = 0;
 };
 size_t groupnorm_parts_ws_bytes(int samples);
+int groupnorm_parts_to_partials(const GnPartGeom& g1, int C, int samples, float* partial_ws, size_t ws_bytes, int* splits_out,
+                                cudaStream_t stream);
 int groupnorm_from_parts(const __half* x1, int C1, const GnPartGeom& g1, const __half* x2, int C2, const GnPartGeom& g2, int samples,
                          long long rows_per_sample, const float* gamma, const float* beta, float eps, int silu, __half* out, float* ws,
                          size_t ws_bytes, cudaStream_t stream);

@@ -436,6 +436,23 @@ static int gn_part_plan(const GnPartGeom& g, int C_src, int samples, GnFin& f) {
   return VC_OK;
 }
 
+// The finalize step alone for ONE source: partial_ws[sample][split][64] = per-group (sum, sumsq) over the sample's rows ON THIS RANK,
+// from the producer's records -- the input of the cross-GPU statistics exchange (peer.cu: gn_peer_allreduce_kernel).
+int groupnorm_parts_to_partials(const GnPartGeom& g1, int C, int samples, float* partial_ws, size_t ws_bytes, int* splits_out,
+                                cudaStream_t stream) {
+  VC_REQUIRE(partial_ws && splits_out && C % 32 == 0, "groupnorm_parts_to_partials: bad args");
+  GnFin f;
+  int rc = gn_part_plan(g1, C, samples, f);
+  if (rc) return rc;
+  f.cg = C / 32; f.c_off = 0; f.split_off = 0; f.total_splits = f.nsplit;
+  VC_REQUIRE(f.cg % g1.sub == 0, "groupnorm_parts_to_partials: group width %d vs sub-group width %d", f.cg, g1.sub);
+  VC_REQUIRE(ws_bytes >= (size_t)samples * f.nsplit * 64 * sizeof(float), "groupnorm_parts_to_partials: workspace too small");
+  gn_part_finalize_kernel<<<dim3(f.nsplit, samples), f.cols * f.lanes, 0, stream>>>(f, partial_ws);
+  VC_CHECK_CUDA(cudaGetLastError());
+  *splits_out = f.nsplit;
+  return VC_OK;
+}
+
 int groupnorm_from_parts(const __half* x1, int C1, const GnPartGeom& g1, const __half* x2, int C2, const GnPartGeom& g2, int samples,
                          long long rows_per_sample, const float* gamma, const float* beta, float eps, int silu, __half* out, float* ws,
                          size_t ws_bytes, cudaStream_t stream) {

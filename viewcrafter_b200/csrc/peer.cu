@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(512) peer_exchange_kernel(const __grid_constan
 }
 
 // (sum, sumsq) per group of this rank's rows -> every rank's slots -> cur_stats[B][world][64]
+// B == 0: the signal / wait step alone -- the completion barrier of a layout switch that a GEMM's epilogue performed (its TMA stores to
+// the peers are complete when that kernel ends; this kernel, next in the stream, fences and publishes the sequence number).
 __global__ void __launch_bounds__(128) gn_peer_allreduce_kernel(const float* __restrict__ partial, int splits, int B, const __grid_constant__ PeerCommDev pc) {
   const int tid = threadIdx.x;
   float mine = 0.f;
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(128) gn_peer_allreduce_kernel(const float* __r
     const int b = tid >> 6, t = tid & 63;
     for (int sp = 0; sp < splits; ++sp) mine += partial[((long long)b * splits + sp) * 64 + t];
   }
-  peer_finish(pc, B, true, mine, tid);
+  peer_finish(pc, B, B > 0, mine, tid);
 }
 
 }  // namespace vc
@@ -324,6 +326,30 @@ int vc_peer_groupnorm_stats(const vc_peer_comm* c, const void* x, int32_t C, int
                                 &splits, reinterpret_cast<cudaStream_t>(stream));
   if (rc) return rc;
   gn_peer_allreduce_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float*>(ws), splits, samples, d);
+  VC_CHECK_CUDA(cudaGetLastError());
+  return VC_OK;
+}
+
+/* completion of a layout switch performed by a GEMM epilogue (vc_gemm_desc.peer): the per-group sums of the tensor just written -- from the
+ * GEMM's gn_part records, summed over this rank's rows -- are published to every rank and the ranks rendezvous; afterwards every peer's
+ * tiles have landed in this rank's receive buffer and cur_stats holds the [samples][world][32][2] sums for vc_groupnorm_apply_parts.
+ * geom == NULL: rendezvous only (sites -> frames: no cross-rank statistics follow). */
+int vc_peer_finish_scatter(const vc_peer_comm* c, const vc_gn_part_geom* geom, int32_t C, int32_t samples, void* ws, size_t ws_bytes, void* stream) {
+  using namespace vc;
+  PeerCommDev d;
+  int rc = to_dev(c, d);
+  if (rc) return rc;
+  int splits = 0, B = 0;
+  if (geom) {
+    VC_REQUIRE(samples >= 1 && samples <= c->Bmax, "peer_finish_scatter: samples %d exceed Bmax %d", samples, c->Bmax);
+    GnPartGeom g;
+    g.part = geom->part; g.n_chunks = geom->n_chunks; g.sub = geom->sub; g.rb_per_z = geom->rb_per_z; g.samples_per_z = geom->samples_per_z;
+    g.rb_per_sample = geom->rb_per_sample;
+    rc = groupnorm_parts_to_partials(g, C, samples, reinterpret_cast<float*>(ws), ws_bytes, &splits, reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    B = samples;
+  }
+  gn_peer_allreduce_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float*>(ws), splits, B, d);
   VC_CHECK_CUDA(cudaGetLastError());
   return VC_OK;
 }

@@ -209,16 +209,21 @@ gn_from_parts_calls = 0      # GroupNorms that took their statistics from a prod
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
            geglu: bool = False, out: Optional[torch.Tensor] = None, out_f32: bool = False,
-           x2: Optional[torch.Tensor] = None, ln=None, ln_out: bool = False, gn_out: bool = False):
+           x2: Optional[torch.Tensor] = None, ln=None, ln_out: bool = False, gn_out: bool = False, peer=None):
     """y = [x|x2] @ w.T (+bias) (GEGLU) (+res).  x: [M,K1] fp16 (row pitch = x.stride(0)), w: [N,K] fp16.
     ln = (stats [M,2] fp32 from layernorm_stats(x), colsum [N] fp32): LayerNorm folded into the epilogue (fold_layernorm).
     ln_out: also return the LayerNorm statistics [M,2] (mean, rstd) of y -- y feeds a LayerNorm next (attention.py:283-292); the
     epilogue leaves per-32-column partial sums of the rows it is writing and a tiny kernel finishes them, so y is not re-read.
-    gn_out: y feeds a GroupNorm next: leave its partial sums (GnPart, attached to y as ``y._vc_gn``; see groupnorm())."""
+    gn_out: y feeds a GroupNorm next: leave its partial sums (GnPart, attached to y as ``y._vc_gn``; see groupnorm()).
+    peer: a parallel.PeerFrameComm.scatter_plan(): the epilogue stores y into the other ranks' receive buffers (multi-GPU layout switch
+    fused into the GEMM); returns the switched tensor."""
     _chk16(x, "linear.x"); _chk16(w, "linear.w")
     M, K1 = x.shape
     N, K = w.shape
     n_out = N // 2 if geglu else N
+    if peer is not None:
+        assert out is None and not geglu and not out_f32 and not ln_out and M == peer.rows_in and N == peer.C
+        out = x.new_empty((0, N))                      # placeholder: the descriptor's output is set by the plan
     if out is None:
         out = torch.empty((M, n_out), device=x.device, dtype=torch.float32 if out_f32 else torch.float16)
     d = GemmDesc()
@@ -245,6 +250,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         assert stats.shape == (M, 2) and stats.dtype == torch.float32 and stats.is_contiguous()
         assert colsum.shape == (N,) and colsum.dtype == torch.float32 and colsum.is_contiguous()
         d.ln_stats, d.ln_colsum = stats.data_ptr(), colsum.data_ptr()
+    if peer is not None:
+        return _peer_gemm(d, peer, x.device)
     out._vc_gn = _gn_part_alloc(d, x.device) if (_want_gn(gn_out, -(-K // 64)) and not out_f32 and not geglu and out.is_contiguous()) else None
     if not ln_out:
         _gemm(d)
@@ -260,6 +267,14 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out, st
 
 
+def _peer_gemm(d: GemmDesc, peer, device):
+    """Launch a GEMM whose epilogue performs a multi-GPU layout switch (parallel._ScatterPlan) and complete the switch."""
+    peer.attach(d)
+    part = _gn_part_alloc(d, device) if peer.to_sites else None      # frames -> sites: the cross-rank GroupNorm sums come from these records
+    _gemm(d)
+    return peer.finish(part)
+
+
 def _conv_box(H: int, W: int):
     # widths that divide 128 pack 128/W image rows into one 128-pixel tile; every other width falls back to one
     # (partially filled, TMA zero-filled) tile per 128-pixel row segment -- correct for any W, full speed for the
@@ -271,13 +286,16 @@ def _conv_box(H: int, W: int):
 
 def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w9: torch.Tensor, bias: Optional[torch.Tensor] = None,
             res: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None, bias_z_div: int = 0,
-            out_f32: bool = False, out: Optional[torch.Tensor] = None, gn_out: bool = False) -> torch.Tensor:
-    """3x3 / stride 1 / pad 1 convolution on [frames*H*W, Cin] rows; w9 = pack_conv3x3(weight).  gn_out: see linear()."""
+            out_f32: bool = False, out: Optional[torch.Tensor] = None, gn_out: bool = False, peer=None) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution on [frames*H*W, Cin] rows; w9 = pack_conv3x3(weight).  gn_out / peer: see linear()."""
     _chk16(x, "conv3x3.x"); _chk16(w9, "conv3x3.w")
     M, K1 = x.shape
     assert M == frames * H * W, (M, frames, H, W)
     K = w9.shape[1]
     N = w9.shape[0] // 9
+    if peer is not None:
+        assert out is None and not out_f32 and M == peer.rows_in and N == peer.C
+        out = x.new_empty((0, N))
     if out is None:
         out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else torch.float16)
     d = GemmDesc()
@@ -301,6 +319,8 @@ def conv3x3(x: torch.Tensor, frames: int, H: int, W: int, w9: torch.Tensor, bias
     d.bias, d.bias_z_div = _ptr(bias), bias_z_div
     if res is not None:
         d.res, d.ldr = res.data_ptr(), res.stride(0)
+    if peer is not None:
+        return _peer_gemm(d, peer, x.device)
     out._vc_gn = _gn_part_alloc(d, x.device) if (_want_gn(gn_out, 9 * -(-K // 64)) and not out_f32 and out.is_contiguous()) else None
     _gemm(d)
     return out
@@ -362,13 +382,15 @@ def upconv3x3(x: torch.Tensor, frames: int, H: int, W: int, packs, bias: Optiona
 
 
 def conv_temporal(x: torch.Tensor, B: int, T: int, HW: int, w3: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                  res: Optional[torch.Tensor] = None, gn_out: bool = False) -> torch.Tensor:
+                  res: Optional[torch.Tensor] = None, gn_out: bool = False, peer=None) -> torch.Tensor:
     """Conv3d (3,1,1) pad (1,0,0) on [(B T) HW, C] rows: three row-shifted GEMM taps; batches never mix (Z = B).  gn_out: see linear()."""
     _chk16(x, "conv_temporal.x")
     M, K = x.shape
     assert M == B * T * HW
     N = w3.shape[0] // 3
-    out = torch.empty((M, N), device=x.device, dtype=torch.float16)
+    if peer is not None:
+        assert M == peer.rows_in and N == peer.C
+    out = torch.empty((0 if peer is not None else M, N), device=x.device, dtype=torch.float16)
     d = GemmDesc()
     d.a, d.lda = x.data_ptr(), x.stride(0)
     d.X, d.Y, d.Z, d.bx, d.by = T * HW, 1, B, 128, 1
@@ -380,6 +402,8 @@ def conv_temporal(x: torch.Tensor, B: int, T: int, HW: int, w3: torch.Tensor, bi
     d.bias = _ptr(bias)
     if res is not None:
         d.res, d.ldr = res.data_ptr(), res.stride(0)
+    if peer is not None:
+        return _peer_gemm(d, peer, x.device)
     out._vc_gn = _gn_part_alloc(d, x.device) if _want_gn(gn_out, 3 * -(-K // 64)) else None
     _gemm(d)
     return out

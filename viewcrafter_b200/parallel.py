@@ -10,6 +10,7 @@ level), which is perfectly balanced.  The two layouts are exchanged with ONE une
 """
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
@@ -111,6 +112,10 @@ class FrameComm:
     def all_reduce(self, t: torch.Tensor):
         self.dist.all_reduce(t, group=self.group)
 
+    def scatter_plan(self, to_sites: bool, B: int, HW: int, Cc: int):
+        """No fused switch with NCCL collectives (see PeerFrameComm.scatter_plan): the caller switches separately."""
+        return None
+
     def groupnorm5d(self, x, B, gamma, beta, eps, silu, stat_rows, fresh: bool):
         """GroupNorm(32) of a site-layout tensor whose statistics span the ranks of the group.  `fresh`: x is the tensor the
         last to_sites() returned (the peer-memory path already holds its statistics)."""
@@ -167,6 +172,8 @@ class PeerFrameComm(FrameComm):
             c.stats_slots[q] = slot_ptrs[q]
         self.c = c
         self._stats_of = None      # data_ptr of the tensor whose statistics cur_stats holds
+        self.fused = os.environ.get("VC_PEER_FUSED", "1") != "0"     # layout switches inside the producing GEMM's epilogue (scatter_plan)
+        self.fused_switches = 0
 
     # -- CUDA IPC plumbing (setup only) -------------------------------------------------------------
     class _Raw:
@@ -260,6 +267,21 @@ class PeerFrameComm(FrameComm):
                    "vc_groupnorm_apply_parts")
         return out
 
+    # -- layout switch fused into the producing GEMM's epilogue ------------------------------------------------
+    def scatter_plan(self, to_sites: bool, B: int, HW: int, Cc: int):
+        """A plan for ops.conv3x3 / conv_temporal / linear(peer=plan): the GEMM that PRODUCES the tensor stores its output tiles straight
+        into the receive buffers of the ranks that own them in the other layout (TMA stores over NVLink, overlapped with its MMAs), and
+        a one-CTA kernel completes the switch (rendezvous + the cross-rank GroupNorm sums from the GEMM's own partial sums).  Replaces
+        GEMM -> local tensor -> peer_exchange_kernel.  None when the shape is not supported (the caller then switches separately)."""
+        P = self.world
+        if not self.fused or P > 4 or HW % P != 0 or Cc % 32 != 0 or B > self.bmax:
+            return None
+        # the decision must be the same on every rank of the group: it depends on ALL frame ranges, not on this rank's
+        for f0, f1 in self.ranges:
+            if f1 - f0 == 0 or (B > 1 and ((f1 - f0) * HW) % 128 != 0):
+                return None
+        return _ScatterPlan(self, to_sites, B, HW, Cc)
+
     def owns(self, t: torch.Tensor) -> bool:
         """True if `t` is a view of one of the reusable receive buffers."""
         p = t.data_ptr()
@@ -272,6 +294,59 @@ class PeerFrameComm(FrameComm):
         for p in self._own_ptrs:
             self.lib.vc_peer_free(p)
         self._peer_ptrs, self._own_ptrs, self._bufs = [], [], {}
+
+
+class _ScatterPlan:
+    """One fused layout switch (PeerFrameComm.scatter_plan): attach() fills the GEMM descriptor, finish() completes the switch."""
+
+    def __init__(self, comm: "PeerFrameComm", to_sites: bool, B: int, HW: int, Cc: int):
+        from . import _lib
+        self.comm, self.to_sites, self.B, self.HW, self.C = comm, to_sites, B, HW, Cc
+        P = comm.world
+        HWl = HW // P
+        Tl = comm.ranges[comm.rank][1] - comm.ranges[comm.rank][0]
+        tmax = max(f1 - f0 for f0, f1 in comm.ranges)
+        self.rows_in = B * Tl * HW if to_sites else B * comm.T * HWl
+        self.rows_out = B * comm.T * HWl if to_sites else B * Tl * HW
+        cap = B * (comm.T * HWl if to_sites else tmax * HW) * Cc            # same on every rank (as in _exchange)
+        self.own, ptrs, _ = comm._buffer("sites" if to_sites else "frames", cap)
+        g = _lib.GemmPeer()
+        g.mode, g.world, g.rank, g.B, g.T, g.HW = (1 if to_sites else 2), P, comm.rank, B, comm.T, HW
+        for q in range(P):
+            g.f0[q] = comm.ranges[q][0]
+            g.dst[q] = ptrs[q]
+        g.f0[P] = comm.T
+        self.g = g
+
+    def attach(self, d):
+        """Route the output of the GEMM described by `d` (its `out` must not be set by the caller)."""
+        import ctypes as C
+        d.peer = C.addressof(self.g)
+        d.out, d.ldo = self.own.data_ptr(), self.C            # never written: the epilogue stores through the per-rank maps
+
+    def finish(self, gn_part):
+        """Rendezvous (+ cross-rank GroupNorm sums for frames -> sites).  Returns the switched tensor (a view of the receive buffer)."""
+        import ctypes as C
+        from . import _lib
+        comm = self.comm
+        geom = None
+        if self.to_sites and gn_part is not None:
+            Tl = comm.ranges[comm.rank][1] - comm.ranges[comm.rank][0]
+            geom = gn_part.geom(self.B, Tl * self.HW)
+        # geom None (channel counts whose GroupNorm groups are not multiples of the 10-channel sub-groups, e.g. reduced test widths):
+        # rendezvous only; groupnorm5d() then takes its statistics with a pass over the received tensor (vc_peer_groupnorm_stats)
+        e0 = comm._mark()
+        _lib.check(comm.lib.vc_peer_finish_scatter(C.byref(comm.c), C.byref(geom) if geom is not None else None, self.C, self.B, comm.ws.data_ptr(),
+                                                   comm.ws.numel() * 4, torch.cuda.current_stream().cuda_stream), "vc_peer_finish_scatter")
+        comm._done(e0)
+        P = comm.world
+        sent = self.rows_in * self.C * 2
+        Tl = comm.ranges[comm.rank][1] - comm.ranges[comm.rank][0]
+        comm.bytes_moved += sent * (P - 1) // P if self.to_sites else sent - self.B * Tl * (self.HW // P) * self.C * 2
+        comm.fused_switches += 1
+        out = self.own[:self.rows_out * self.C].view(self.rows_out, self.C)
+        comm._stats_of = out.data_ptr() if geom is not None else None
+        return out
 
 
 class CfgComm:

@@ -370,15 +370,21 @@ class UNetModel(nn.Module):
             xs = ops.linear(h, P["skip_w"], bias=P["skip_b"], x2=skip)
         else:
             xs = h
-        h2 = ops.conv3x3(b, BT, H, W, P["w2"], bias=P["b2"], res=xs, gn_out=True)
+        # multi-GPU: the frames -> sites switch the TemporalConvBlock needs is performed by conv2's own epilogue when the peer-memory path
+        # offers a plan (its output tiles go straight to the owning ranks), and the switch back by the last temporal conv's
+        to_s = comm.scatter_plan(True, B, HW, P["w2"].shape[0] // 9) if (comm and "tconv" in P) else None
+        h2 = ops.conv3x3(b, BT, H, W, P["w2"], bias=P["b2"], res=xs, gn_out=True, peer=to_s)
         if "tconv" in P:
             # TemporalConvBlock: needs every frame of a pixel -> (optionally) transpose frames<->sites across GPUs
-            t = ident = comm.to_sites(h2, B, HW) if comm else h2
+            t = ident = h2 if to_s is not None else (comm.to_sites(h2, B, HW) if comm else h2)
             Tg, HWl = (comm.T, HW // comm.world) if comm else (T, HW)
+            n_tc, to_f = len(P["tconv"]), None
             for i, (g, be, w3, b3) in enumerate(P["tconv"]):
                 t = UNetModel._gn5d(t, B, g, be, 1e-5, True, comm, Tg * HW, fresh=(i == 0))   # statistics over (C/32, T, H, W)
-                t = ops.conv_temporal(t, B, Tg, HWl, w3, bias=b3, res=ident if i == 3 else None, gn_out=comm is None)
-            h2 = comm.to_frames(t, B, HW) if comm else t
+                last = i == n_tc - 1
+                to_f = comm.scatter_plan(False, B, HW, w3.shape[0] // 3) if (comm and last) else None
+                t = ops.conv_temporal(t, B, Tg, HWl, w3, bias=b3, res=ident if last else None, gn_out=comm is None, peer=to_f)
+            h2 = t if to_f is not None else (comm.to_frames(t, B, HW) if comm else t)
         return h2
 
     @staticmethod
@@ -390,7 +396,7 @@ class UNetModel(nn.Module):
         return comm.groupnorm5d(x, B, gamma, beta, eps, silu, stat_rows, fresh)
 
     @staticmethod
-    def _spatial_tf(P, h, ctx, B, T, H, W, expand=False):
+    def _spatial_tf(P, h, ctx, B, T, H, W, expand=False, out_plan=None):
         """expand=True (shared CFG prefix): `h` holds ONE batch element that is identical for the B=2
         conditional / unconditional branches; everything up to and including attn1 of the first block does not see the
         context, so it runs once and is duplicated right before the first cross-attention."""
@@ -427,14 +433,16 @@ class UNetModel(nn.Module):
             last = Q is P["blocks"][-1]
             x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x, ln_out=fold and not last)
             x, st = x if (fold and not last) else (x, None)
-        return ops.linear(x, P["out_w"], bias=P["out_b"], res=h, gn_out=True)
+        # out_plan (multi-GPU): proj_out's epilogue performs the frames -> sites switch the TemporalTransformer that follows needs
+        return ops.linear(x, P["out_w"], bias=P["out_b"], res=h, gn_out=True, peer=out_plan)
 
     @staticmethod
-    def _temporal_tf(P, h, B, T, H, W, comm=None):
+    def _temporal_tf(P, h, B, T, H, W, comm=None, pre_sites=False):
+        """pre_sites: `h` already is in the site layout (the producing GEMM switched it, see _spatial_tf(out_plan=...))."""
         HW, heads = H * W, P["heads"]
         C = heads * 64
         Tg, HWl = (comm.T, HW // comm.world) if comm else (T, HW)
-        t_in = comm.to_sites(h, B, HW) if comm else h
+        t_in = h if pre_sites else (comm.to_sites(h, B, HW) if comm else h)
         fold = _LN_FOLD
         x = ops.linear(UNetModel._gn5d(t_in, B, *P["gn"], 1e-6, False, comm, Tg * HW, fresh=True), P["in_w"], bias=P["in_b"], ln_out=fold)
         x, st = x if fold else (x, None)
@@ -451,19 +459,25 @@ class UNetModel(nn.Module):
             last = Q is P["blocks"][-1]
             x = ops.linear(g, Q["ff2_w"], bias=Q["ff2_b"], res=x, ln_out=fold and not last)
             x, st = x if (fold and not last) else (x, None)
-        out = ops.linear(x, P["out_w"], bias=P["out_b"], res=t_in, gn_out=comm is None)
-        return comm.to_frames(out, B, HW) if comm else out
+        to_f = comm.scatter_plan(False, B, HW, P["out_w"].shape[0]) if comm else None
+        out = ops.linear(x, P["out_w"], bias=P["out_b"], res=t_in, gn_out=comm is None, peer=to_f)
+        return out if to_f is not None else (comm.to_frames(out, B, HW) if comm else out)
 
     def _run_stage(self, stage, h, skip, emb, ctx, B, T, H, W):
-        for P in stage:
+        comm, pre_sites = self._comm, False
+        for idx, P in enumerate(stage):
             k = P["kind"]
             if k == "R":
-                h = self._res(P, h, skip, emb, B, T, H, W, self._comm)
+                h = self._res(P, h, skip, emb, B, T, H, W, comm)
                 skip = None
             elif k == "S":
-                h = self._spatial_tf(P, h, ctx, B, T, H, W)
+                nxt = stage[idx + 1]["kind"] if idx + 1 < len(stage) else None
+                plan = comm.scatter_plan(True, B, H * W, P["out_w"].shape[0]) if (comm and nxt == "T") else None
+                h = self._spatial_tf(P, h, ctx, B, T, H, W, out_plan=plan)
+                pre_sites = plan is not None
             elif k == "T":
-                h = self._temporal_tf(P, h, B, T, H, W, self._comm)
+                h = self._temporal_tf(P, h, B, T, H, W, comm, pre_sites=pre_sites)
+                pre_sites = False
             elif k == "D":
                 cols, H, W = ops.im2col_s2(h, B * T, H, W)
                 h = ops.linear(cols, P["w"], bias=P["b"], gn_out=True)
