@@ -1,0 +1,73 @@
+"""torchrun target (N = 2 or 4): the layout switches fused into GEMM epilogues at the REAL level shapes of the 25x72x128 workload (CTA-pair
+kernels, 7-13 frames per rank), each checked bit for bit against GEMM + separate exchange kernel, with a synchronize + print after every
+case so that a device fault is attributable.  VC_PROBE_LEVELS=0,1,2,3 selects the levels (3 = 9x16: patches straddle ranks and frames)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+from viewcrafter_b200 import ops, parallel
+
+comm = parallel._make_comm(dist, rank, world, None, torch.device("cuda", local), True)
+assert isinstance(comm, parallel.PeerFrameComm), "peer-memory comm unavailable"
+comm.fused = "1"
+T = 25
+f0, f1 = comm.bind(T)
+Tl = f1 - f0
+levels = [int(v) for v in os.environ.get("VC_PROBE_LEVELS", "0,1,2,3").split(",")]
+shapes = {0: (72, 128, 320), 1: (36, 64, 640), 2: (18, 32, 1280), 3: (9, 16, 1280)}
+ok = True
+g = torch.Generator().manual_seed(7 + rank)
+for lv in levels:
+    H, W, C = shapes[lv]
+    HW, HWl, B = H * W, H * W // world, 1
+    x = (torch.randn(B * Tl * HW, C, generator=g) * 0.7).half().cuda()
+    r = (torch.randn(B * Tl * HW, C, generator=g) * 0.5).half().cuda()
+    w9 = (torch.randn(9 * C, C, generator=g) * (1.0 / (3 * C ** 0.5))).half().cuda()
+    w1 = (torch.randn(C, C, generator=g) * (1.0 / C ** 0.5)).half().cuda()
+    w3 = (torch.randn(3 * C, C, generator=g) * (1.0 / (1.7 * C ** 0.5))).half().cuda()
+    bias = (torch.randn(C, generator=g) * 0.1).cuda()
+    gam, bet = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.1
+
+    def step(name, fn):
+        global ok
+        try:
+            res = fn()
+            torch.cuda.synchronize()
+        except Exception as e:
+            print(f"[rank {rank}] level {lv} {name}: EXCEPTION {str(e)[:200]}", flush=True)
+            ok = False
+            raise
+        print(f"[rank {rank}] level {lv} ({H}x{W}, C={C}, HWl={HWl}, Tl={Tl}) {name}: {res}", flush=True)
+        ok = ok and bool(res)
+
+    ref = comm.to_sites(ops.conv3x3(x, B * Tl, H, W, w9, bias=bias, res=r), B, HW).clone()
+    torch.cuda.synchronize()
+    holder = {}
+
+    def conv_sites():
+        holder["s"] = ops.conv3x3(x, B * Tl, H, W, w9, bias=bias, res=r, peer=comm.scatter_plan(True, B, HW, C))
+        return torch.equal(holder["s"], ref)
+    step("conv3x3 -> sites", conv_sites)
+
+    def gn_after():
+        n_f = comm.groupnorm5d(holder["s"], B, gam, bet, 1e-5, True, T * HW, True)
+        n_r = comm.groupnorm5d(ref.clone(), B, gam, bet, 1e-5, True, T * HW, False)
+        return float((n_f.float() - n_r.float()).abs().max()) < 4e-3
+    step("GroupNorm with the GEMM's sums", gn_after)
+    ref2 = comm.to_sites(ops.linear(x, w1, bias=bias, res=r), B, HW).clone()
+    step("linear -> sites", lambda: torch.equal(ops.linear(x, w1, bias=bias, res=r, peer=comm.scatter_plan(True, B, HW, C)), ref2))
+    a_s = ref2.clone()
+    ref3 = comm.to_frames(ops.conv_temporal(a_s, B, T, HWl, w3, bias=bias, res=a_s), B, HW).clone()
+    step("temporal conv -> frames", lambda: torch.equal(ops.conv_temporal(a_s, B, T, HWl, w3, bias=bias, res=a_s, peer=comm.scatter_plan(False, B, HW, C)), ref3))
+    ref4 = comm.to_frames(ops.linear(a_s, w1, bias=bias, res=a_s), B, HW).clone()
+    step("linear -> frames", lambda: torch.equal(ops.linear(a_s, w1, bias=bias, res=a_s, peer=comm.scatter_plan(False, B, HW, C)), ref4))
+flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("PEER_FUSED_PROBE_OK" if float(flag) > 0 else "PEER_FUSED_PROBE_FAILED", "levels", levels, flush=True)
+torch.cuda.synchronize(); dist.barrier()
+os._exit(0 if float(flag) > 0 else 1)

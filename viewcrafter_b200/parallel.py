@@ -172,7 +172,9 @@ class PeerFrameComm(FrameComm):
             c.stats_slots[q] = slot_ptrs[q]
         self.c = c
         self._stats_of = None      # data_ptr of the tensor whose statistics cur_stats holds
-        self.fused = os.environ.get("VC_PEER_FUSED", "1") != "0"     # layout switches inside the producing GEMM's epilogue (scatter_plan)
+        # layout switches inside the producing GEMM's epilogue (scatter_plan): "0" off, "1" every supported shape, "aligned" (default) only
+        # shapes whose 32-row epilogue patches never straddle a rank's pixel range or a frame (H*W/P and H*W multiples of 32)
+        self.fused = os.environ.get("VC_PEER_FUSED", "aligned")
         self.fused_switches = 0
 
     # -- CUDA IPC plumbing (setup only) -------------------------------------------------------------
@@ -274,7 +276,9 @@ class PeerFrameComm(FrameComm):
         a one-CTA kernel completes the switch (rendezvous + the cross-rank GroupNorm sums from the GEMM's own partial sums).  Replaces
         GEMM -> local tensor -> peer_exchange_kernel.  None when the shape is not supported (the caller then switches separately)."""
         P = self.world
-        if not self.fused or P > 4 or HW % P != 0 or Cc % 32 != 0 or B > self.bmax:
+        if self.fused == "0" or P > 4 or HW % P != 0 or Cc % 32 != 0 or B > self.bmax:
+            return None
+        if self.fused == "aligned" and ((HW // P) % 32 != 0 or HW % 32 != 0):
             return None
         # the decision must be the same on every rank of the group: it depends on ALL frame ranges, not on this rank's
         for f0, f1 in self.ranges:
