@@ -32,6 +32,13 @@ for lv in levels:
     bias = (torch.randn(C, generator=g) * 0.1).cuda()
     gam, bet = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.1
 
+    def poison(to_sites):
+        """overwrite this rank's receive buffer so that a tile the fused GEMM fails to deliver cannot pass as the stale reference"""
+        ent = comm._bufs.get("sites" if to_sites else "frames")
+        if ent is not None:
+            ent[0].fill_(-7.0)
+        torch.cuda.synchronize(); dist.barrier()
+
     def step(name, fn):
         global ok
         try:
@@ -49,6 +56,7 @@ for lv in levels:
     holder = {}
 
     def conv_sites():
+        poison(True)
         holder["s"] = ops.conv3x3(x, B * Tl, H, W, w9, bias=bias, res=r, peer=comm.scatter_plan(True, B, HW, C))
         return torch.equal(holder["s"], ref)
     step("conv3x3 -> sites", conv_sites)
@@ -59,12 +67,12 @@ for lv in levels:
         return float((n_f.float() - n_r.float()).abs().max()) < 4e-3
     step("GroupNorm with the GEMM's sums", gn_after)
     ref2 = comm.to_sites(ops.linear(x, w1, bias=bias, res=r), B, HW).clone()
-    step("linear -> sites", lambda: torch.equal(ops.linear(x, w1, bias=bias, res=r, peer=comm.scatter_plan(True, B, HW, C)), ref2))
+    step("linear -> sites", lambda: (poison(True), torch.equal(ops.linear(x, w1, bias=bias, res=r, peer=comm.scatter_plan(True, B, HW, C)), ref2))[1])
     a_s = ref2.clone()
     ref3 = comm.to_frames(ops.conv_temporal(a_s, B, T, HWl, w3, bias=bias, res=a_s), B, HW).clone()
-    step("temporal conv -> frames", lambda: torch.equal(ops.conv_temporal(a_s, B, T, HWl, w3, bias=bias, res=a_s, peer=comm.scatter_plan(False, B, HW, C)), ref3))
+    step("temporal conv -> frames", lambda: (poison(False), torch.equal(ops.conv_temporal(a_s, B, T, HWl, w3, bias=bias, res=a_s, peer=comm.scatter_plan(False, B, HW, C)), ref3))[1])
     ref4 = comm.to_frames(ops.linear(a_s, w1, bias=bias, res=a_s), B, HW).clone()
-    step("linear -> frames", lambda: torch.equal(ops.linear(a_s, w1, bias=bias, res=a_s, peer=comm.scatter_plan(False, B, HW, C)), ref4))
+    step("linear -> frames", lambda: (poison(False), torch.equal(ops.linear(a_s, w1, bias=bias, res=a_s, peer=comm.scatter_plan(False, B, HW, C)), ref4))[1])
 flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -227,6 +227,7 @@ __device__ __forceinline__ EpiTile epi_tile(const GemmParams& p, int tile, int l
 // peer mode: the warp's staged 32 x 32 tile goes to the rank(s) owning its rows in the other layout (executed by one lane)
 __device__ __forceinline__ void peer_scatter32(const GemmParams& p, const EpiTile& t, int col0, const uint8_t* stage) {
   const GemmPeer& g = p.peer;
+  if (t.wz >= p.Z) return;                     // the padding m-tile of an odd tile count (CTA pairs): its coordinates wrap to (x0 = 0, z = Z)
   int lin = t.wy * p.X + t.wx;                 // first row of the warp's patch inside its z-slab (patches are row-contiguous: host check)
   int slab = t.wz;
   if (g.wrap) { slab = fast_div(g.div_rps, lin); lin -= slab * g.rps; }
