@@ -27,9 +27,12 @@ except Exception as e:
 PY
   stamp bench_fused
 fi
+# NOTE: a bare `wait` also waits for the `tee` of the exec redirection above and never returns (this cost the rest of the round's GPU budget):
+# wait for the job's PID only
 ( CUDA_VISIBLE_DEVICES=1 timeout 400 python -m pytest tests -m gpu -q -rf --deselect tests/test_multigpu_gpu.py > $O/d3_pytest.log 2>&1; echo "pytest rc=$?" >> $O/d3_pytest.log ) &
+PYTEST_PID=$!
 CUDA_VISIBLE_DEVICES=0 timeout 400 python bench.py --steps 6 --warmup 3 > $O/d3_bench_n1_full.json 2> $O/d3_bench_n1_full.err; echo "bench N=1 full rc=$? $(cut -c1-160 $O/d3_bench_n1_full.json)"
-wait
+wait $PYTEST_PID
 tail -6 $O/d3_pytest.log
 python - <<PY
 import json

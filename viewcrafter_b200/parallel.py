@@ -175,6 +175,9 @@ class PeerFrameComm(FrameComm):
         # layout switches inside the producing GEMM's epilogue (scatter_plan): "0" off, "1" every supported shape, "aligned" (default) only
         # shapes whose 32-row epilogue patches never straddle a rank's pixel range or a frame (H*W/P and H*W multiples of 32)
         self.fused = os.environ.get("VC_PEER_FUSED", "aligned")
+        # ... and only for frame groups of at most this many ranks: 2 is what was validated on hardware (round 2: probe at the real level shapes,
+        # sharded forward vs single GPU, graph replay, bench); the kernels handle up to 4 ranks (VC_PEER_FUSED_MAXP=4)
+        self.fused_max_p = int(os.environ.get("VC_PEER_FUSED_MAXP", "2"))
         self.fused_switches = 0
 
     # -- CUDA IPC plumbing (setup only) -------------------------------------------------------------
@@ -276,7 +279,7 @@ class PeerFrameComm(FrameComm):
         a one-CTA kernel completes the switch (rendezvous + the cross-rank GroupNorm sums from the GEMM's own partial sums).  Replaces
         GEMM -> local tensor -> peer_exchange_kernel.  None when the shape is not supported (the caller then switches separately)."""
         P = self.world
-        if self.fused == "0" or P > 4 or HW % P != 0 or Cc % 32 != 0 or B > self.bmax:
+        if self.fused == "0" or P > min(4, self.fused_max_p) or HW % P != 0 or Cc % 32 != 0 or B > self.bmax:
             return None
         if self.fused == "aligned" and ((HW // P) % 32 != 0 or HW % 32 != 0):
             return None
