@@ -350,3 +350,41 @@ def test_upsample_conv_parity_decomposition_equals_interpolate_then_conv():
     ref16 = F.conv2d(F.interpolate(x.half().float(), scale_factor=2, mode="nearest"), w, b, padding=1)
     assert float((y - ref16).abs().max()) < 2e-2, float((y - ref16).abs().max())
     assert float((y - ref).abs().max()) < 3e-2
+
+
+def test_groupnorm_partial_sum_geometry_of_every_producer_consumer_pair():
+    """ops.GnPart.geom: which 32-row blocks of a producer's gn_part records make up sample s of the consuming GroupNorm
+    (base = (s // samples_per_z) * rb_per_z + (s % samples_per_z) * rb_per_sample), or None when samples do not fall on block boundaries."""
+    from viewcrafter_b200 import ops
+    part = torch.zeros(8)
+
+    def gp(X, Y, Z, bx, by, N=320):
+        tx, ty = -(-X // bx), -(-Y // by)
+        return ops.GnPart(part, N // 32, 10, tx * ty * 4, X * Y, Z, linear=(by == 1 and bx == 128 and (Y == 1 or X % 128 == 0)))
+
+    def tup(g):
+        return None if g is None else (g.rb_per_z, g.samples_per_z, g.rb_per_sample)
+
+    T, B = 25, 2
+    # 3x3 conv at 72x128 (one 128-pixel tile per image row): per-frame GroupNorm and the 5-D GroupNorm of the TemporalConvBlock
+    c0 = gp(128, 72, B * T, 128, 1)
+    assert tup(c0.geom(B * T, 72 * 128)) == (288, 1, 288)
+    assert tup(c0.geom(B, T * 72 * 128)) == (T * 288, 1, T * 288)
+    assert c0.geom(B * T + 1, 72 * 128) is None                                   # row count mismatch
+    # 3x3 conv at 18x32 (tiles of 4 image rows, the fifth tile of a frame half empty): blocks are per frame, padding blocks hold zeros
+    c2 = gp(32, 18, B * T, 32, 4)
+    assert tup(c2.geom(B * T, 576)) == (20, 1, 20) and tup(c2.geom(B, T * 576)) == (T * 20, 1, T * 20)
+    # temporal conv (X = T*HW rows per batch element, Z = B): 5-D consumer = one slab; per-frame consumer needs HW % 32 == 0
+    t2 = gp(T * 576, 1, B, 128, 1)
+    rbz = -(-T * 576 // 128) * 4
+    assert tup(t2.geom(B, T * 576)) == (rbz, 1, rbz)
+    assert tup(t2.geom(B * T, 576)) == (rbz, T, 18)
+    t3 = gp(T * 144, 1, B, 128, 1)
+    assert t3.geom(B * T, 144) is None and t3.geom(B, T * 144) is not None        # 144 rows per frame are not whole 32-row blocks
+    # plain linear over all rows (one slab): frames and batch elements are runs of 32-row blocks when their row counts divide by 32
+    l0 = gp(B * T * 2304, 1, 1, 128, 1)
+    assert tup(l0.geom(B * T, 2304)) == (B * T * 2304 // 128 * 4, B * T, 72)
+    assert tup(l0.geom(B, T * 2304)) == (B * T * 2304 // 128 * 4, B, T * 72)
+    l3 = gp(B * T * 144, 1, 1, 128, 1)
+    assert l3.geom(B * T, 144) is None and l3.geom(B, T * 144) is None            # 3600 rows per batch element: 112.5 blocks
+    assert l3.geom(1, B * T * 144) is not None
