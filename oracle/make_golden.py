@@ -119,6 +119,82 @@ def gen_ddim():
     np.savez_compressed(os.path.join(OUT, "ddim_small.npz"), **out)
 
 
+def gen_ddim_options():
+    """The rarely used switches of the unmodified two-way sampler (ddim.py:136-325) on the toy denoiser: mask / x0 blending (with and
+    without clean_cond), a `timesteps` subset, noise_dropout, temperature, precision=16, batch size 2 with guidance rescale (per-sample
+    statistics), decode() and stochastic_encode().  Step noise comes from recorded tensors (noise_like is patched); q_sample and
+    dropout draw from the global CPU generator after torch.manual_seed -- the product must make the same draws in the same order."""
+    ref_shims.install()
+    import lvdm.models.samplers.ddim as ddim_mod
+    from lvdm.models.ddpm3d import DDPM
+    out = {}
+    shape = (1, 4, 3, 4, 6)
+
+    def setup(S, seed, base=0.5, shp=shape):
+        model = _stub_model(base)
+        model.apply_model = lambda x, t, c, **kw: toy_denoiser(x, t, c)
+        model.q_sample = lambda x0, t, noise=None: DDPM.q_sample(model, x0, t, noise)
+        g = torch.Generator().manual_seed(seed)
+        x_T = torch.randn(shp, generator=g)
+        noises = [torch.randn(shp, generator=g) for _ in range(S)]
+        cond = {"b": torch.randn(shp, generator=g), "k": torch.tensor([1.3])}
+        uncond = {"b": torch.randn(shp, generator=g), "k": torch.tensor([0.4])}
+        it = iter(noises)
+        ddim_mod.noise_like = lambda shape_, device, repeat=False: next(it)
+        return model, _cpu_sampler(model), x_T, noises, cond, uncond, g
+
+    def record(tag, x_T, noises, cond, uncond, samples, inter=None):
+        out[f"{tag}_x_T"] = x_T.numpy(); out[f"{tag}_noises"] = torch.stack(noises).numpy()
+        out[f"{tag}_cond_b"] = cond["b"].numpy(); out[f"{tag}_uncond_b"] = uncond["b"].numpy()
+        out[f"{tag}_samples"] = samples.float().numpy()
+        if inter is not None:
+            out[f"{tag}_n_inter"] = np.asarray(len(inter["x_inter"]))
+            out[f"{tag}_pred_x0_last"] = inter["pred_x0"][-1].float().numpy()
+
+    common = dict(batch_size=1, shape=shape[1:], eta=1.0, verbose=False, unconditional_guidance_scale=7.5, timestep_spacing="uniform_trailing",
+                  guidance_rescale=0.7)
+    for tag, clean in (("mask", False), ("maskclean", True)):
+        model, smp, x_T, noises, cond, uncond, g = setup(6, 21)
+        x0 = torch.randn(shape, generator=g)
+        mask = (torch.rand((1, 1, 3, 4, 6), generator=g) > 0.5).float()
+        torch.manual_seed(123)
+        samples, inter = smp.sample(S=6, conditioning=cond, x_T=x_T, unconditional_conditioning=uncond, mask=mask, x0=x0,
+                                    **(dict(clean_cond=True) if clean else {}), **common)
+        record(tag, x_T, noises, cond, uncond, samples, inter)
+        out[f"{tag}_x0"] = x0.numpy(); out[f"{tag}_mask"] = mask.numpy()
+    # `timesteps` subset: only ddim_sampling takes it (sample() does not forward it)
+    model, smp, x_T, noises, cond, uncond, g = setup(10, 22)
+    smp.make_schedule(ddim_num_steps=10, ddim_discretize="uniform_trailing", ddim_eta=1.0, verbose=False)
+    samples, inter = smp.ddim_sampling(cond, shape, x_T=x_T, timesteps=6, unconditional_guidance_scale=7.5, unconditional_conditioning=uncond,
+                                       verbose=False, guidance_rescale=0.7)
+    record("subset", x_T, noises, cond, uncond, samples, inter)
+    model, smp, x_T, noises, cond, uncond, g = setup(5, 23)
+    torch.manual_seed(321)
+    samples, inter = smp.sample(S=5, conditioning=cond, x_T=x_T, unconditional_conditioning=uncond, noise_dropout=0.25, **common)
+    record("dropout", x_T, noises, cond, uncond, samples, inter)
+    model, smp, x_T, noises, cond, uncond, g = setup(5, 24)
+    samples, inter = smp.sample(S=5, conditioning=cond, x_T=x_T, unconditional_conditioning=uncond, temperature=0.6, **common)
+    record("temp", x_T, noises, cond, uncond, samples, inter)
+    model, smp, x_T, noises, cond, uncond, g = setup(5, 25)
+    samples, inter = smp.sample(S=5, conditioning=cond, x_T=x_T, unconditional_conditioning=uncond, precision=16, **common)
+    record("prec16", x_T, noises, cond, uncond, samples, inter)
+    out["prec16_first_inter_dtype"] = np.asarray(str(inter["x_inter"][0].dtype))
+    shp2 = (2, 4, 3, 4, 6)
+    model, smp, x_T, noises, cond, uncond, g = setup(5, 26, shp=shp2)
+    samples, inter = smp.sample(S=5, conditioning=cond, x_T=x_T, unconditional_conditioning=uncond, **dict(common, batch_size=2))
+    record("batch2", x_T, noises, cond, uncond, samples, inter)
+    # decode(): the last t_start steps of the schedule from a given latent (no guidance rescale, ddim.py:288-308)
+    model, smp, x_T, noises, cond, uncond, g = setup(5, 27)
+    smp.make_schedule(ddim_num_steps=8, ddim_discretize="uniform_trailing", ddim_eta=1.0, verbose=False)
+    x_dec = smp.decode(x_T, cond, 5, unconditional_guidance_scale=7.5, unconditional_conditioning=uncond)
+    record("decode", x_T, noises, cond, uncond, x_dec)
+    # stochastic_encode(): q(x_t | x_0) with the DDIM alphas gathered by index t (ddim.py:310-325)
+    enc_noise = torch.randn(shape, generator=g)
+    out["stoch_x0"] = x_T.numpy(); out["stoch_noise"] = enc_noise.numpy()
+    out["stoch_out"] = smp.stochastic_encode(x_T, torch.tensor([3]), noise=enc_noise).numpy()
+    np.savez_compressed(os.path.join(OUT, "ddim_options.npz"), **out)
+
+
 def gen_ddim_multicond():
     """The unmodified three-way-CFG sampler (ddim_multiplecond.py) on the toy denoiser: S=5 with cfg_img=2.5 and S=8 with the
     default cfg_img (= the text scale); base 0.3 so that the un-fixed ddim_scale_arr_prev[0] matters."""
@@ -220,7 +296,7 @@ def gen_resampler():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["schedule", "ddim", "ddim_multicond", "unet", "vae", "vae_enc", "resampler"]
+    which = sys.argv[1:] or ["schedule", "ddim", "ddim_options", "ddim_multicond", "unet", "vae", "vae_enc", "resampler"]
     with torch.no_grad():
         for w in which:
             globals()["gen_" + w]()

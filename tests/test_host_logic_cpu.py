@@ -388,3 +388,96 @@ def test_groupnorm_partial_sum_geometry_of_every_producer_consumer_pair():
     l3 = gp(B * T * 144, 1, 1, 128, 1)
     assert l3.geom(B * T, 144) is None and l3.geom(B, T * 144) is None            # 3600 rows per batch element: 112.5 blocks
     assert l3.geom(1, B * T * 144) is not None
+
+
+def _toy_model(base):
+    from viewcrafter_b200.diffusion import LatentDiffusion
+    model = LatentDiffusion(dict(UNET_PARAMS, model_channels=64), None, base_scale=base).eval()
+    model.apply_model = lambda x, t, c, **kw: torch.tanh(0.7 * x * c["k"] + 0.05 * torch.sin(t.float())[:, None, None, None, None]) + 0.1 * c["b"]
+    return model
+
+
+def _with_recorded_noise(g, tag, fn):
+    """Run fn() with torch.randn (the sampler's per-step draw) replaced by the recorded tensors of the reference run."""
+    import viewcrafter_b200.ddim as mod
+    noises = iter(torch.from_numpy(g[f"{tag}_noises"]))
+    real = torch.randn
+    try:
+        mod.torch.randn = lambda shape, device=None: next(noises)
+        return fn()
+    finally:
+        mod.torch.randn = real
+
+
+@pytest.mark.parametrize("tag", ["mask", "maskclean", "subset", "dropout", "temp", "prec16", "batch2"])
+def test_sampler_options_match_the_unmodified_reference_sampler(cpu_ops, golden_dir, tag):
+    """The switches of DDIMSampler.sample / ddim_sampling beyond the ViewCrafter defaults -- mask / x0 blending (q_sample draw, clean_cond),
+    a `timesteps` subset, noise_dropout (global-RNG dropout after the step draw), temperature, precision=16 (x_T rounded to fp16), batch 2
+    with guidance rescale (per-sample statistics) -- against outputs of the unmodified reference sampler on the toy denoiser
+    (tests/golden/ddim_options.npz, oracle/make_golden.py: gen_ddim_options)."""
+    from viewcrafter_b200.ddim import DDIMSampler
+    g = np.load(os.path.join(golden_dir, "ddim_options.npz"))
+    model = _toy_model(0.5)
+    x_T = torch.from_numpy(g[f"{tag}_x_T"])
+    cond = {"k": torch.tensor([1.3]), "b": torch.from_numpy(g[f"{tag}_cond_b"])}
+    unc = {"k": torch.tensor([0.4]), "b": torch.from_numpy(g[f"{tag}_uncond_b"])}
+    smp = DDIMSampler(model)
+    common = dict(batch_size=x_T.shape[0], shape=tuple(x_T.shape[1:]), eta=1.0, verbose=False, unconditional_guidance_scale=7.5,
+                  timestep_spacing="uniform_trailing", guidance_rescale=0.7, conditioning=cond, x_T=x_T, unconditional_conditioning=unc)
+
+    def run():
+        if tag in ("mask", "maskclean"):
+            torch.manual_seed(123)
+            extra = dict(clean_cond=True) if tag == "maskclean" else {}
+            return smp.sample(S=6, mask=torch.from_numpy(g[f"{tag}_mask"]), x0=torch.from_numpy(g[f"{tag}_x0"]), **extra, **common)
+        if tag == "subset":
+            smp.make_schedule(ddim_num_steps=10, ddim_discretize="uniform_trailing", ddim_eta=1.0, verbose=False)
+            return smp.ddim_sampling(cond, tuple(x_T.shape), x_T=x_T, timesteps=6, unconditional_guidance_scale=7.5,
+                                     unconditional_conditioning=unc, verbose=False, guidance_rescale=0.7)
+        if tag == "dropout":
+            torch.manual_seed(321)
+            return smp.sample(S=5, noise_dropout=0.25, **common)
+        if tag == "temp":
+            return smp.sample(S=5, temperature=0.6, **common)
+        if tag == "prec16":
+            return smp.sample(S=5, precision=16, **common)
+        return smp.sample(S=5, **common)
+
+    out, inter = _with_recorded_noise(g, tag, run)
+    assert len(inter["x_inter"]) == int(g[f"{tag}_n_inter"])
+    np.testing.assert_allclose(out.float().numpy(), g[f"{tag}_samples"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(inter["pred_x0"][-1].float().numpy(), g[f"{tag}_pred_x0_last"], rtol=0, atol=5e-5)
+    if tag == "prec16":
+        assert str(inter["x_inter"][0].dtype) == str(g["prec16_first_inter_dtype"]) == "torch.float16" and out.dtype == torch.float32
+
+
+def test_sampler_decode_and_stochastic_encode_match_the_reference(cpu_ops, golden_dir):
+    """DDIMSampler.decode (the last t_start steps from a given latent) and stochastic_encode (q(x_t | x_0) from the DDIM tables), ddim.py:288-325."""
+    from viewcrafter_b200.ddim import DDIMSampler
+    g = np.load(os.path.join(golden_dir, "ddim_options.npz"))
+    model = _toy_model(0.5)
+    x = torch.from_numpy(g["decode_x_T"])
+    cond = {"k": torch.tensor([1.3]), "b": torch.from_numpy(g["decode_cond_b"])}
+    unc = {"k": torch.tensor([0.4]), "b": torch.from_numpy(g["decode_uncond_b"])}
+    smp = DDIMSampler(model)
+    smp.make_schedule(ddim_num_steps=8, ddim_discretize="uniform_trailing", ddim_eta=1.0, verbose=False)
+    seen = []
+    dec = _with_recorded_noise(g, "decode", lambda: smp.decode(x, cond, 5, unconditional_guidance_scale=7.5, unconditional_conditioning=unc,
+                                                                callback=seen.append))
+    assert seen == [0, 1, 2, 3, 4]
+    np.testing.assert_allclose(dec.numpy(), g["decode_samples"], rtol=0, atol=5e-5)
+    enc = smp.stochastic_encode(torch.from_numpy(g["stoch_x0"]), torch.tensor([3]), noise=torch.from_numpy(g["stoch_noise"]))
+    np.testing.assert_allclose(enc.numpy(), g["stoch_out"], rtol=0, atol=1e-6)
+
+
+def test_sampler_options_the_reference_cannot_run_either_raise(cpu_ops):
+    from viewcrafter_b200.ddim import DDIMSampler
+    smp = DDIMSampler(_toy_model(0.5))
+    smp.make_schedule(4, "uniform_trailing", 1.0, verbose=False)
+    x, c, t = torch.zeros(1, 4, 3, 4, 6), {"k": torch.tensor([1.0]), "b": torch.zeros(1, 4, 3, 4, 6)}, torch.tensor([999])
+    with pytest.raises(NotImplementedError):
+        smp.ddim_sampling(c, x.shape, ddim_use_original_steps=True)                    # ddim.py:248 reads an attribute that is never set
+    with pytest.raises(NotImplementedError):
+        smp.p_sample_ddim(x, c, t, index=3, quantize_denoised=True)                    # needs a VQ first stage
+    with pytest.raises(AssertionError):
+        smp.p_sample_ddim(x, c, t, index=3, score_corrector=object())                  # ddim.py:240 asserts the eps parameterisation

@@ -102,28 +102,33 @@ class DDIMSampler(object):
                       quantize_denoised=False, mask=None, x0=None, img_callback=None, log_every_t=100, temperature=1.,
                       noise_dropout=0., score_corrector=None, corrector_kwargs=None, unconditional_guidance_scale=1.,
                       unconditional_conditioning=None, verbose=True, precision=None, fs=None, guidance_rescale=0.0, **kwargs):
-        if ddim_use_original_steps or timesteps is not None:
-            raise NotImplementedError("viewcrafter_b200.DDIMSampler: only the DDIM sub-sequence path is implemented")
-        if precision is not None and int(precision) == 16:
-            raise NotImplementedError("viewcrafter_b200.DDIMSampler: precision=16 (fp16 latents between steps, ddim.py:155-157) is not "
-                                      "implemented; the latents stay fp32 and the U-Net computes in fp16 internally")
-        if mask is not None:
-            raise NotImplementedError("viewcrafter_b200.DDIMSampler: mask/x0 blending is not on the ViewCrafter path (mask=None)")
+        if ddim_use_original_steps:
+            # the reference's own branch reads self.ddim_sigmas_for_original_num_steps, which its make_schedule never defines (ddim.py:248)
+            raise NotImplementedError("viewcrafter_b200.DDIMSampler: ddim_use_original_steps is not implemented (it fails in the reference too)")
         device = self._device()
         b = shape[0]
         img = torch.randn(shape, device=device) if x_T is None else x_T
+        if precision is not None and int(precision) == 16:
+            img = img.to(dtype=torch.float16)               # ddim.py:154-156: only x_T is rounded; every later latent is fp32 again
         steps = self.ddim_timesteps
+        if timesteps is not None:                           # ddim.py:160-162: the first `timesteps / S` share of the sub-sequence, minus one
+            subset_end = int(min(timesteps / steps.shape[0], 1) * steps.shape[0]) - 1
+            steps = steps[:subset_end]
         total = steps.shape[0]
         intermediates = {'x_inter': [img], 'pred_x0': [img]}
-        kwargs.pop("clean_cond", None)
+        clean_cond = kwargs.pop("clean_cond", False)
         for i, step in enumerate(np.flip(steps)):
             index = total - i - 1
             ts = torch.full((b,), int(step), device=device, dtype=torch.long)
+            if mask is not None:                            # ddim.py:178-185: keep the (noised) original where mask == 1 (plain tensor math:
+                assert x0 is not None                       # not on the ViewCrafter path, which passes mask=None)
+                img_orig = x0 if clean_cond else self.model.q_sample(x0, ts)
+                img = img_orig * mask + (1. - mask) * img
             img, pred_x0 = self.p_sample_ddim(img, cond, ts, index=index, quantize_denoised=quantize_denoised,
                                               temperature=temperature, noise_dropout=noise_dropout,
                                               score_corrector=score_corrector, corrector_kwargs=corrector_kwargs,
                                               unconditional_guidance_scale=unconditional_guidance_scale,
-                                              unconditional_conditioning=unconditional_conditioning, fs=fs,
+                                              unconditional_conditioning=unconditional_conditioning, mask=mask, x0=x0, fs=fs,
                                               guidance_rescale=guidance_rescale, _step=int(step), **kwargs)
             if callback:
                 callback(i)
@@ -175,12 +180,7 @@ class DDIMSampler(object):
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None, uc_type=None,
                       conditional_guidance_scale_temporal=None, mask=None, x0=None, guidance_rescale=0.0, _step=None, **kwargs):
-        if use_original_steps or quantize_denoised or score_corrector is not None or noise_dropout > 0.:
-            raise NotImplementedError("viewcrafter_b200.DDIMSampler: option not on the ViewCrafter inference path")
-        if getattr(self.model, "parameterization", "v") != "v":
-            raise NotImplementedError("viewcrafter_b200.DDIMSampler: only the v-parameterisation is implemented")
-        if x.shape[0] != 1 and guidance_rescale > 0.0 and unconditional_conditioning is not None:
-            raise NotImplementedError("guidance rescale statistics are per sample; run batch size 1 (configs/infer_config.py:35)")
+        self._check_step_options(use_original_steps, quantize_denoised, score_corrector)
         step = int(t[0].item()) if _step is None else _step
         if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
             v_c, v_u = self.model.apply_model(x, t, c, **kwargs), None
@@ -190,11 +190,78 @@ class DDIMSampler(object):
             v_c, v_u = self._apply_both(x, t, c, unconditional_conditioning, kwargs)
         sc = self.step_scalars(index, step)
         sc["cfg_scale"], sc["guidance_rescale"] = float(unconditional_guidance_scale), float(guidance_rescale)
+        noise = self._step_noise(x, repeat_noise, temperature, noise_dropout)
+        return self._fused_update(x, v_c, v_u, noise, sc)
+
+    # -- pieces shared with the three-way sampler (ddim_multiplecond.py) ------------------------------------------------
+    def _check_step_options(self, use_original_steps, quantize_denoised, score_corrector):
+        if use_original_steps:
+            raise NotImplementedError("viewcrafter_b200.DDIMSampler: use_original_steps is not implemented (ddim.py:248 fails in the reference too)")
+        if quantize_denoised:
+            raise NotImplementedError("viewcrafter_b200.DDIMSampler: quantize_denoised needs a VQ first stage (first_stage_model.quantize); "
+                                      "AutoencoderKL has none")
+        if getattr(self.model, "parameterization", "v") != "v":
+            raise NotImplementedError("viewcrafter_b200.DDIMSampler: only the v-parameterisation is implemented")
+        if score_corrector is not None:
+            raise AssertionError("not implemented")          # ddim.py:239-241 asserts parameterization == 'eps' before using a score corrector
+
+    @staticmethod
+    def _step_noise(x, repeat_noise, temperature, noise_dropout):
+        """noise_like * temperature, then dropout (ddim.py:275-277; the scalar sigma_t is applied by the fused update, which commutes with both)."""
         shape = (1, *x.shape[1:]) if repeat_noise else x.shape
         noise = torch.randn(shape, device=x.device)                      # same draw as lvdm/common.py:31-34
         if repeat_noise:
             noise = noise.repeat(x.shape[0], *((1,) * (x.dim() - 1)))
         if temperature != 1.:
             noise = noise * temperature
-        return ops.ddim_update(x.float().contiguous(), v_c.float().contiguous(), None if v_u is None else v_u.float().contiguous(),
-                               noise.contiguous(), sc)
+        if noise_dropout > 0.:
+            noise = torch.nn.functional.dropout(noise, p=noise_dropout)
+        return noise.contiguous()
+
+    @staticmethod
+    def _fused_update(x, v_c, v_u, noise, sc, **extra):
+        """One fused update for the batch; the guidance rescale uses per-SAMPLE statistics (utils_diffusion.py:147-158: std over every axis but
+        the batch axis) while the kernel reduces over its whole input, so a batch with guidance rescale is updated sample by sample."""
+        f = lambda v: None if v is None else v.float().contiguous()
+        x, v_c, v_u = f(x), f(v_c), f(v_u)
+        extra = {k: (f(v) if isinstance(v, torch.Tensor) else v) for k, v in extra.items()}
+        if x.shape[0] == 1 or v_u is None or sc["guidance_rescale"] <= 0.0:
+            return ops.ddim_update(x, v_c, v_u, noise, sc, **extra)
+        outs = []
+        for b in range(x.shape[0]):
+            eb = {k: (v[b:b + 1].contiguous() if isinstance(v, torch.Tensor) else v) for k, v in extra.items()}
+            outs.append(ops.ddim_update(x[b:b + 1].contiguous(), v_c[b:b + 1].contiguous(), v_u[b:b + 1].contiguous(), noise[b:b + 1].contiguous(), sc, **eb))
+        return torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
+
+    # -- img2img helpers of the reference sampler (ddim.py:288-325) ------------------------------------------------------------
+    @torch.no_grad()
+    def decode(self, x_latent, cond, t_start, unconditional_guidance_scale=1.0, unconditional_conditioning=None, use_original_steps=False,
+               callback=None):
+        """The last `t_start` steps of the current schedule starting from `x_latent` (no guidance rescale, like the reference)."""
+        if use_original_steps:
+            raise NotImplementedError("viewcrafter_b200.DDIMSampler.decode: use_original_steps is not implemented")
+        timesteps = self.ddim_timesteps[:t_start]
+        total_steps = timesteps.shape[0]
+        print(f"Running DDIM Sampling with {total_steps} timesteps")
+        x_dec = x_latent
+        for i, step in enumerate(np.flip(timesteps)):
+            index = total_steps - i - 1
+            ts = torch.full((x_latent.shape[0],), int(step), device=x_latent.device, dtype=torch.long)
+            x_dec, _ = self.p_sample_ddim(x_dec, cond, ts, index=index, unconditional_guidance_scale=unconditional_guidance_scale,
+                                          unconditional_conditioning=unconditional_conditioning, _step=int(step))
+            if callback:
+                callback(i)
+        return x_dec
+
+    @torch.no_grad()
+    def stochastic_encode(self, x0, t, use_original_steps=False, noise=None):
+        """q(x_t | x_0) with the DDIM tables gathered by INDEX t (ddim.py:310-325): fast, not exactly invertible."""
+        if use_original_steps:
+            sqrt_ac, sqrt_1mac = self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod
+        else:
+            sqrt_ac = torch.sqrt(torch.as_tensor(self.ddim_alphas, dtype=torch.float32))
+            sqrt_1mac = torch.as_tensor(self.ddim_sqrt_one_minus_alphas, dtype=torch.float32)
+        if noise is None:
+            noise = torch.randn_like(x0)
+        g = lambda a: a.to(x0.device).gather(-1, t.to(x0.device)).reshape(t.shape[0], *((1,) * (x0.dim() - 1)))
+        return g(sqrt_ac) * x0 + g(sqrt_1mac) * noise

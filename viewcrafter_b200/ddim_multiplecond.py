@@ -28,10 +28,7 @@ class DDIMSampler(_TwoWaySampler):
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None, uc_type=None, cfg_img=None,
                       mask=None, x0=None, guidance_rescale=0.0, _step=None, **kwargs):
-        if use_original_steps or quantize_denoised or score_corrector is not None or noise_dropout > 0.:
-            raise NotImplementedError("viewcrafter_b200.DDIMSampler(multicond): option not on the ViewCrafter inference path")
-        if getattr(self.model, "parameterization", "v") != "v":
-            raise NotImplementedError("viewcrafter_b200.DDIMSampler(multicond): only the v-parameterisation is implemented")
+        self._check_step_options(use_original_steps, quantize_denoised, score_corrector)
         if getattr(self.model, "_cfg", None) is not None:
             raise NotImplementedError("viewcrafter_b200.DDIMSampler(multicond): the 2-way CFG rank split does not cover three branches")
         if cfg_img is None:
@@ -42,8 +39,6 @@ class DDIMSampler(_TwoWaySampler):
         if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
             v_c = self.model.apply_model(x, t, c, **kwargs)
         else:
-            if x.shape[0] != 1 and guidance_rescale > 0.0:
-                raise NotImplementedError("guidance rescale statistics are per sample; run batch size 1 (configs/infer_config.py:35)")
             if uc_img is None:
                 raise ValueError("three-way CFG needs unconditional_conditioning_img_nonetext (image_guided_synthesis only builds it "
                                  "when cfg_img != 1.0, utils/diffusion_utils.py:157-163)")
@@ -51,11 +46,5 @@ class DDIMSampler(_TwoWaySampler):
             v_i = self.model.apply_model(x, t, uc_img, **kwargs)
         sc = self.step_scalars(index, step)
         sc["cfg_scale"], sc["guidance_rescale"] = float(unconditional_guidance_scale), float(guidance_rescale)
-        shape = (1, *x.shape[1:]) if repeat_noise else x.shape
-        noise = torch.randn(shape, device=x.device)                          # same draw as lvdm/common.py:31-34
-        if repeat_noise:
-            noise = noise.repeat(x.shape[0], *((1,) * (x.dim() - 1)))
-        if temperature != 1.:
-            noise = noise * temperature
-        f = lambda v: None if v is None else v.float().contiguous()
-        return ops.ddim_update(f(x), f(v_c), f(v_u), noise.contiguous(), sc, v_uncond_img=f(v_i), cfg_img=float(cfg_img))
+        noise = self._step_noise(x, repeat_noise, temperature, noise_dropout)
+        return self._fused_update(x, v_c, v_u, noise, sc, v_uncond_img=v_i, cfg_img=float(cfg_img))

@@ -64,6 +64,11 @@ class LatentDiffusion(nn.Module):
     def _gather(a, t, x):
         return a.gather(-1, t).reshape(t.shape[0], *((1,) * (x.dim() - 1)))
 
+    def q_sample(self, x_start, t, noise=None):
+        """Forward diffusion to step t (ddpm3d.py:305-308); the sampler's mask / x0 blending calls it (ddim.py:182)."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return self._gather(self.sqrt_alphas_cumprod, t, x_start) * x_start + self._gather(self.sqrt_one_minus_alphas_cumprod, t, x_start) * noise
+
     def predict_start_from_z_and_v(self, x_t, t, v):
         return self._gather(self.sqrt_alphas_cumprod, t, x_t) * x_t - self._gather(self.sqrt_one_minus_alphas_cumprod, t, x_t) * v
 
