@@ -117,9 +117,10 @@ def _cfg_worker(rank, world, port, q):
     mpx.undo()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_cfg_split_times_frame_sharding_matches_single_process(world):
-    """world 2 = pure CFG split (cond on rank 0, uncond on rank 1); world 4 = CFG split x 2-way frame sharding."""
+    """world 2 = pure CFG split (cond on rank 0, uncond on rank 1); world 4 / 8 = CFG split x 2- / 4-way frame sharding (the layouts
+    bench.py --gpus 4 / 8 runs: two frame groups, pair groups for the CFG exchange)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
